@@ -1,0 +1,276 @@
+"""ctypes binding of the CPU oracle (oracle/halo2_oracle.c). TEST INFRASTRUCTURE ONLY.
+
+Allowed importers: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs.
+The product package (spectre_b200/) must never import this module.
+
+All field elements cross this boundary as numpy uint64 arrays of shape (..., 4): the Montgomery limbs
+halo2curves keeps in memory (SURVEY.md 8b "Data conventions"). Helpers convert to / from Python ints.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libhalo2_oracle.so")
+
+R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+P_MOD = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+MONT_R = 1 << 256
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "halo2_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "clean", "all"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.orc_init()
+        _lib.orc_domain_new.restype = ctypes.c_void_p
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def default_threads():
+    return os.cpu_count() or 1
+
+
+# ---- int <-> Montgomery limb conversion (pure Python, independent of the C code) ----------------
+def to_mont(vals, mod):
+    """list/iterable of Python ints -> (n,4) uint64 Montgomery limbs."""
+    vals = list(vals)
+    out = np.empty((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        m = (v % mod) * MONT_R % mod
+        for j in range(4):
+            out[i, j] = (m >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+def from_mont(arr, mod):
+    arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+    rinv = pow(MONT_R, -1, mod)
+    out = []
+    for row in arr:
+        m = int(row[0]) | (int(row[1]) << 64) | (int(row[2]) << 128) | (int(row[3]) << 192)
+        out.append(m * rinv % mod)
+    return out
+
+
+def fr(vals):
+    return to_mont(vals, R_MOD)
+
+
+def fq(vals):
+    return to_mont(vals, P_MOD)
+
+
+def fr_ints(arr):
+    return from_mont(arr, R_MOD)
+
+
+def fq_ints(arr):
+    return from_mont(arr, P_MOD)
+
+
+def affine_ints(arr):
+    """(n,8) uint64 G1Affine -> list of (x,y) ints; identity -> (0,0)."""
+    arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 8)
+    xs = fq_ints(arr[:, :4]); ys = fq_ints(arr[:, 4:])
+    return list(zip(xs, ys))
+
+
+# ---- wrapped entry points --------------------------------------------------------------------------
+def fr_random_chacha(n, seed):
+    """n Fr elements as `Fr::random(&mut ChaCha20Rng::from_seed(seed))` would draw them. seed: int or 32 bytes."""
+    if isinstance(seed, int):
+        seed = seed.to_bytes(32, "little")
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().orc_fr_random_chacha(_p(out), ctypes.c_size_t(n), ctypes.c_char_p(seed))
+    return out
+
+
+def best_fft(a, omega, log_n, threads=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    omega = np.ascontiguousarray(omega, dtype=np.uint64)
+    assert a.shape == (1 << log_n, 4)
+    lib().orc_best_fft(_p(a), _p(omega), ctypes.c_uint32(log_n), ctypes.c_int(threads or default_threads()))
+    return a
+
+
+def best_multiexp(coeffs, bases, threads=None):
+    """-> (12,) uint64 Jacobian point."""
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64); bases = np.ascontiguousarray(bases, dtype=np.uint64)
+    n = coeffs.shape[0]
+    assert bases.shape[0] == n, "best_multiexp: coeffs.len() != bases.len()"
+    out = np.empty(12, dtype=np.uint64)
+    lib().orc_best_multiexp(_p(coeffs), _p(bases), ctypes.c_size_t(n), ctypes.c_int(threads or default_threads()), _p(out))
+    return out
+
+
+def g1_to_affine(j):
+    j = np.ascontiguousarray(j, dtype=np.uint64)
+    out = np.empty(8, dtype=np.uint64)
+    lib().orc_g1_to_affine(_p(out), _p(j))
+    return out
+
+
+def g1_generator():
+    out = np.empty(8, dtype=np.uint64)
+    lib().orc_g1_generator(_p(out))
+    return out
+
+
+def g1_mul(base, scalar):
+    base = np.ascontiguousarray(base, dtype=np.uint64); scalar = np.ascontiguousarray(scalar, dtype=np.uint64)
+    out = np.empty(12, dtype=np.uint64)
+    lib().orc_g1_mul(_p(out), _p(base), _p(scalar))
+    return out
+
+
+def g1_add(a, b):
+    out = np.empty(12, dtype=np.uint64)
+    lib().orc_g1_add(_p(out), _p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)))
+    return out
+
+
+def g1_on_curve(p):
+    return bool(lib().orc_g1_on_curve(_p(np.ascontiguousarray(p, dtype=np.uint64))))
+
+
+def g1_fixed_base_mul(scalars, threads=None):
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    n = scalars.shape[0]
+    out = np.empty((n, 8), dtype=np.uint64)
+    lib().orc_g1_fixed_base_mul(_p(scalars), ctypes.c_size_t(n), ctypes.c_int(threads or default_threads()), _p(out))
+    return out
+
+
+def srs_tau():
+    out = np.empty(4, dtype=np.uint64)
+    lib().orc_srs_tau(_p(out))
+    return out
+
+
+def srs_g(k, start, count, threads=None):
+    out = np.empty((count, 8), dtype=np.uint64)
+    lib().orc_srs_g(ctypes.c_uint32(k), ctypes.c_size_t(start), ctypes.c_size_t(count), ctypes.c_int(threads or default_threads()), _p(out))
+    return out
+
+
+def srs_g_lagrange(k, start, count, threads=None):
+    out = np.empty((count, 8), dtype=np.uint64)
+    lib().orc_srs_g_lagrange(ctypes.c_uint32(k), ctypes.c_size_t(start), ctypes.c_size_t(count), ctypes.c_int(threads or default_threads()), _p(out))
+    return out
+
+
+def srs_s_g2():
+    out = np.empty((4, 4), dtype=np.uint64)
+    lib().orc_srs_s_g2(_p(out))
+    return out
+
+
+def commit_known_tau(coeffs):
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    out = np.empty(8, dtype=np.uint64)
+    lib().orc_commit_known_tau(_p(coeffs), ctypes.c_size_t(coeffs.shape[0]), _p(out))
+    return out
+
+
+def commit_lagrange_known_tau(k, evals):
+    evals = np.ascontiguousarray(evals, dtype=np.uint64)
+    out = np.empty(8, dtype=np.uint64)
+    lib().orc_commit_lagrange_known_tau(ctypes.c_uint32(k), _p(evals), ctypes.c_size_t(evals.shape[0]), _p(out))
+    return out
+
+
+class Domain:
+    """EvaluationDomain::new(j, k) restated (oracle side)."""
+
+    def __init__(self, j, k):
+        self.j, self.k = j, k
+        self.h = ctypes.c_void_p(lib().orc_domain_new(ctypes.c_uint32(j), ctypes.c_uint32(k)))
+        ek = ctypes.c_uint32(0)
+        self.omega = np.empty(4, dtype=np.uint64); self.extended_omega = np.empty(4, dtype=np.uint64)
+        consts = np.empty((6, 4), dtype=np.uint64)
+        lib().orc_domain_describe(self.h, ctypes.byref(ek), _p(self.omega), _p(self.extended_omega), _p(consts), None)
+        self.extended_k = ek.value
+        (self.omega_inv, self.extended_omega_inv, self.g_coset, self.g_coset_inv,
+         self.ifft_divisor, self.extended_ifft_divisor) = [consts[i].copy() for i in range(6)]
+        self.t_evaluations = np.empty((1 << (self.extended_k - k), 4), dtype=np.uint64)
+        lib().orc_domain_describe(self.h, ctypes.byref(ek), _p(self.omega), _p(self.extended_omega), _p(consts), _p(self.t_evaluations))
+
+    def __del__(self):
+        try:
+            lib().orc_domain_free(self.h)
+        except Exception:
+            pass
+
+    def lagrange_to_coeff(self, a, threads=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+        lib().orc_lagrange_to_coeff(self.h, _p(a), ctypes.c_int(threads or default_threads()))
+        return a
+
+    def coeff_to_extended(self, a, threads=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty((1 << self.extended_k, 4), dtype=np.uint64)
+        lib().orc_coeff_to_extended(self.h, _p(a), _p(out), ctypes.c_int(threads or default_threads()))
+        return out
+
+    def extended_to_coeff(self, a, threads=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+        out = np.empty(((1 << self.k) * (self.j - 1), 4), dtype=np.uint64)
+        lib().orc_extended_to_coeff(self.h, _p(a), _p(out), ctypes.c_int(threads or default_threads()))
+        return out
+
+    def divide_by_vanishing_poly(self, a):
+        a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+        lib().orc_divide_by_vanishing_poly(self.h, _p(a))
+        return a
+
+
+def eval_polynomial(poly, point):
+    poly = np.ascontiguousarray(poly, dtype=np.uint64)
+    out = np.empty(4, dtype=np.uint64)
+    lib().orc_eval_polynomial(_p(out), _p(poly), ctypes.c_size_t(poly.shape[0]), _p(np.ascontiguousarray(point, dtype=np.uint64)))
+    return out
+
+
+def kate_division(a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    q = np.empty((a.shape[0] - 1, 4), dtype=np.uint64)
+    lib().orc_kate_division(_p(q), _p(a), ctypes.c_size_t(a.shape[0]), _p(np.ascontiguousarray(b, dtype=np.uint64)))
+    return q
+
+
+def batch_invert(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    lib().orc_batch_invert(_p(a), ctypes.c_size_t(a.shape[0]))
+    return a
+
+
+def fr_binop(name, a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64)
+    out = np.empty(4, dtype=np.uint64)
+    getattr(lib(), "orc_" + name)(_p(out), _p(a), _p(b))
+    return out
+
+
+def fr_seq(n):
+    """Montgomery limbs of 0, 1, ..., n-1 (range-table column), built by repeated addition in the oracle."""
+    out = np.zeros((n, 4), dtype=np.uint64)
+    lib().orc_fr_seq(_p(out), ctypes.c_size_t(n))
+    return out
