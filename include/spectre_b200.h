@@ -1,0 +1,151 @@
+/*
+ * spectre_b200.h -- C ABI of libspectre_b200.so, the B200-native backend for the Halo2/KZG create_proof
+ * hot path of ChainSafe/Spectre (MSM over BN254 G1, NTT over Fr, EvaluationDomain and batch polynomial ops).
+ *
+ * This is the drop-in boundary of SURVEY.md section 8b: exactly what a Rust `extern "C"` block in a
+ * `[patch]`-ed halo2_proofs would bind (INTEGRATION.md shows that block). Spectre itself reaches these
+ * routines only through snark_verifier_sdk::{gen_pk, gen_proof_shplonk, gen_snark_shplonk,
+ * gen_evm_proof_shplonk} at lightclient-circuits/src/util/circuit.rs:131,158,177,211,263; the functions
+ * replaced live in the un-vendored crate halo2_proofs ([UPSTREAM], reference Cargo.toml:44-48).
+ *
+ * Data conventions (identical to halo2curves' in-memory types, so `&[Fr]` / `&[G1Affine]` pass as pointers):
+ *   spb_fr / spb_fq : 4 x u64 little-endian limbs of a*2^256 mod m (Montgomery form), 32 bytes
+ *   spb_g1_affine   : {x, y}, 64 bytes, identity encoded as x = y = 0
+ *   spb_g1          : Jacobian {x, y, z}, 96 bytes, affine = (x/z^2, y/z^3), identity z = 0
+ * Pointers are HOST pointers unless a function name ends in `_dev`; the library never keeps a caller pointer
+ * after returning and never frees caller memory. All functions are thread-safe (one lock per context).
+ * Return value: 0 = ok, negative = error (spb_last_error gives the text); nothing aborts or throws.
+ * There is no CPU fallback inside the library: without a usable CUDA device spb_init fails.
+ */
+#ifndef SPECTRE_B200_H
+#define SPECTRE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct { uint64_t l[4]; } spb_fr;
+typedef struct { uint64_t l[4]; } spb_fq;
+typedef struct { spb_fq x, y; } spb_g1_affine;
+typedef struct { spb_fq x, y, z; } spb_g1;
+
+typedef struct spb_ctx spb_ctx;
+typedef struct spb_srs spb_srs;       /* device-resident ParamsKZG: g and g_lagrange */
+typedef struct spb_domain spb_domain; /* EvaluationDomain<Fr> constants */
+
+#define SPB_OK 0
+#define SPB_ERR_CUDA (-1)
+#define SPB_ERR_ARG (-2)
+#define SPB_ERR_OOM (-3)
+#define SPB_ERR_STATE (-4)
+
+#define SPB_BASIS_G 0          /* monomial basis  (Params::commit)          */
+#define SPB_BASIS_G_LAGRANGE 1 /* Lagrange basis  (Params::commit_lagrange) */
+
+/* ---- context -------------------------------------------------------------------------------------------- */
+/* One context drives n_dev devices of this process (device_ids == NULL: devices 0..n_dev-1). With n_dev > 1
+ * an MSM is sharded by point range over the devices and the partial sums are folded on the host; NTTs run
+ * on the first device. Multi-process use (one context per rank, torch.distributed / NCCL between ranks) is
+ * what bench.py does. Returns NULL on failure (no CUDA device, bad id). */
+spb_ctx* spb_init(const int* device_ids, int n_dev);
+void spb_shutdown(spb_ctx* ctx);
+const char* spb_last_error(spb_ctx* ctx);
+/* kernels launched by this context so far, and device milliseconds of the last timed call (CUDA events on the
+ * context's own stream, taken inside every spb_msm* / spb_ntt* call). */
+uint64_t spb_kernel_launches(spb_ctx* ctx);
+float spb_last_device_ms(spb_ctx* ctx);
+int spb_device_count(void);
+/* pin / unpin a caller buffer so host<->device copies run at full PCIe rate (optional) */
+int spb_host_register(spb_ctx* ctx, void* ptr, size_t bytes);
+int spb_host_unregister(spb_ctx* ctx, void* ptr);
+
+/* ---- ParamsKZG ------------------------------------------------------------------------------------------- */
+/* Replaces holding ParamsKZG<Bn256>{g, g_lagrange} on the host ([UPSTREAM] halo2_proofs/src/poly/kzg/commitment.rs;
+ * created by the reference through gen_srs at prover/src/cli.rs:48,64,87,113,141,165,191,218 and
+ * prover/src/prover.rs:55). Copies both bases (2^k points each) to the device(s) once; either may be NULL. */
+int spb_srs_upload(spb_ctx* ctx, uint32_t k, const spb_g1_affine* g, const spb_g1_affine* g_lagrange, spb_srs** out);
+/* ParamsKZG::setup(k, rng) with the secret drawn by the caller: g[i] = s^i G1, g_lagrange[i] = L_i(s) G1,
+ * computed on the device (fixed-base scalar multiplication) -- what halo2-base's gen_srs(k) produces when
+ * `s` is the first Fr::random of ChaCha20Rng::from_seed([0;32]). */
+int spb_srs_setup(spb_ctx* ctx, uint32_t k, const spb_fr* s, spb_srs** out);
+/* copy a range of a resident basis back to the host (ParamsKZG::get_g / write) */
+int spb_srs_download(spb_ctx* ctx, const spb_srs* srs, int basis, size_t start, size_t count, spb_g1_affine* out);
+void spb_srs_free(spb_ctx* ctx, spb_srs* srs);
+
+/* ---- MSM -------------------------------------------------------------------------------------------------- */
+/* best_multiexp(coeffs, bases) -> G1 ([UPSTREAM] halo2_proofs/src/arithmetic.rs): sum_i scalars[i] * bases[i].
+ * `out` is the Jacobian point normalised to z = 1 (identity: x = 0, y = 1, z = 0). */
+int spb_msm_raw(spb_ctx* ctx, const spb_fr* scalars, const spb_g1_affine* bases, size_t n, spb_g1* out);
+/* Params::commit / commit_lagrange: MSM of `n` scalars against the first n points of a resident basis. */
+int spb_msm(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* scalars, size_t n, spb_g1* out);
+/* same with the scalars already resident on device 0 of the context */
+int spb_msm_dev(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* d_scalars, size_t n, spb_g1* out);
+/* number of G1 additions (mixed + full) the last MSM executed on the device(s) */
+uint64_t spb_last_msm_adds(spb_ctx* ctx);
+
+/* ---- NTT -------------------------------------------------------------------------------------------------- */
+/* best_fft(a, omega, log_n) ([UPSTREAM] halo2_proofs/src/arithmetic.rs): in place, natural order,
+ * a[i] <- sum_j a[j] omega^(ij), no scaling. */
+int spb_ntt(spb_ctx* ctx, spb_fr* a, uint32_t log_n, const spb_fr* omega);
+int spb_ntt_dev(spb_ctx* ctx, spb_fr* d_a, uint32_t log_n, const spb_fr* omega);
+
+/* ---- EvaluationDomain ([UPSTREAM] halo2_proofs/src/poly/domain.rs) -------------------------------------- */
+/* EvaluationDomain::new(j, k) */
+int spb_domain_new(spb_ctx* ctx, uint32_t j, uint32_t k, spb_domain** out);
+void spb_domain_free(spb_ctx* ctx, spb_domain* d);
+uint32_t spb_domain_extended_k(const spb_domain* d);
+/* omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv, ifft_divisor, extended_ifft_divisor */
+void spb_domain_constants(const spb_domain* d, spb_fr out[8]);
+/* lagrange_to_coeff: a (2^k values) in place */
+int spb_lagrange_to_coeff(spb_ctx* ctx, const spb_domain* d, spb_fr* a);
+/* coeff_to_lagrange: a (2^k values) in place (plain forward transform) */
+int spb_coeff_to_lagrange(spb_ctx* ctx, const spb_domain* d, spb_fr* a);
+/* coeff_to_extended: in = 2^k coefficients, out = 2^extended_k evaluations on the zeta-coset */
+int spb_coeff_to_extended(spb_ctx* ctx, const spb_domain* d, const spb_fr* in, spb_fr* out);
+/* extended_to_coeff: in = 2^extended_k evaluations, out = 2^k * (j-1) coefficients */
+int spb_extended_to_coeff(spb_ctx* ctx, const spb_domain* d, const spb_fr* in, spb_fr* out);
+/* divide_by_vanishing_poly: a (2^extended_k) in place, a[i] *= t_evaluations[i mod 2^(extended_k-k)] */
+int spb_divide_by_vanishing(spb_ctx* ctx, const spb_domain* d, spb_fr* a);
+/* device-resident variants (pointers on device 0 of the context) */
+int spb_lagrange_to_coeff_dev(spb_ctx* ctx, const spb_domain* d, spb_fr* d_a);
+int spb_coeff_to_extended_dev(spb_ctx* ctx, const spb_domain* d, const spb_fr* d_in, spb_fr* d_out);
+int spb_extended_to_coeff_dev(spb_ctx* ctx, const spb_domain* d, const spb_fr* d_in, spb_fr* d_out);
+int spb_divide_by_vanishing_dev(spb_ctx* ctx, const spb_domain* d, spb_fr* d_a);
+
+/* ---- batch polynomial arithmetic ([UPSTREAM] halo2_proofs/src/arithmetic.rs, ff::BatchInvert) ---------- */
+/* a[i] <- a[i]^-1, zeros stay zero (BatchInvert semantics) */
+int spb_batch_invert(spb_ctx* ctx, spb_fr* a, size_t n);
+/* eval_polynomial(poly, point) */
+int spb_eval_polynomial(spb_ctx* ctx, const spb_fr* poly, size_t n, const spb_fr* point, spb_fr* out);
+/* kate_division(a, b): q (n-1 values) = a(X) / (X - b), remainder dropped */
+int spb_kate_division(spb_ctx* ctx, const spb_fr* a, size_t n, const spb_fr* b, spb_fr* q);
+/* running product z[0] = 1, z[i+1] = z[i] * a[i]  (the permutation / lookup grand-product scan), n values in, n out */
+int spb_grand_product(spb_ctx* ctx, const spb_fr* a, size_t n, spb_fr* z);
+/* out[i] = a[i] * b[i] + c * d[i]  style helpers are built by the caller from: */
+int spb_vec_mul(spb_ctx* ctx, spb_fr* a, const spb_fr* b, size_t n);                 /* a[i] *= b[i]        */
+int spb_vec_axpy(spb_ctx* ctx, spb_fr* y, const spb_fr* alpha, const spb_fr* x, size_t n); /* y[i] += alpha*x[i] */
+int spb_vec_scale(spb_ctx* ctx, spb_fr* a, const spb_fr* alpha, size_t n);           /* a[i] *= alpha       */
+
+/* ---- test / bench utilities -------------------------------------------------------------------------------- */
+/* out[i] = scalars[i] * G1 (affine), computed on the device */
+int spb_g1_fixed_base_mul(spb_ctx* ctx, const spb_fr* scalars, size_t n, spb_g1_affine* out);
+/* Elementwise device arithmetic exposed for parity tests of the field/curve layer: op 0 mul, 1 add, 2 sub;
+ * field 0 = Fr, 1 = Fq. */
+int spb_test_field_op(spb_ctx* ctx, int field, int op, const spb_fr* a, const spb_fr* b, spb_fr* out, size_t n);
+/* modular-multiply throughput microbenchmark: `iters` dependent products per thread over `threads` threads;
+ * returns device milliseconds in *ms. */
+int spb_bench_modmul(spb_ctx* ctx, int field, uint32_t threads, uint32_t iters, int ilp, float* ms);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,366 @@
+// C ABI of libspectre_b200.so: context, NTT, EvaluationDomain. (MSM entry points are in msm.cu, batch
+// polynomial ops in poly.cu.) See include/spectre_b200.h for the contract of every function.
+#include "common.cuh"
+#include "ntt.cuh"
+#include "../../include/spectre_b200.h"
+#include <stdarg.h>
+#include <string.h>
+
+using namespace spb;
+
+static_assert(sizeof(spb_fr) == sizeof(Fr) && sizeof(spb_g1_affine) == sizeof(G1Affine) && sizeof(spb_g1) == sizeof(G1Jac),
+              "C ABI structs must match the device structs byte for byte");
+
+namespace spb {
+
+int set_error(spb_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (ctx) ctx->last_error = buf;
+  return code;
+}
+
+void* slot(spb_ctx* ctx, DeviceState& d, const char* name, size_t bytes) {
+  DevBuf& b = d.slots[name];
+  if (b.cap >= bytes && b.ptr) return b.ptr;
+  if (b.ptr) { cudaStreamSynchronize(d.stream); cudaFree(b.ptr); b.ptr = nullptr; b.cap = 0; }
+  size_t want = bytes + bytes / 8;  // a little headroom so growing sizes do not realloc every call
+  cudaError_t e = cudaMalloc(&b.ptr, want);
+  if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.ptr, want); }
+  if (e != cudaSuccess) { set_error(ctx, SPB_ERR_OOM, "cudaMalloc(%zu) for slot %s: %s", want, name, cudaGetErrorString(e)); b.ptr = nullptr; return nullptr; }
+  b.cap = want;
+  return b.ptr;
+}
+
+}  // namespace spb
+
+struct spb_domain {
+  uint32_t j, k, extended_k, quotient_poly_degree;
+  Fr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv, ifft_divisor, extended_ifft_divisor;
+  uint32_t t_len;
+  Fr* d_t_evaluations;  // device, t_len values
+  int device;
+};
+
+template <class P>
+__global__ void field_op_kernel(int op, const Fp<P>* a, const Fp<P>* b, Fp<P>* o, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp<P> x = a[i], y = b[i], r;
+  if (op == 0) r = fp_mul(x, y);
+  else if (op == 1) r = fp_add(x, y);
+  else r = fp_sub(x, y);
+  o[i] = r;
+}
+
+// ILP independent multiply chains per thread; result folded and written so nothing is optimised away
+template <class P, int ILP>
+__global__ void modmul_bench_kernel(Fp<P>* out, uint32_t iters) {
+  Fp<P> x[ILP], y;
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < ILP; j++) { x[j] = fp_one<P>(); x[j].l[0] ^= tid * 2654435761u + j; x[j].l[7] &= 0x0fffffffu; }
+  y = x[0]; y.l[1] ^= 0x9e3779b9u;
+  for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < ILP; j++) x[j] = fp_mul(x[j], y);
+  }
+  Fp<P> acc = x[0];
+#pragma unroll
+  for (int j = 1; j < ILP; j++) acc = fp_add(acc, x[j]);
+  out[tid] = acc;
+}
+
+extern "C" {
+
+int spb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+spb_ctx* spb_init(const int* device_ids, int n_dev) {
+  int avail = spb_device_count();
+  if (n_dev <= 0) n_dev = 1;
+  if (avail <= 0) { fprintf(stderr, "spectre_b200: no CUDA device visible; this library has no CPU fallback\n"); return nullptr; }
+  spb_ctx* ctx = new spb_ctx();
+  for (int i = 0; i < n_dev; i++) {
+    int id = device_ids ? device_ids[i] : i;
+    if (id < 0 || id >= avail) { fprintf(stderr, "spectre_b200: device id %d out of range (have %d)\n", id, avail); delete ctx; return nullptr; }
+    DeviceState d; d.device = id;
+    if (cudaSetDevice(id) != cudaSuccess) { delete ctx; return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, id) != cudaSuccess) { delete ctx; return nullptr; }
+    d.sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
+    cudaEventCreate(&d.ev0); cudaEventCreate(&d.ev1);
+    d.pinned_cap = 1 << 20;
+    if (cudaMallocHost(&d.pinned, d.pinned_cap) != cudaSuccess) { delete ctx; return nullptr; }
+    ctx->dev.push_back(d);
+  }
+  return ctx;
+}
+
+void spb_shutdown(spb_ctx* ctx) {
+  if (!ctx) return;
+  for (auto& d : ctx->dev) {
+    cudaSetDevice(d.device);
+    cudaStreamSynchronize(d.stream);
+    for (auto& kv : d.slots) if (kv.second.ptr) cudaFree(kv.second.ptr);
+    for (auto& t : d.ntt_tables) { cudaFree(t.tw_lo); cudaFree(t.tw_hi); }
+    if (d.pinned) cudaFreeHost(d.pinned);
+    cudaEventDestroy(d.ev0); cudaEventDestroy(d.ev1);
+    cudaStreamDestroy(d.stream);
+  }
+  delete ctx;
+}
+
+const char* spb_last_error(spb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+uint64_t spb_kernel_launches(spb_ctx* ctx) { return ctx ? ctx->n_kernel_launches : 0; }
+float spb_last_device_ms(spb_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
+
+int spb_host_register(spb_ctx* ctx, void* ptr, size_t bytes) {
+  SPB_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int spb_host_unregister(spb_ctx* ctx, void* ptr) {
+  SPB_CUDA(ctx, cudaHostUnregister(ptr));
+  return 0;
+}
+
+// ---- NTT ---------------------------------------------------------------------------------------------------
+static int ntt_timed(spb_ctx* ctx, DeviceState& d, const Fr* src, Fr* dst, uint32_t k, const Fr& omega, const NttOpts& o) {
+  SPB_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+  SPB_TRY(ntt_device(ctx, d, src, dst, k, omega, o));
+  SPB_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  SPB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, d.ev0, d.ev1));
+  return 0;
+}
+
+int spb_ntt_dev(spb_ctx* ctx, spb_fr* d_a, uint32_t log_n, const spb_fr* omega) {
+  if (!ctx || !d_a || !omega) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  Fr w; memcpy(&w, omega, 32);
+  return ntt_timed(ctx, d, (const Fr*)d_a, (Fr*)d_a, log_n, w, NttOpts());
+}
+
+// host-buffer transform through a device staging slot
+static int ntt_host(spb_ctx* ctx, const Fr* in, size_t n_in_copy, Fr* out, size_t n_out_copy, uint32_t k, const Fr& omega, const NttOpts& o) {
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  size_t n = (size_t)1 << k;
+  Fr* buf = (Fr*)slot(ctx, d, "ntt_io", n * sizeof(Fr));
+  if (!buf) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(buf, in, n_in_copy * sizeof(Fr), cudaMemcpyHostToDevice, d.stream));
+  SPB_TRY(ntt_timed(ctx, d, buf, buf, k, omega, o));
+  SPB_CUDA(ctx, cudaMemcpyAsync(out, buf, n_out_copy * sizeof(Fr), cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_ntt(spb_ctx* ctx, spb_fr* a, uint32_t log_n, const spb_fr* omega) {
+  if (!ctx || !a || !omega) return SPB_ERR_ARG;
+  if (log_n > 28) return set_error(ctx, SPB_ERR_ARG, "spb_ntt: log_n %u > 28", log_n);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Fr w; memcpy(&w, omega, 32);
+  size_t n = (size_t)1 << log_n;
+  return ntt_host(ctx, (const Fr*)a, n, (Fr*)a, n, log_n, w, NttOpts());
+}
+
+// ---- EvaluationDomain --------------------------------------------------------------------------------------
+__global__ void vanishing_table_kernel(Fr* t, Fr cur0, Fr step, uint32_t len) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  Fr cur = fp_mul(cur0, fp_pow_u64(step, i));
+  t[i] = fp_inv(fp_sub(cur, fp_one<FrParams>()));
+}
+__global__ void mul_periodic_kernel(Fr* a, const Fr* t, uint64_t n, uint32_t mask) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr v = ntt_ld_stream(a + i);
+  ntt_stg(a + i, fp_mul(v, ntt_ldg(t + (i & mask))));
+}
+
+int spb_domain_new(spb_ctx* ctx, uint32_t j, uint32_t k, spb_domain** out) {
+  if (!ctx || !out || j < 2) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  spb_domain* dm = new spb_domain();
+  dm->j = j; dm->k = k; dm->quotient_poly_degree = j - 1;
+  uint64_t n = 1ull << k;
+  uint32_t ek = k;
+  while ((1ull << ek) < n * dm->quotient_poly_degree) ek++;
+  if (ek > 28) { delete dm; return set_error(ctx, SPB_ERR_ARG, "domain: extended_k %u > 28", ek); }
+  dm->extended_k = ek;
+  Fr w; { constexpr uint32_t v[8] = SPB_FR_ROOT_OF_UNITY_MONT; for (int i = 0; i < 8; i++) w.l[i] = v[i]; }
+  for (uint32_t i = ek; i < 28; i++) w = fp_sqr(w);
+  dm->extended_omega = w; dm->extended_omega_inv = fp_inv(w);
+  for (uint32_t i = k; i < ek; i++) w = fp_sqr(w);
+  dm->omega = w; dm->omega_inv = fp_inv(w);
+  { constexpr uint32_t v[8] = SPB_FR_ZETA_MONT; for (int i = 0; i < 8; i++) dm->g_coset.l[i] = v[i]; }
+  dm->g_coset_inv = fp_sqr(dm->g_coset);
+  dm->ifft_divisor = fp_inv(fr_from_u64(n));
+  dm->extended_ifft_divisor = fp_inv(fr_from_u64(1ull << ek));
+  dm->t_len = 1u << (ek - k);
+  DeviceState& d = ctx->dev[0];
+  dm->device = d.device;
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  SPB_CUDA(ctx, cudaMalloc(&dm->d_t_evaluations, dm->t_len * sizeof(Fr)));
+  Fr cur0 = fp_pow_u64(dm->g_coset, n), step = fp_pow_u64(dm->extended_omega, n);
+  vanishing_table_kernel<<<(dm->t_len + 63) / 64, 64, 0, d.stream>>>(dm->d_t_evaluations, cur0, step, dm->t_len);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  *out = dm;
+  return 0;
+}
+
+void spb_domain_free(spb_ctx* ctx, spb_domain* dm) {
+  if (!dm) return;
+  if (ctx) { std::lock_guard<std::mutex> lk(ctx->mu); cudaSetDevice(dm->device); cudaFree(dm->d_t_evaluations); }
+  delete dm;
+}
+uint32_t spb_domain_extended_k(const spb_domain* d) { return d ? d->extended_k : 0; }
+void spb_domain_constants(const spb_domain* d, spb_fr out[8]) {
+  const Fr* src[8] = {&d->omega, &d->omega_inv, &d->extended_omega, &d->extended_omega_inv, &d->g_coset, &d->g_coset_inv, &d->ifft_divisor, &d->extended_ifft_divisor};
+  for (int i = 0; i < 8; i++) memcpy(&out[i], src[i], 32);
+}
+
+static void l2c_opts(const spb_domain* dm, Fr post[3], NttOpts& o) { for (int i = 0; i < 3; i++) post[i] = dm->ifft_divisor; o.post3 = post; }
+static void c2e_opts(const spb_domain* dm, Fr pre[3], NttOpts& o) {
+  pre[0] = fp_one<FrParams>(); pre[1] = dm->g_coset; pre[2] = dm->g_coset_inv;
+  o.pre3 = pre; o.n_in = 1ull << dm->k;
+}
+static void e2c_opts(const spb_domain* dm, Fr post[3], NttOpts& o) {
+  post[0] = dm->extended_ifft_divisor;
+  post[1] = fp_mul(dm->extended_ifft_divisor, dm->g_coset_inv);
+  post[2] = fp_mul(dm->extended_ifft_divisor, dm->g_coset);
+  o.post3 = post; o.n_out = (1ull << dm->k) * dm->quotient_poly_degree;
+}
+
+int spb_lagrange_to_coeff(spb_ctx* ctx, const spb_domain* dm, spb_fr* a) {
+  if (!ctx || !dm || !a) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Fr post[3]; NttOpts o; l2c_opts(dm, post, o);
+  size_t n = (size_t)1 << dm->k;
+  return ntt_host(ctx, (const Fr*)a, n, (Fr*)a, n, dm->k, dm->omega_inv, o);
+}
+int spb_coeff_to_lagrange(spb_ctx* ctx, const spb_domain* dm, spb_fr* a) {
+  if (!ctx || !dm || !a) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  size_t n = (size_t)1 << dm->k;
+  return ntt_host(ctx, (const Fr*)a, n, (Fr*)a, n, dm->k, dm->omega, NttOpts());
+}
+int spb_coeff_to_extended(spb_ctx* ctx, const spb_domain* dm, const spb_fr* in, spb_fr* out) {
+  if (!ctx || !dm || !in || !out) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Fr pre[3]; NttOpts o; c2e_opts(dm, pre, o);
+  return ntt_host(ctx, (const Fr*)in, (size_t)1 << dm->k, (Fr*)out, (size_t)1 << dm->extended_k, dm->extended_k, dm->extended_omega, o);
+}
+int spb_extended_to_coeff(spb_ctx* ctx, const spb_domain* dm, const spb_fr* in, spb_fr* out) {
+  if (!ctx || !dm || !in || !out) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Fr post[3]; NttOpts o; e2c_opts(dm, post, o);
+  return ntt_host(ctx, (const Fr*)in, (size_t)1 << dm->extended_k, (Fr*)out, ((size_t)1 << dm->k) * dm->quotient_poly_degree, dm->extended_k, dm->extended_omega_inv, o);
+}
+static int div_vanishing_device(spb_ctx* ctx, DeviceState& d, const spb_domain* dm, Fr* d_a) {
+  uint64_t e = 1ull << dm->extended_k;
+  mul_periodic_kernel<<<(unsigned)((e + 255) / 256), 256, 0, d.stream>>>(d_a, dm->d_t_evaluations, e, dm->t_len - 1);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches++;
+  return 0;
+}
+int spb_divide_by_vanishing(spb_ctx* ctx, const spb_domain* dm, spb_fr* a) {
+  if (!ctx || !dm || !a) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  size_t e = (size_t)1 << dm->extended_k;
+  Fr* buf = (Fr*)slot(ctx, d, "ntt_io", e * sizeof(Fr));
+  if (!buf) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(buf, a, e * sizeof(Fr), cudaMemcpyHostToDevice, d.stream));
+  SPB_TRY(div_vanishing_device(ctx, d, dm, buf));
+  SPB_CUDA(ctx, cudaMemcpyAsync(a, buf, e * sizeof(Fr), cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+int spb_lagrange_to_coeff_dev(spb_ctx* ctx, const spb_domain* dm, spb_fr* d_a) {
+  if (!ctx || !dm || !d_a) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0]; SPB_CUDA(ctx, cudaSetDevice(d.device));
+  Fr post[3]; NttOpts o; l2c_opts(dm, post, o);
+  return ntt_timed(ctx, d, (const Fr*)d_a, (Fr*)d_a, dm->k, dm->omega_inv, o);
+}
+int spb_coeff_to_extended_dev(spb_ctx* ctx, const spb_domain* dm, const spb_fr* d_in, spb_fr* d_out) {
+  if (!ctx || !dm || !d_in || !d_out) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0]; SPB_CUDA(ctx, cudaSetDevice(d.device));
+  Fr pre[3]; NttOpts o; c2e_opts(dm, pre, o);
+  return ntt_timed(ctx, d, (const Fr*)d_in, (Fr*)d_out, dm->extended_k, dm->extended_omega, o);
+}
+int spb_extended_to_coeff_dev(spb_ctx* ctx, const spb_domain* dm, const spb_fr* d_in, spb_fr* d_out) {
+  if (!ctx || !dm || !d_in || !d_out) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0]; SPB_CUDA(ctx, cudaSetDevice(d.device));
+  Fr post[3]; NttOpts o; e2c_opts(dm, post, o);
+  return ntt_timed(ctx, d, (const Fr*)d_in, (Fr*)d_out, dm->extended_k, dm->extended_omega_inv, o);
+}
+int spb_divide_by_vanishing_dev(spb_ctx* ctx, const spb_domain* dm, spb_fr* d_a) {
+  if (!ctx || !dm || !d_a) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0]; SPB_CUDA(ctx, cudaSetDevice(d.device));
+  SPB_TRY(div_vanishing_device(ctx, d, dm, (Fr*)d_a));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+// ---- test utilities ----------------------------------------------------------------------------------------
+int spb_test_field_op(spb_ctx* ctx, int field, int op, const spb_fr* a, const spb_fr* b, spb_fr* out, size_t n) {
+  if (!ctx || !a || !b || !out) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  Fr* buf = (Fr*)slot(ctx, d, "test_io", 3 * n * sizeof(Fr));
+  if (!buf) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(buf, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  SPB_CUDA(ctx, cudaMemcpyAsync(buf + n, b, n * 32, cudaMemcpyHostToDevice, d.stream));
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (field == 0) field_op_kernel<FrParams><<<blocks, 128, 0, d.stream>>>(op, (const Fr*)buf, (const Fr*)(buf + n), (Fr*)(buf + 2 * n), n);
+  else field_op_kernel<FqParams><<<blocks, 128, 0, d.stream>>>(op, (const Fq*)buf, (const Fq*)(buf + n), (Fq*)(buf + 2 * n), n);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaMemcpyAsync(out, buf + 2 * n, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_bench_modmul(spb_ctx* ctx, int field, uint32_t threads, uint32_t iters, int ilp, float* ms) {
+  if (!ctx || !ms) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  threads = (threads + 255) / 256 * 256;
+  Fr* buf = (Fr*)slot(ctx, d, "test_io", (size_t)threads * sizeof(Fr));
+  if (!buf) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+  unsigned blocks = threads / 256;
+  if (field == 0) {
+    if (ilp == 1) modmul_bench_kernel<FrParams, 1><<<blocks, 256, 0, d.stream>>>((Fr*)buf, iters);
+    else if (ilp == 2) modmul_bench_kernel<FrParams, 2><<<blocks, 256, 0, d.stream>>>((Fr*)buf, iters);
+    else modmul_bench_kernel<FrParams, 4><<<blocks, 256, 0, d.stream>>>((Fr*)buf, iters);
+  } else {
+    if (ilp == 1) modmul_bench_kernel<FqParams, 1><<<blocks, 256, 0, d.stream>>>((Fq*)buf, iters);
+    else if (ilp == 2) modmul_bench_kernel<FqParams, 2><<<blocks, 256, 0, d.stream>>>((Fq*)buf, iters);
+    else modmul_bench_kernel<FqParams, 4><<<blocks, 256, 0, d.stream>>>((Fq*)buf, iters);
+  }
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  SPB_CUDA(ctx, cudaEventElapsedTime(ms, d.ev0, d.ev1));
+  return 0;
+}
+
+}  // extern "C"

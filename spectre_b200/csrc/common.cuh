@@ -1,0 +1,83 @@
+// Internal plumbing shared by the translation units of libspectre_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "curve.cuh"
+#include "../../include/spectre_b200.h"
+
+namespace spb {
+
+
+// Grow-only device buffer (workspace slots live for the lifetime of the context: no malloc in the hot path).
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+};
+
+struct NttTables {
+  Fr omega;
+  uint32_t k, h;
+  Fr* tw_lo = nullptr;  // 2^h
+  Fr* tw_hi = nullptr;  // 2^(k-h)
+};
+
+struct DeviceState {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::map<std::string, DevBuf> slots;
+  std::vector<NttTables> ntt_tables;
+  void* pinned = nullptr;  // small pinned staging area for results
+  size_t pinned_cap = 0;
+};
+
+}  // namespace spb
+
+struct spb_ctx {
+  std::vector<spb::DeviceState> dev;
+  std::mutex mu;
+  std::string last_error;
+  // counters (per-call instrumentation behind the C ABI)
+  uint64_t n_kernel_launches = 0;
+  float last_kernel_ms = 0.f;
+};
+
+namespace spb {
+
+int set_error(spb_ctx* ctx, int code, const char* fmt, ...);
+// returns nullptr (and sets the error) on failure
+void* slot(spb_ctx* ctx, DeviceState& d, const char* name, size_t bytes);
+
+#define SPB_CUDA(ctx, call)                                                                      \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) return spb::set_error(ctx, SPB_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define SPB_TRY(expr)            \
+  do {                           \
+    int rc_ = (expr);            \
+    if (rc_ != 0) return rc_;    \
+  } while (0)
+
+// ---- ntt.cu ----
+struct NttOpts {
+  uint64_t n_in = 0, n_out = 0;  // 0 = n
+  const Fr* pre3 = nullptr;      // host pointers to 3 factors, or nullptr
+  const Fr* post3 = nullptr;
+};
+// d_src/d_dst device pointers (may alias); omega host value (Montgomery)
+int ntt_device(spb_ctx* ctx, DeviceState& d, const Fr* d_src, Fr* d_dst, uint32_t log_n, const Fr& omega, const NttOpts& opts);
+
+// ---- host field helpers (64-bit path) ----
+inline Fr fr_from_u64(uint64_t v) {
+  Fr a = fp_zero<FrParams>(); a.l[0] = (uint32_t)v; a.l[1] = (uint32_t)(v >> 32);
+  return fp_to_mont(a);
+}
+
+}  // namespace spb

@@ -1,0 +1,230 @@
+// Fr number-theoretic transform for sm_100a: multi-pass (four-step / six-step family) decimation-in-frequency
+// NTT with shared-memory tiles, radix-4 register butterflies and shared-memory twiddle staging.
+//
+// Replaces halo2_proofs::arithmetic::best_fft ([UPSTREAM] halo2_proofs/src/arithmetic.rs; reached from the
+// reference through EvaluationDomain inside create_proof / keygen, lightclient-circuits/src/util/circuit.rs:
+// 131,158,177,211,263). Contract kept exactly: out[i] = sum_j in[j] * omega^(i*j), natural order in and out,
+// no 1/n scaling. The optional pre/post factors fuse what EvaluationDomain does around the transform
+// (zeta-coset distribution, zero padding, 1/n, truncation) into the first load and the last store.
+//
+// Decomposition. n = 2^k is split into P <= 3 digits of s_1..s_P bits, most significant first on the
+// input side: j = (j_1 | j_2 | j_3), and least significant first on the output side:
+// i = i_1 + 2^{s_1} i_2 + 2^{s_1+s_2} i_3. Pass p transforms digit p (2^{s_p}-point sub-NTTs at stride
+// 2^{b_p}, b_p = bits below the digit) for every value of the other digits, then multiplies by the
+// inter-digit twiddle omega_{N}^{ j_{p+1} * (i_1 + 2^{s_1} i_2 + ...) }, N = 2^{s_1+..+s_{p+1}}. Passes
+// 1..P-1 keep the positional layout (digit p now holds i_p); the last pass writes the digit-reversed
+// address, which is the natural-order result. A tile is one sub-NTT length times C neighbouring
+// columns, so every global access is a C*32-byte contiguous run.
+//
+// Inside a tile the sub-NTT is DIF (natural in, bit-reversed out): the bit reversal costs nothing
+// because it is folded into the global row address of the store. Data sit in shared memory as eight
+// 32-bit limb planes with one pad word per 32 (conflict-free for every power-of-two stride); each
+// thread runs two butterfly levels in registers per shared-memory round trip.
+//
+// Roofline: algorithmic bytes = 64 B/element; HBM traffic = P * 64 B/element. The kernel is
+// bound by the INT32 multiply pipe ((k/2 + P-1 + [P>1]) Montgomery products of ~139 IMAD each per element),
+// not by HBM -- DESIGN.md carries both numbers.
+#pragma once
+#include "field.cuh"
+
+namespace spb {
+
+struct NttPassParams {
+  const Fr* src;
+  Fr* dst;
+  const Fr* tw_lo;   // omega^i,           i < 2^h
+  const Fr* tw_hi;   // omega^(i * 2^h),   i < 2^(k-h)
+  uint32_t k;        // log2 n
+  uint32_t h;        // split of the two-level power table
+  uint32_t s;        // log2 length of this pass's sub-NTT
+  uint32_t a;        // bits above the digit (already transformed digits)
+  uint32_t b;        // bits below the digit
+  uint32_t logc;     // log2 columns per tile
+  uint32_t s1;       // bits of the first digit (== s when a == 0)
+  uint32_t b_next;   // bits below the NEXT digit (passes before the last)
+  uint32_t first, last;
+  uint32_t use_pre, use_post;
+  uint64_t n_in;     // elements >= n_in of the input are zero (not read)
+  uint64_t n_out;    // only outputs < n_out are stored
+  Fr pre[3];         // input i multiplied by pre[i % 3]   (first pass)
+  Fr post[3];        // output i multiplied by post[i % 3] (last pass)
+};
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ uint32_t ntt_pad(uint32_t i) { return i + (i >> 5); }
+
+struct NttSmem {
+  uint32_t* data;   // 8 planes of plane_words
+  uint32_t* tw;     // 8 planes of tw_words
+  uint32_t plane_words, tw_words, col_stride;
+  __device__ __forceinline__ Fr load(uint32_t col, uint32_t i) const {
+    Fr r; uint32_t o = col * col_stride + ntt_pad(i);
+#pragma unroll
+    for (int l = 0; l < 8; l++) r.l[l] = data[l * plane_words + o];
+    return r;
+  }
+  __device__ __forceinline__ void store(uint32_t col, uint32_t i, const Fr& v) const {
+    uint32_t o = col * col_stride + ntt_pad(i);
+#pragma unroll
+    for (int l = 0; l < 8; l++) data[l * plane_words + o] = v.l[l];
+  }
+  __device__ __forceinline__ Fr twiddle(uint32_t j) const {
+    Fr r;
+#pragma unroll
+    for (int l = 0; l < 8; l++) r.l[l] = tw[l * tw_words + j];
+    return r;
+  }
+};
+
+__device__ __forceinline__ Fr ntt_ldg(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 lo = __ldg(q), hi = __ldg(q + 1);
+  Fr r; r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w; r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+  return r;
+}
+__device__ __forceinline__ Fr ntt_ld_stream(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 lo = __ldcs(q), hi = __ldcs(q + 1);
+  Fr r; r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w; r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+  return r;
+}
+__device__ __forceinline__ void ntt_stg(Fr* p, const Fr& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+  q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// omega^E through the two-level table (one product unless a level is trivial)
+__device__ __forceinline__ Fr ntt_omega_pow(const NttPassParams& p, uint64_t e) {
+  uint64_t hi = e >> p.h, lo = e & ((1ull << p.h) - 1);
+  if (lo == 0) return ntt_ldg(p.tw_hi + hi);
+  Fr wl = ntt_ldg(p.tw_lo + lo);
+  if (hi == 0) return wl;
+  return fp_mul(ntt_ldg(p.tw_hi + hi), wl);
+}
+
+#if defined(SPB_NTT_KERNELS)
+// One kernel for every pass. Block = one tile (2^s rows of the digit x 2^logc columns).
+__global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
+  extern __shared__ uint32_t smem_raw[];
+  const uint32_t S = 1u << p.s, C = 1u << p.logc, T = blockDim.x, tid = threadIdx.x;
+  NttSmem sm;
+  sm.col_stride = ntt_pad(S - 1) + 1;
+  // make the column stride == 32/C (mod 32) so that a warp touching C columns x 32/C rows is conflict-free
+  { uint32_t want = (C >= 32) ? 1u : 32u / C; uint32_t r = sm.col_stride & 31u; sm.col_stride += (want + 32u - r) & 31u; }
+  sm.plane_words = sm.col_stride * C;
+  sm.tw_words = (S >> 1) ? (S >> 1) : 1;
+  sm.data = smem_raw;
+  sm.tw = smem_raw + 8 * sm.plane_words;
+
+  // ---- tile coordinates ---------------------------------------------------------------------------
+  // not last: tile = (hi, lo chunk);           element (r, c) at ((hi << s) + r) << b  +  lo0 + c
+  // last    : tile = (hi-with-i_1-chunk, all);  column c is the row whose first digit is i1_0 + c
+  const uint64_t tile = blockIdx.x;
+  uint64_t hi = 0, lo0 = 0, i1_0 = 0, hi_rest = 0;
+  const uint32_t rest_bits = p.a > p.s1 ? p.a - p.s1 : 0;  // bits of hi that are not the first digit (last pass, P = 3)
+  if (!p.last) {
+    const uint32_t chunks_log = p.b - p.logc;
+    hi = tile >> chunks_log;
+    lo0 = (tile & ((1ull << chunks_log) - 1)) << p.logc;
+  } else if (p.a > 0) {
+    // chunk along the first digit; remaining hi bits (second digit when P = 3) are fixed per tile
+    hi_rest = tile & ((1ull << rest_bits) - 1);
+    i1_0 = (tile >> rest_bits) << p.logc;
+  }
+
+  // ---- stage sub-NTT twiddles omega_{2^s}^j = omega^(j << (k-s)) into shared memory -----------------
+  for (uint32_t j = tid; j < (S >> 1); j += T) {
+    Fr w = ntt_omega_pow(p, (uint64_t)j << (p.k - p.s));
+#pragma unroll
+    for (int l = 0; l < 8; l++) sm.tw[l * sm.tw_words + j] = w.l[l];
+  }
+
+  // ---- load tile (natural order), fusing zero padding and the zeta-coset pre-scale -----------------
+  for (uint32_t e = tid; e < S * C; e += T) {
+    // lanes run along the contiguous global direction: columns for strided passes, the row for the last one
+    uint32_t c, r;
+    uint64_t gi;
+    if (!p.last) { c = e & (C - 1); r = e >> p.logc; gi = ((((hi << p.s) + r) << p.b) + lo0 + c); }
+    else { r = e & (S - 1); c = e >> p.s; gi = ((((i1_0 + c) << rest_bits) + hi_rest) << p.s) + r; }
+    Fr v;
+    if (p.first && gi >= p.n_in) v = fp_zero<FrParams>();
+    else {
+      v = ntt_ld_stream(p.src + gi);
+      if (p.first && p.use_pre) { uint32_t m = (uint32_t)(gi % 3); if (m) v = fp_mul(v, p.pre[m]); }
+    }
+    sm.store(c, r, v);
+  }
+  __syncthreads();
+
+  // ---- DIF butterflies ------------------------------------------------------------------------------
+  uint32_t m = S >> 1;  // current half-size
+  if (p.s & 1) {        // odd number of levels: one radix-2 level first
+    for (uint32_t e = tid; e < (S >> 1) * C; e += T) {
+      uint32_t c = e / (S >> 1), t = e % (S >> 1);
+      Fr x0 = sm.load(c, t), x1 = sm.load(c, t + m);
+      Fr u = fp_add(x0, x1), d = fp_sub(x0, x1);
+      if (m > 1 && t) d = fp_mul(d, sm.twiddle(t));
+      sm.store(c, t, u); sm.store(c, t + m, d);
+    }
+    m >>= 1;
+    __syncthreads();
+  }
+  for (; m >= 2; m >>= 2) {
+    const uint32_t q = m >> 1;                      // quarter stride
+    const uint32_t tws = (S >> 1) / m;              // twiddle index step for level m
+    for (uint32_t e = tid; e < (S >> 2) * C; e += T) {
+      uint32_t c = e / (S >> 2), t = e % (S >> 2);
+      uint32_t g = t / q, j = t % q, i = g * 2 * m + j;
+      Fr x0 = sm.load(c, i), x1 = sm.load(c, i + q), x2 = sm.load(c, i + m), x3 = sm.load(c, i + m + q);
+      // level m
+      Fr u0 = fp_add(x0, x2), u2 = fp_sub(x0, x2);
+      Fr u1 = fp_add(x1, x3), u3 = fp_sub(x1, x3);
+      if (j) u2 = fp_mul(u2, sm.twiddle(j * tws));
+      u3 = fp_mul(u3, sm.twiddle((j + q) * tws));
+      // level m/2 (twiddle omega_m^j for both pairs)
+      Fr v0 = fp_add(u0, u1), v1 = fp_sub(u0, u1);
+      Fr v2 = fp_add(u2, u3), v3 = fp_sub(u2, u3);
+      if (j) { Fr w = sm.twiddle(2 * j * tws); v1 = fp_mul(v1, w); v3 = fp_mul(v3, w); }
+      sm.store(c, i, v0); sm.store(c, i + q, v1); sm.store(c, i + m, v2); sm.store(c, i + m + q, v3);
+    }
+    __syncthreads();
+  }
+
+  // ---- store: position qpos holds digit value rev(qpos); fuse inter-digit twiddle / post-scale -----
+  for (uint32_t e = tid; e < S * C; e += T) {
+    uint32_t c = e & (C - 1), qpos = e >> p.logc;
+    uint32_t kd = p.s ? (__brev(qpos) >> (32 - p.s)) : 0;
+    Fr v = sm.load(c, qpos);
+    if (!p.last) {
+      // K' = i_1 + 2^{s_1} i_2 + ... restricted to the digits done so far. With P <= 3 the digits above the
+      // current one are just i_1 (= hi), so K' = hi + 2^a * kd.
+      uint64_t kprime = hi + ((uint64_t)kd << p.a);
+      uint64_t lo = lo0 + c;
+      // exponent of omega_n: j_next * K' * 2^(bits below the next digit)
+      uint64_t jn = lo >> p.b_next;
+      uint64_t ex = (jn * kprime) << p.b_next;
+      if (ex) v = fp_mul(v, ntt_omega_pow(p, ex));
+      uint64_t go = ((((hi << p.s) + kd) << p.b) + lo);
+      ntt_stg(p.dst + go, v);
+    } else {
+      uint64_t o = (i1_0 + c) + (hi_rest << p.s1) + ((uint64_t)kd << p.a);
+      if (o < p.n_out) {
+        if (p.use_post) v = fp_mul(v, p.post[o % 3]);
+        ntt_stg(p.dst + o, v);
+      }
+    }
+  }
+}
+
+// out[i] = base^(i << shift), i < count  (power tables; also reused for coset / vanishing constants)
+__global__ void fr_pow_table_kernel(Fr* out, Fr base, uint64_t count, uint32_t shift) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  out[i] = fp_pow_u64(base, i << shift);
+}
+
+#endif  // SPB_NTT_KERNELS
+#endif  // __CUDACC__
+}  // namespace spb

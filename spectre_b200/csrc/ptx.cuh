@@ -10,6 +10,7 @@
 // (tests/test_hostemu.py). The product never ships that mode.
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
 
 #if defined(__CUDACC__)
 #define SPB_HD __host__ __device__ __forceinline__

@@ -1,0 +1,333 @@
+"""Host-side mirror of the halo2_proofs surface that Spectre's prover reaches on the create_proof hot path,
+bound to libspectre_b200.so through its C ABI (include/spectre_b200.h) with ctypes.
+
+The names, argument meaning and failure behaviour follow the upstream Rust items so parity tests read like
+the reference's own use of them (reference call sites: lightclient-circuits/src/util/circuit.rs:11-16,131,158,
+177,211,263; prover/src/prover.rs:9-13,55):
+
+    halo2_proofs::arithmetic::best_fft            -> best_fft(a, omega, log_n)
+    halo2_proofs::arithmetic::best_multiexp       -> best_multiexp(coeffs, bases)
+    halo2_proofs::poly::EvaluationDomain          -> EvaluationDomain(j, k)
+    halo2_proofs::poly::kzg::commitment::ParamsKZG-> ParamsKZG.setup / .from_parts / .commit / .commit_lagrange
+    arithmetic::{eval_polynomial, kate_division}, ff::BatchInvert -> same names
+
+Field elements are numpy uint64 arrays (..., 4) holding halo2curves' in-memory Montgomery limbs; G1Affine is
+(..., 8) = x‖y with identity (0,0); G1 (Jacobian) is (12,) = x‖y‖z.
+
+This is the real Rust binding's stand-in (no cargo in this image; INTEGRATION.md has the Rust `extern "C"`
+block). There is NO CPU fallback: importing works anywhere, but creating a Backend without the built
+library or without a CUDA device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspectre_b200.so")
+
+BASIS_G = 0
+BASIS_G_LAGRANGE = 1
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the C-ABI library. Raises if it has not been built (python -m spectre_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BackendError("libspectre_b200.so is not built (run `python -m spectre_b200.build`); there is no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.spb_init.restype = ctypes.c_void_p
+        lib.spb_init.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.spb_last_error.restype = ctypes.c_char_p
+        lib.spb_last_error.argtypes = [ctypes.c_void_p]
+        lib.spb_kernel_launches.restype = ctypes.c_uint64
+        lib.spb_kernel_launches.argtypes = [ctypes.c_void_p]
+        lib.spb_last_device_ms.restype = ctypes.c_float
+        lib.spb_last_device_ms.argtypes = [ctypes.c_void_p]
+        if hasattr(lib, "spb_last_msm_adds"):
+            lib.spb_last_msm_adds.restype = ctypes.c_uint64
+            lib.spb_last_msm_adds.argtypes = [ctypes.c_void_p]
+        lib.spb_domain_extended_k.restype = ctypes.c_uint32
+        lib.spb_domain_extended_k.argtypes = [ctypes.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _fr_array(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 4)
+    assert a.shape[-1] == 4
+    if n is not None:
+        assert a.shape[0] == n, "length mismatch"
+    return a
+
+
+class Backend:
+    """One spb_ctx. `devices`: list of CUDA device ids driven by this process (default [0])."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        devices = list(devices) if devices is not None else [0]
+        ids = (ctypes.c_int * len(devices))(*devices)
+        self.ctx = self.lib.spb_init(ids, len(devices))
+        if not self.ctx:
+            raise BackendError("spb_init failed: no usable CUDA device (the library has no CPU fallback)")
+        self.ctx = ctypes.c_void_p(self.ctx)
+        self.devices = devices
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.spb_shutdown(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise BackendError("%s failed (%d): %s" % (what, rc, self.lib.spb_last_error(self.ctx).decode()))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.spb_kernel_launches(self.ctx))
+
+    @property
+    def last_device_ms(self):
+        return float(self.lib.spb_last_device_ms(self.ctx))
+
+    @property
+    def last_msm_adds(self):
+        return int(self.lib.spb_last_msm_adds(self.ctx))
+
+    # ---- arithmetic::best_fft --------------------------------------------------------------------------
+    def best_fft(self, a, omega, log_n):
+        """In-place on a copy; returns the transformed array. Panics (AssertionError) like upstream when
+        a.len() != 1 << log_n."""
+        a = _fr_array(a).copy()
+        assert a.shape[0] == 1 << log_n, "best_fft: a.len() != 1 << log_n"
+        omega = _fr_array(omega, 1)
+        self.check(self.lib.spb_ntt(self.ctx, _p(a), ctypes.c_uint32(log_n), _p(omega)), "spb_ntt")
+        return a
+
+    def best_fft_dev(self, d_ptr, omega, log_n):
+        omega = _fr_array(omega, 1)
+        self.check(self.lib.spb_ntt_dev(self.ctx, _p(d_ptr), ctypes.c_uint32(log_n), _p(omega)), "spb_ntt_dev")
+
+    # ---- arithmetic::best_multiexp ---------------------------------------------------------------------
+    def best_multiexp(self, coeffs, bases):
+        coeffs = _fr_array(coeffs)
+        bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        assert coeffs.shape[0] == bases.shape[0], "best_multiexp: coeffs.len() != bases.len()"
+        out = np.empty(12, dtype=np.uint64)
+        self.check(self.lib.spb_msm_raw(self.ctx, _p(coeffs), _p(bases), ctypes.c_size_t(coeffs.shape[0]), _p(out)), "spb_msm_raw")
+        return out
+
+    # ---- batch ops -------------------------------------------------------------------------------------
+    def batch_invert(self, a):
+        a = _fr_array(a).copy()
+        self.check(self.lib.spb_batch_invert(self.ctx, _p(a), ctypes.c_size_t(a.shape[0])), "spb_batch_invert")
+        return a
+
+    def eval_polynomial(self, poly, point):
+        poly = _fr_array(poly); point = _fr_array(point, 1)
+        out = np.empty(4, dtype=np.uint64)
+        self.check(self.lib.spb_eval_polynomial(self.ctx, _p(poly), ctypes.c_size_t(poly.shape[0]), _p(point), _p(out)), "spb_eval_polynomial")
+        return out
+
+    def kate_division(self, a, b):
+        a = _fr_array(a); b = _fr_array(b, 1)
+        q = np.empty((a.shape[0] - 1, 4), dtype=np.uint64)
+        self.check(self.lib.spb_kate_division(self.ctx, _p(a), ctypes.c_size_t(a.shape[0]), _p(b), _p(q)), "spb_kate_division")
+        return q
+
+    def grand_product(self, a):
+        a = _fr_array(a)
+        z = np.empty_like(a)
+        self.check(self.lib.spb_grand_product(self.ctx, _p(a), ctypes.c_size_t(a.shape[0]), _p(z)), "spb_grand_product")
+        return z
+
+    def vec_mul(self, a, b):
+        a = _fr_array(a).copy(); b = _fr_array(b, a.shape[0])
+        self.check(self.lib.spb_vec_mul(self.ctx, _p(a), _p(b), ctypes.c_size_t(a.shape[0])), "spb_vec_mul")
+        return a
+
+    def vec_axpy(self, y, alpha, x):
+        y = _fr_array(y).copy(); x = _fr_array(x, y.shape[0]); alpha = _fr_array(alpha, 1)
+        self.check(self.lib.spb_vec_axpy(self.ctx, _p(y), _p(alpha), _p(x), ctypes.c_size_t(y.shape[0])), "spb_vec_axpy")
+        return y
+
+    def vec_scale(self, a, alpha):
+        a = _fr_array(a).copy(); alpha = _fr_array(alpha, 1)
+        self.check(self.lib.spb_vec_scale(self.ctx, _p(a), _p(alpha), ctypes.c_size_t(a.shape[0])), "spb_vec_scale")
+        return a
+
+    # ---- utilities -------------------------------------------------------------------------------------
+    def g1_fixed_base_mul(self, scalars):
+        scalars = _fr_array(scalars)
+        out = np.empty((scalars.shape[0], 8), dtype=np.uint64)
+        self.check(self.lib.spb_g1_fixed_base_mul(self.ctx, _p(scalars), ctypes.c_size_t(scalars.shape[0]), _p(out)), "spb_g1_fixed_base_mul")
+        return out
+
+    def test_field_op(self, field, op, a, b):
+        a = _fr_array(a); b = _fr_array(b, a.shape[0])
+        out = np.empty_like(a)
+        f = {"fr": 0, "fq": 1}[field]; o = {"mul": 0, "add": 1, "sub": 2}[op]
+        self.check(self.lib.spb_test_field_op(self.ctx, f, o, _p(a), _p(b), _p(out), ctypes.c_size_t(a.shape[0])), "spb_test_field_op")
+        return out
+
+    def bench_modmul(self, field="fq", threads=148 * 2048, iters=2000, ilp=2):
+        ms = ctypes.c_float(0)
+        self.check(self.lib.spb_bench_modmul(self.ctx, {"fr": 0, "fq": 1}[field], ctypes.c_uint32(threads), ctypes.c_uint32(iters), ilp, ctypes.byref(ms)), "spb_bench_modmul")
+        threads = (threads + 255) // 256 * 256
+        return ms.value, threads * iters * ilp / (ms.value * 1e-3)
+
+
+class EvaluationDomain:
+    """EvaluationDomain::<Fr>::new(j, k) ([UPSTREAM] halo2_proofs/src/poly/domain.rs)."""
+
+    def __init__(self, backend, j, k):
+        self.be = backend
+        self.j, self.k = j, k
+        h = ctypes.c_void_p()
+        backend.check(backend.lib.spb_domain_new(backend.ctx, ctypes.c_uint32(j), ctypes.c_uint32(k), ctypes.byref(h)), "spb_domain_new")
+        self.h = h
+        self.extended_k = int(backend.lib.spb_domain_extended_k(h))
+        c = np.empty((8, 4), dtype=np.uint64)
+        backend.lib.spb_domain_constants(h, _p(c))
+        (self.omega, self.omega_inv, self.extended_omega, self.extended_omega_inv, self.g_coset, self.g_coset_inv,
+         self.ifft_divisor, self.extended_ifft_divisor) = [c[i].copy() for i in range(8)]
+
+    def __del__(self):
+        try:
+            if self.be.ctx:
+                self.be.lib.spb_domain_free(self.be.ctx, self.h)
+        except Exception:
+            pass
+
+    def get_omega(self):
+        return self.omega
+
+    def extended_len(self):
+        return 1 << self.extended_k
+
+    def lagrange_to_coeff(self, a):
+        a = _fr_array(a).copy()
+        assert a.shape[0] == 1 << self.k
+        self.be.check(self.be.lib.spb_lagrange_to_coeff(self.be.ctx, self.h, _p(a)), "spb_lagrange_to_coeff")
+        return a
+
+    def coeff_to_lagrange(self, a):
+        a = _fr_array(a).copy()
+        assert a.shape[0] == 1 << self.k
+        self.be.check(self.be.lib.spb_coeff_to_lagrange(self.be.ctx, self.h, _p(a)), "spb_coeff_to_lagrange")
+        return a
+
+    def coeff_to_extended(self, a):
+        a = _fr_array(a)
+        assert a.shape[0] == 1 << self.k
+        out = np.empty((1 << self.extended_k, 4), dtype=np.uint64)
+        self.be.check(self.be.lib.spb_coeff_to_extended(self.be.ctx, self.h, _p(a), _p(out)), "spb_coeff_to_extended")
+        return out
+
+    def extended_to_coeff(self, a):
+        a = _fr_array(a)
+        assert a.shape[0] == 1 << self.extended_k
+        out = np.empty(((1 << self.k) * (self.j - 1), 4), dtype=np.uint64)
+        self.be.check(self.be.lib.spb_extended_to_coeff(self.be.ctx, self.h, _p(a), _p(out)), "spb_extended_to_coeff")
+        return out
+
+    def divide_by_vanishing_poly(self, a):
+        a = _fr_array(a).copy()
+        assert a.shape[0] == 1 << self.extended_k
+        self.be.check(self.be.lib.spb_divide_by_vanishing(self.be.ctx, self.h, _p(a)), "spb_divide_by_vanishing")
+        return a
+
+
+class ParamsKZG:
+    """ParamsKZG<Bn256> with g and g_lagrange resident on the device(s)."""
+
+    def __init__(self, backend, k, handle):
+        self.be, self.k, self.n, self.h = backend, k, 1 << k, handle
+
+    @classmethod
+    def setup(cls, backend, k, s):
+        """ParamsKZG::setup(k, rng) where `s` is the secret the rng would draw (Montgomery limbs)."""
+        s = _fr_array(s, 1)
+        h = ctypes.c_void_p()
+        backend.check(backend.lib.spb_srs_setup(backend.ctx, ctypes.c_uint32(k), _p(s), ctypes.byref(h)), "spb_srs_setup")
+        return cls(backend, k, h)
+
+    @classmethod
+    def from_parts(cls, backend, k, g=None, g_lagrange=None):
+        """What ParamsKZG::read yields: upload the two bases (either may be None)."""
+        n = 1 << k
+        if g is not None:
+            g = np.ascontiguousarray(g, dtype=np.uint64).reshape(-1, 8); assert g.shape[0] == n
+        if g_lagrange is not None:
+            g_lagrange = np.ascontiguousarray(g_lagrange, dtype=np.uint64).reshape(-1, 8); assert g_lagrange.shape[0] == n
+        h = ctypes.c_void_p()
+        backend.check(backend.lib.spb_srs_upload(backend.ctx, ctypes.c_uint32(k), _p(g), _p(g_lagrange), ctypes.byref(h)), "spb_srs_upload")
+        return cls(backend, k, h)
+
+    def __del__(self):
+        try:
+            if self.be.ctx:
+                self.be.lib.spb_srs_free(self.be.ctx, self.h)
+        except Exception:
+            pass
+
+    def _commit(self, basis, poly):
+        poly = _fr_array(poly)
+        assert poly.shape[0] <= self.n, "commit: polynomial longer than the SRS"
+        out = np.empty(12, dtype=np.uint64)
+        self.be.check(self.be.lib.spb_msm(self.be.ctx, self.h, basis, _p(poly), ctypes.c_size_t(poly.shape[0]), _p(out)), "spb_msm")
+        return out
+
+    def commit(self, poly, blind=None):
+        """Params::commit (monomial basis); the blind is ignored, as in the KZG scheme upstream."""
+        return self._commit(BASIS_G, poly)
+
+    def commit_lagrange(self, poly, blind=None):
+        return self._commit(BASIS_G_LAGRANGE, poly)
+
+    def commit_dev(self, basis, d_ptr, n):
+        out = np.empty(12, dtype=np.uint64)
+        self.be.check(self.be.lib.spb_msm_dev(self.be.ctx, self.h, basis, _p(d_ptr), ctypes.c_size_t(n), _p(out)), "spb_msm_dev")
+        return out
+
+    def get_g(self, start=0, count=None, basis=BASIS_G):
+        count = self.n - start if count is None else count
+        out = np.empty((count, 8), dtype=np.uint64)
+        self.be.check(self.be.lib.spb_srs_download(self.be.ctx, self.h, basis, ctypes.c_size_t(start), ctypes.c_size_t(count), _p(out)), "spb_srs_download")
+        return out
+
+
+def jacobian_to_affine_ints(j, p_mod=0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47):
+    """(12,) Jacobian Montgomery limbs -> (x, y) canonical ints, identity -> (0, 0). Pure Python (for tests/logs)."""
+    j = np.ascontiguousarray(j, dtype=np.uint64).reshape(3, 4)
+    rinv = pow(1 << 256, -1, p_mod)
+    v = [(int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192) * rinv % p_mod for r in j]
+    if v[2] == 0:
+        return (0, 0)
+    zi = pow(v[2], -1, p_mod)
+    return (v[0] * zi * zi % p_mod, v[1] * zi * zi * zi % p_mod)
