@@ -1,0 +1,287 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the create_proof hot path (BASELINE.json configs[1]):
+BN254 G1 Pippenger MSM over 2^20 random points / uniform scalars per GPU, B200 vs the CPU best_multiexp.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one MSM of n = 2^20 pairs per GPU against a resident basis (what one ParamsKZG::commit_lagrange of
+a k=20 column is). With N ranks the step is ONE MSM of N*2^20 pairs sharded by point range: every
+rank reduces its range to a single point, the 96-byte partials are all-gathered over NCCL and folded locally.
+`value` = pairs per second of the whole job with scalars resident in HBM; `e2e` = the same through the host-buffer
+C-ABI call (pinned host scalars -> H2D -> kernels -> 96-byte result D2H inside the timed region).
+
+Extra keys: `roofline` (dominant kernel msm_accumulate_kernel vs measured HBM peak, plus the INT32-pipe view that
+actually binds it), `cpu_baseline` (the oracle port of halo2's best_multiexp on this box's cores), `ntt`
+(Fr NTT elements/s at 2^20 / 2^22, device-resident), `stages_ms`, `clocks`, `gpu_launches`.
+
+--impl reference times the CPU restatement of the reference's own path (oracle/_ref; the Rust crates cannot be
+built in this image -- DESIGN.md) on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = 20
+N_PAIRS = 1 << LOG_N
+N_SCALAR_SETS = 8  # 8 x 32 MiB of scalars rotate through the timed steps: 256 MiB > 126 MB L2
+R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+
+
+def rand_fr(n, seed):
+    """n pseudo-random valid Fr residues (uniform 252-bit Montgomery limbs; < r)."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    return a
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def run_reference(args):
+    """CPU arm: the oracle's restatement of halo2 best_multiexp (the reference's own path) on the host cores."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build(); orc.lib()
+    threads = os.cpu_count() or 1
+    sc = orc.fr_random_chacha(N_PAIRS, 0x5eed0003)
+    bases = orc.g1_fixed_base_mul(orc.fr_random_chacha(N_PAIRS, 0x5eed0002), threads=threads)
+    for _ in range(args.warmup):
+        orc.best_multiexp(sc[: 1 << 14], bases[: 1 << 14], threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.best_multiexp(sc, bases, threads=threads)
+    dt = time.perf_counter() - t0
+    val = N_PAIRS * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "bn254_g1_msm_pairs_per_s", "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u256 (4x64-bit Montgomery limbs, CPU)", "data": "synthetic",
+        "config": {"workload": "BN254 G1 MSM 2^20 random points / uniform scalars (BASELINE configs[1])", "log_n": LOG_N},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": "full 2^20-pair MSM per step, C restatement of halo2 best_multiexp (oracle/halo2_oracle.c); the Rust reference cannot be built here"},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ntt", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.steps > 5:
+            args.steps = 5  # each step is a full 2^20 MSM on the CPU (about a second or two)
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from spectre_b200 import halo2
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    be = halo2.Backend([local_rank])
+
+    # ---- inputs (untimed): this rank's point range and scalar sets ------------------------------------------
+    pts = be.g1_fixed_base_mul(rand_fr(N_PAIRS, 0x5eed0002 + 1000 * rank))   # random points h_i * G1
+    params = halo2.ParamsKZG.from_parts(be, LOG_N, g_lagrange=pts)
+    host_sets = [torch.from_numpy(rand_fr(N_PAIRS, 0x5eed0003 + 1000 * rank + s).view(np.int64)).pin_memory() for s in range(N_SCALAR_SETS)]
+    dev_sets = [h.to(dev) for h in host_sets]
+    torch.cuda.synchronize()
+
+    def fold_partials(partial):
+        """all-gather the 96-byte Jacobian partials and fold them (EC addition is not an NCCL reduction op)."""
+        if world == 1:
+            return partial
+        t = torch.from_numpy(partial.view(np.int64)).to(dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return halo2.g1_sum(torch.stack(out).cpu().numpy().view(np.uint64))
+
+    def step_dev(i):
+        s = dev_sets[i % N_SCALAR_SETS]
+        return fold_partials(params.commit_dev(halo2.BASIS_G_LAGRANGE, s.data_ptr(), N_PAIRS))
+
+    def step_e2e(i):
+        s = host_sets[i % N_SCALAR_SETS]
+        return fold_partials(params.commit_lagrange(s.numpy().view(np.uint64)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        acc_ms = 0.0
+        stage = {}
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(i)
+            acc_ms += be.last_device_ms
+            for k, v in be.last_msm_stage_ms.items():
+                stage[k] = stage.get(k, 0.0) + v
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([wall_ms, acc_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), {k: v / steps for k, v in stage.items()}
+
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = be.kernel_launches
+    wall_ms, dev_ms, stages = timed(step_dev, args.steps, args.warmup)
+    launches = be.kernel_launches - launches0
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    adds = be.last_msm_adds
+    e2e_wall_ms, _, _ = timed(step_e2e, max(3, args.steps // 2), 3)
+    e2e_steps = max(3, args.steps // 2)
+
+    total_pairs = N_PAIRS * world
+    ms_per_step = wall_ms / args.steps
+    value = total_pairs / (ms_per_step * 1e-3)
+    e2e_value = total_pairs / (e2e_wall_ms / e2e_steps * 1e-3)
+
+    if rank != 0:
+        be.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    c, W = be.msm_geometry(N_PAIRS)
+    acc_ms = stages.get("accumulate", 0.0)
+    algo_bytes = 96.0 * N_PAIRS  # 32 B scalar + 64 B affine base per pair, per launch (one rank's MSM)
+    achieved = algo_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
+    # INT32 multiply-pipe view: a mixed XYZZ addition is 8M+2S = 10 Montgomery products; measured product peak 68 G/s
+    modmul_per_launch = 10.0 * (adds - 2 * W * (1 << (c - 1)))
+    roofline = {
+        "kernel": "msm_accumulate_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": acc_ms,
+        "note": "integer-ALU bound, not HBM bound (SURVEY.md finding 6): see int32_pipe",
+        "int32_pipe": {"achieved_gmodmul_per_s": modmul_per_launch / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
+                       "peak_gmodmul_per_s": 68.2, "peak_source": "tools/microbench.py modmul on this pool's B200 (profiles/r01_microbench.md)"},
+    }
+    if roofline["int32_pipe"]["achieved_gmodmul_per_s"]:
+        roofline["int32_pipe"]["frac"] = roofline["int32_pipe"]["achieved_gmodmul_per_s"] / 68.2
+
+    line = {
+        "metric": "bn254_g1_msm_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, INT32 IMAD)",
+        "data": "synthetic",
+        "config": {"workload": "BN254 G1 MSM 2^20 random points / uniform scalars per GPU (BASELINE configs[1]); N ranks = one N*2^20 MSM sharded by point range",
+                   "log_n": LOG_N, "window_bits": c, "windows": W, "l2": "scalars rotate over 8 resident sets (256 MiB > 126 MB L2); the 64 MiB basis is reused as in the prover",
+                   "collective": "all_gather of 96-byte partial sums (NCCL)" if world > 1 else "none"},
+        "device_ms_per_step": dev_ms / args.steps, "g1_adds_per_s": adds * world / (ms_per_step * 1e-3), "stages_ms": stages,
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": N_PAIRS * 32, "d2h_bytes_per_step": 96, "ms_per_step": e2e_wall_ms / e2e_steps},
+        "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline,
+    }
+
+    # ---- NTT throughput (the other half of BASELINE.json's metric), device-resident, rank 0 ------------------
+    if not args.no_ntt:
+        ntt = {}
+        root = pow(7, (R_MOD - 1) >> 28, R_MOD)
+        for k in (20, 22):
+            w = pow(root, 1 << (28 - k), R_MOD) * (1 << 256) % R_MOD
+            omega = np.array([[(w >> (64 * j)) & (2**64 - 1) for j in range(4)]], dtype=np.uint64)
+            t = torch.from_numpy(rand_fr(1 << k, k).view(np.int64)).to(dev)
+            times = []
+            for _ in range(8):
+                be.best_fft_dev(t.data_ptr(), omega, k)
+                times.append(be.last_device_ms)
+            ms = float(np.median(times[3:]))
+            ntt["2^%d" % k] = {"ms": ms, "elems_per_s": (1 << k) / (ms * 1e-3), "algo_GBps": (1 << k) * 64 / (ms * 1e-3) / 1e9,
+                               "hbm_frac": (1 << k) * 64 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+            del t
+        line["ntt"] = ntt
+
+    # ---- CPU baseline (oracle port of best_multiexp) on this box's cores, bounded sample ----------------------
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle as orc
+        orc.build(); orc.lib()
+        threads = os.cpu_count() or 1
+        sc = host_sets[0].numpy().view(np.uint64)
+        t0 = time.perf_counter()
+        cpu_res = orc.best_multiexp(sc, pts, threads=threads)
+        dt = time.perf_counter() - t0
+        gpu_res = params.commit_lagrange(sc)
+        same = bool(np.array_equal(orc.g1_to_affine(cpu_res), orc.g1_to_affine(gpu_res)))
+        line["cpu_baseline"] = {"value": N_PAIRS / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                "sample": "one full 2^20-pair MSM (same scalars and bases as the GPU step), C port of halo2 best_multiexp",
+                                "seconds": dt, "result_equals_gpu": same}
+        if not same:
+            line["error"] = "GPU result differs from the CPU oracle"
+    print(json.dumps(line), flush=True)
+    be.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

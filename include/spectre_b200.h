@@ -88,6 +88,16 @@ int spb_msm(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* scalars, 
 int spb_msm_dev(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* d_scalars, size_t n, spb_g1* out);
 /* number of G1 additions (mixed + full) the last MSM executed on the device(s) */
 uint64_t spb_last_msm_adds(spb_ctx* ctx);
+/* device milliseconds of the last MSM's stages on the context's first device, from CUDA events on the stream the
+ * kernels ran on: [0] digit histogram, [1] bucket-offset scan, [2] scatter, [3] bucket accumulation (the dominant
+ * kernel), [4] chain stitch, [5] segment running sums, [6] per-window sum. */
+void spb_last_msm_stage_ms(spb_ctx* ctx, float out[7]);
+/* window width c and window count the library uses for an n-pair MSM */
+void spb_msm_geometry(size_t n, uint32_t* c, uint32_t* windows);
+
+/* Sum of n Jacobian points on the host (folding the per-rank / per-device partial results of a sharded MSM after
+ * the all-gather; EC addition is not an NCCL reduction). Result normalised to z = 1. No context needed. */
+int spb_g1_sum(const spb_g1* pts, size_t n, spb_g1* out);
 
 /* ---- NTT -------------------------------------------------------------------------------------------------- */
 /* best_fft(a, omega, log_n) ([UPSTREAM] halo2_proofs/src/arithmetic.rs): in place, natural order,

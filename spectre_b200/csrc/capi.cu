@@ -94,6 +94,7 @@ spb_ctx* spb_init(const int* device_ids, int n_dev) {
     d.sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     cudaEventCreate(&d.ev0); cudaEventCreate(&d.ev1);
+    for (int e = 0; e < 8; e++) cudaEventCreate(&d.stage_ev[e]);
     d.pinned_cap = 1 << 20;
     if (cudaMallocHost(&d.pinned, d.pinned_cap) != cudaSuccess) { delete ctx; return nullptr; }
     ctx->dev.push_back(d);
@@ -110,6 +111,7 @@ void spb_shutdown(spb_ctx* ctx) {
     for (auto& t : d.ntt_tables) { cudaFree(t.tw_lo); cudaFree(t.tw_hi); }
     if (d.pinned) cudaFreeHost(d.pinned);
     cudaEventDestroy(d.ev0); cudaEventDestroy(d.ev1);
+    for (int e = 0; e < 8; e++) cudaEventDestroy(d.stage_ev[e]);
     cudaStreamDestroy(d.stream);
   }
   delete ctx;
@@ -125,6 +127,16 @@ int spb_host_register(spb_ctx* ctx, void* ptr, size_t bytes) {
 }
 int spb_host_unregister(spb_ctx* ctx, void* ptr) {
   SPB_CUDA(ctx, cudaHostUnregister(ptr));
+  return 0;
+}
+
+// host-only fold of partial MSM results (multi-rank all-gather + local add; EC addition is not an NCCL op)
+int spb_g1_sum(const spb_g1* pts, size_t n, spb_g1* out) {
+  if (!out || (n && !pts)) return SPB_ERR_ARG;
+  G1Xyzz acc = xyzz_identity();
+  for (size_t i = 0; i < n; i++) { G1Jac j; memcpy(&j, &pts[i], sizeof j); xyzz_add(acc, xyzz_from_jac(j)); }
+  G1Jac r = jac_from_affine(xyzz_to_affine(acc));
+  memcpy(out, &r, sizeof r);
   return 0;
 }
 

@@ -31,6 +31,7 @@ struct DeviceState {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // MSM stage boundaries
   std::map<std::string, DevBuf> slots;
   std::vector<NttTables> ntt_tables;
   void* pinned = nullptr;  // small pinned staging area for results
@@ -46,6 +47,7 @@ struct spb_ctx {
   // counters (per-call instrumentation behind the C ABI)
   uint64_t n_kernel_launches = 0;
   float last_kernel_ms = 0.f;
+  float msm_stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};  // count, scan, scatter, accumulate, stitch, segment, window (device 0)
 };
 
 namespace spb {

@@ -1,0 +1,313 @@
+// BN254 G1 multi-scalar multiplication for sm_100a: signed-digit windowed Pippenger with a
+// counting sort and a load-balanced segmented bucket accumulation.
+//
+// Replaces halo2_proofs::arithmetic::best_multiexp / multiexp_serial ([UPSTREAM] halo2_proofs/src/arithmetic.rs;
+// reached from every ParamsKZG::commit / commit_lagrange inside create_proof and keygen, reference call sites
+// lightclient-circuits/src/util/circuit.rs:131,158,177,211,263). The contract is the group element
+// sum_i scalars[i] * bases[i]; integers are exact, so any correct schedule is bit-identical to the CPU
+// result after affine normalisation.
+//
+// Pipeline (one MSM of n pairs, window width c, W = ceil(255/c) windows, B = 2^(c-1) buckets per window):
+//   1. digits   : Montgomery -> canonical scalar (one product), signed c-bit digits d_w in (-B, B], histogram
+//                 of (w, |d_w|) with global atomics; zero digits are dropped here.
+//   2. scan     : exclusive prefix sum of the W*B counters (bucket offsets).
+//   3. scatter  : each non-zero digit writes (key = w*B + |d|-1, value = point index | sign << 31) at
+//                 atomicAdd(cursor[key]) -- a counting sort; order inside a bucket is irrelevant.
+//   4. accumulate: the sorted entry list is cut into fixed chunks of L entries, ONE THREAD PER CHUNK, so every
+//                 thread performs the same number of mixed XYZZ additions whatever the digit distribution
+//                 (witness columns put hundreds of thousands of points into one bucket). A run of equal keys
+//                 that lies inside a chunk is a complete bucket and is stored directly; the run that leaves
+//                 a chunk ("tail") and the run that enters one ("head") are stored as chunk pieces.
+//   5. stitch   : one thread per tail piece walks the following head pieces of the same key and stores the
+//                 bucket; chains longer than a cap (giant buckets) go to a block-wide tree reduction.
+//   6. reduce   : per window S_w = sum_b b * bucket[b]: running sums over segments of 16 buckets, a small
+//                 scalar multiplication by the segment offset, and a block tree sum per window.
+//   7. host     : sum_w 2^(c w) S_w by Horner (W*c doublings on the CPU 64-bit path) and one inversion.
+//
+// Roofline: algorithmic bytes = 96 B per pair. The kernel that dominates (step 4) executes
+// W mixed additions of 8M+2S (~1390 IMAD.WIDE) per pair: it is bound by the INT32 multiply pipe by two
+// orders of magnitude, not by HBM. DESIGN.md states both fractions.
+//
+// Every function below is written per thread (`tid`) so that tests/hostemu can run the identical code
+// serially on the CPU (-DSPB_EMULATE_PTX) against the oracle.
+#pragma once
+#include "curve.cuh"
+
+namespace spb {
+
+struct MsmGeom {
+  uint32_t c;        // window bits
+  uint32_t W;        // windows
+  uint32_t B;        // buckets per window = 2^(c-1)
+  uint32_t L;        // entries per accumulation chunk
+};
+
+static const uint32_t kNoKey = 0xffffffffu;
+
+#if defined(__CUDA_ARCH__)
+SPB_D uint32_t spb_atomic_inc(uint32_t* p) { return atomicAdd(p, 1u); }
+#else
+inline uint32_t spb_atomic_inc(uint32_t* p) { uint32_t v = *p; *p = v + 1; return v; }
+#endif
+
+// canonical little-endian scalar -> signed digit of window w. carry chain recomputed from window 0: cheap
+// (W <= 64 iterations of shifts) and keeps the digit kernels free of per-scalar storage.
+struct DigitIter {
+  uint32_t limbs[8];
+  uint32_t c, carry, w;
+  SPB_HD void init(const Fr& canonical, uint32_t c_) {
+    for (int i = 0; i < 8; i++) limbs[i] = canonical.l[i];
+    c = c_; carry = 0; w = 0;
+  }
+  // returns signed digit of the next window
+  SPB_HD int32_t next() {
+    uint32_t bit = w * c, word = bit >> 5, sh = bit & 31;
+    uint64_t v = 0;
+    if (word < 8) {
+      v = limbs[word];
+      if (word + 1 < 8) v |= (uint64_t)limbs[word + 1] << 32;
+      v >>= sh;
+    }
+    uint32_t raw = (uint32_t)(v & ((1u << c) - 1)) + carry;
+    w++;
+    if (raw > (1u << (c - 1))) { carry = 1; return (int32_t)raw - (int32_t)(1u << c); }
+    carry = 0;
+    return (int32_t)raw;
+  }
+};
+
+// ---- step 1: histogram ---------------------------------------------------------------------------------
+SPB_HD void msm_count_thread(uint64_t tid, uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* counts) {
+  if (tid >= n) return;
+  Fr s = fp_from_mont(scalars[tid]);
+  if (fp_is_zero(s)) return;
+  DigitIter it; it.init(s, g.c);
+  for (uint32_t w = 0; w < g.W; w++) {
+    int32_t d = it.next();
+    if (d == 0) continue;
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    spb_atomic_inc(&counts[w * g.B + mag - 1]);
+  }
+}
+
+// ---- step 3: scatter -----------------------------------------------------------------------------------
+SPB_HD void msm_scatter_thread(uint64_t tid, uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* cursor,
+                               uint32_t* ent_key, uint32_t* ent_val) {
+  if (tid >= n) return;
+  Fr s = fp_from_mont(scalars[tid]);
+  if (fp_is_zero(s)) return;
+  DigitIter it; it.init(s, g.c);
+  for (uint32_t w = 0; w < g.W; w++) {
+    int32_t d = it.next();
+    if (d == 0) continue;
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    uint32_t key = w * g.B + mag - 1;
+    uint32_t pos = spb_atomic_inc(&cursor[key]);
+    ent_key[pos] = key;
+    ent_val[pos] = (uint32_t)tid | (d < 0 ? 0x80000000u : 0u);
+  }
+}
+
+// ---- step 4: chunked accumulation ----------------------------------------------------------------------
+SPB_HD G1Affine msm_load_point(const G1Affine* bases, uint32_t val) {
+#if defined(__CUDA_ARCH__)
+  const uint4* q = reinterpret_cast<const uint4*>(bases + (val & 0x7fffffffu));
+  uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  G1Affine p;
+  p.x.l[0] = a.x; p.x.l[1] = a.y; p.x.l[2] = a.z; p.x.l[3] = a.w; p.x.l[4] = b.x; p.x.l[5] = b.y; p.x.l[6] = b.z; p.x.l[7] = b.w;
+  p.y.l[0] = c.x; p.y.l[1] = c.y; p.y.l[2] = c.z; p.y.l[3] = c.w; p.y.l[4] = d.x; p.y.l[5] = d.y; p.y.l[6] = d.z; p.y.l[7] = d.w;
+#else
+  G1Affine p = bases[val & 0x7fffffffu];
+#endif
+  if (val & 0x80000000u) p.y = fp_neg(p.y);
+  return p;
+}
+
+// One chunk = entries [tid*L, min((tid+1)*L, M)). Outputs:
+//   buckets[key]        for runs that are whole buckets
+//   head_key/head[tid]  first run when it started in an earlier chunk (kNoKey if none)
+//   tail_key/tail[tid]  last run when it continues into the next chunk, or a single-run chunk whose bucket
+//                       starts here and continues (chain start)                      (kNoKey if none)
+SPB_HD void msm_accumulate_thread(uint64_t tid, uint64_t M, MsmGeom g, const uint32_t* ent_key, const uint32_t* ent_val,
+                                  const G1Affine* bases, G1Xyzz* buckets, uint32_t* head_key, G1Xyzz* head,
+                                  uint32_t* tail_key, G1Xyzz* tail) {
+  uint64_t lo = tid * g.L;
+  if (lo >= M) return;
+  uint64_t hi = lo + g.L < M ? lo + g.L : M;
+  uint32_t hk = kNoKey, tk = kNoKey;
+  uint32_t cur = ent_key[lo];
+  bool run_started_before = lo > 0 && ent_key[lo - 1] == cur;  // the current run began in an earlier chunk
+  G1Xyzz acc = xyzz_from_affine(msm_load_point(bases, ent_val[lo]));
+  for (uint64_t e = lo + 1; e < hi; e++) {
+    uint32_t k = ent_key[e];
+    G1Affine p = msm_load_point(bases, ent_val[e]);
+    if (k == cur) {
+      xyzz_add_mixed(acc, p);
+    } else {
+      // the run of `cur` ends inside this chunk
+      if (run_started_before) { hk = cur; head[tid] = acc; }
+      else buckets[cur] = acc;
+      run_started_before = false;
+      cur = k;
+      acc = xyzz_from_affine(p);
+    }
+  }
+  bool continues = hi < M && ent_key[hi] == cur;
+  if (continues) {
+    if (run_started_before) { hk = cur; head[tid] = acc; }  // middle link of a chain
+    else { tk = cur; tail[tid] = acc; }                     // chain start
+  } else {
+    if (run_started_before) { hk = cur; head[tid] = acc; }  // last link of a chain
+    else buckets[cur] = acc;                                // whole bucket
+  }
+  head_key[tid] = hk;
+  tail_key[tid] = tk;
+}
+
+// ---- step 5: stitch chains ------------------------------------------------------------------------------
+// chain started by tail[tid]: links are head[tid+1], head[tid+2], ... while their key matches.
+// Short chains are summed here; long ones are queued for msm_giant_block.
+SPB_HD void msm_stitch_thread(uint64_t tid, uint64_t T, uint32_t cap, const uint32_t* head_key, const G1Xyzz* head,
+                              const uint32_t* tail_key, const G1Xyzz* tail, G1Xyzz* buckets, uint32_t* giant_count,
+                              uint32_t* giant_list) {
+  if (tid >= T) return;
+  uint32_t key = tail_key[tid];
+  if (key == kNoKey) return;
+  uint64_t j = tid + 1, len = 0;
+  while (j < T && head_key[j] == key && len <= cap) { j++; len++; }
+  if (len > cap) { uint32_t slot = spb_atomic_inc(giant_count); giant_list[slot] = (uint32_t)tid; return; }
+  G1Xyzz acc = tail[tid];
+  for (uint64_t q = tid + 1; q < tid + 1 + len; q++) xyzz_add(acc, head[q]);
+  buckets[key] = acc;
+}
+
+// ---- step 6a: per-segment running sums -----------------------------------------------------------------
+// segment `seg` of window `w` covers bucket values b = seg*s + 1 .. seg*s + s; output = sum_b b * bucket[b]
+SPB_HD void msm_segment_thread(uint64_t tid, MsmGeom g, uint32_t s, const G1Xyzz* buckets, G1Xyzz* seg_out) {
+  uint32_t segs = g.B / s;
+  if (tid >= (uint64_t)g.W * segs) return;
+  uint32_t w = (uint32_t)(tid / segs), seg = (uint32_t)(tid % segs);
+  const G1Xyzz* bk = buckets + (uint64_t)w * g.B + (uint64_t)seg * s;  // bk[j] holds value seg*s + j + 1
+  G1Xyzz run = xyzz_identity(), res = xyzz_identity();
+  for (int j = (int)s - 1; j >= 0; j--) {
+    xyzz_add(run, bk[j]);
+    xyzz_add(res, run);
+  }
+  // res = sum (j+1) bk[j];  add (seg*s) * run
+  if (seg) { G1Xyzz off = xyzz_mul_u32(run, seg * s); xyzz_add(res, off); }
+  seg_out[tid] = res;
+}
+
+#if defined(__CUDACC__) && defined(SPB_MSM_KERNELS)
+// ---- kernels --------------------------------------------------------------------------------------------
+// The number of sorted entries M is read from device memory (the last element of the offset scan), so the
+// whole MSM is enqueued without a host round trip between the sort and the accumulation.
+__global__ void msm_count_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* counts) {
+  msm_count_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, n, scalars, g, counts);
+}
+__global__ void msm_scatter_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* cursor, uint32_t* ent_key, uint32_t* ent_val) {
+  msm_scatter_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, n, scalars, g, cursor, ent_key, ent_val);
+}
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* total, MsmGeom g, const uint32_t* ent_key, const uint32_t* ent_val,
+                                                             const G1Affine* bases, G1Xyzz* buckets, uint32_t* head_key, G1Xyzz* head,
+                                                             uint32_t* tail_key, G1Xyzz* tail) {
+  msm_accumulate_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, *total, g, ent_key, ent_val, bases, buckets, head_key, head, tail_key, tail);
+}
+__global__ void __launch_bounds__(128) msm_stitch_kernel(const uint32_t* total, uint32_t L, uint32_t cap, const uint32_t* head_key, const G1Xyzz* head,
+                                                         const uint32_t* tail_key, const G1Xyzz* tail, G1Xyzz* buckets, uint32_t* giant_count, uint32_t* giant_list) {
+  uint64_t T = ((uint64_t)*total + L - 1) / L;
+  msm_stitch_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, T, cap, head_key, head, tail_key, tail, buckets, giant_count, giant_list);
+}
+
+// block-wide sum of NT points held one per thread; result in thread 0's `v`
+template <int NT>
+__device__ void block_sum_xyzz(G1Xyzz& v, G1Xyzz* sh) {
+  const int tid = threadIdx.x;
+  for (int stride = NT / 2; stride >= 1; stride >>= 1) {
+    if (tid >= stride && tid < 2 * stride) sh[tid - stride] = v;
+    __syncthreads();
+    if (tid < stride) xyzz_add(v, sh[tid]);
+    __syncthreads();
+  }
+}
+
+// giant chains (queued by the stitch kernel): one block per chain, grid-stride over the queue
+__global__ void __launch_bounds__(128) msm_giant_kernel(const uint32_t* total, uint32_t L, const uint32_t* giant_count, const uint32_t* giant_list,
+                                                        const uint32_t* head_key, const G1Xyzz* head, const uint32_t* tail_key, const G1Xyzz* tail,
+                                                        G1Xyzz* buckets) {
+  __shared__ G1Xyzz sh[64];
+  const uint64_t T = ((uint64_t)*total + L - 1) / L;
+  const uint32_t count = *giant_count;
+  for (uint32_t gi = blockIdx.x; gi < count; gi += gridDim.x) {
+    uint64_t t0 = giant_list[gi];
+    uint32_t key = tail_key[t0];
+    G1Xyzz acc = xyzz_identity();
+    for (uint64_t j = t0 + 1 + threadIdx.x; j < T && head_key[j] == key; j += 128) xyzz_add(acc, head[j]);
+    block_sum_xyzz<128>(acc, sh);
+    if (threadIdx.x == 0) { xyzz_add(acc, tail[t0]); buckets[key] = acc; }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128) msm_segment_kernel(MsmGeom g, uint32_t s, const G1Xyzz* buckets, G1Xyzz* seg_out) {
+  msm_segment_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, g, s, buckets, seg_out);
+}
+
+// one block per window: S_w = sum of its `segs` segment results
+__global__ void __launch_bounds__(128) msm_window_kernel(uint32_t segs, const G1Xyzz* seg_out, G1Xyzz* window_out) {
+  __shared__ G1Xyzz sh[64];
+  const G1Xyzz* p = seg_out + (uint64_t)blockIdx.x * segs;
+  G1Xyzz acc = xyzz_identity();
+  for (uint32_t j = threadIdx.x; j < segs; j += 128) xyzz_add(acc, p[j]);
+  block_sum_xyzz<128>(acc, sh);
+  if (threadIdx.x == 0) window_out[blockIdx.x] = acc;
+}
+
+// out[i] = scalars[i] * G1 (affine): plain double-and-add per thread + one inversion. Setup / test utility.
+__global__ void __launch_bounds__(128) g1_fixed_base_mul_kernel(const Fr* scalars, uint64_t n, G1Affine* out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = fp_from_mont(scalars[i]);
+  G1Affine gen; gen.x = fp_one<FqParams>(); gen.y = fp_dbl(gen.x);  // (1, 2)
+  G1Xyzz acc = xyzz_identity();
+  for (int b = 253; b >= 0; b--) {
+    acc = xyzz_dbl(acc);
+    if ((s.l[b >> 5] >> (b & 31)) & 1) xyzz_add_mixed(acc, gen);
+  }
+  out[i] = xyzz_to_affine(acc);
+}
+
+// scalars of ParamsKZG::setup: mode 0: out[i] = s^i ; mode 1: out[i] = coef * w^i / (s - w^i)  (L_i(s))
+__global__ void srs_scalars_kernel(int mode, Fr s, Fr w, Fr coef, uint64_t start, uint64_t n, Fr* out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mode == 0) { out[i] = fp_pow_u64(s, start + i); return; }
+  Fr wi = fp_pow_u64(w, start + i);
+  out[i] = fp_mul(fp_mul(coef, wi), fp_inv(fp_sub(s, wi)));
+}
+#endif
+
+// ---- step 7 (host): Horner over windows ------------------------------------------------------------------
+inline G1Xyzz msm_combine_windows(const G1Xyzz* S, uint32_t W, uint32_t c) {
+  G1Xyzz acc = xyzz_identity();
+  for (int w = (int)W - 1; w >= 0; w--) {
+    for (uint32_t i = 0; i < c; i++) acc = xyzz_dbl(acc);
+    xyzz_add(acc, S[w]);
+  }
+  return acc;
+}
+
+// window width minimising  n*W + 3.5 * W * 2^(c-1)  (mixed adds + weighted bucket-reduction adds)
+inline MsmGeom msm_choose_geometry(uint64_t n) {
+  MsmGeom best; best.c = 0; double best_cost = 0;
+  for (uint32_t c = 3; c <= 20; c++) {
+    uint32_t W = (255 + c - 1) / c;
+    double cost = (double)n * W + 3.5 * W * (double)(1u << (c - 1));
+    if (!best.c || cost < best_cost) { best.c = c; best.W = W; best_cost = cost; }
+  }
+  best.B = 1u << (best.c - 1);
+  best.L = 32;
+  return best;
+}
+
+}  // namespace spb

@@ -1,0 +1,255 @@
+// Batch polynomial arithmetic over Fr on the device: replaces halo2_proofs::arithmetic::{eval_polynomial,
+// kate_division, parallelize-d axpy/scale loops} and ff::BatchInvert as used by plonk::{permutation, lookup,
+// vanishing} and the SHPLONK opener ([UPSTREAM] halo2_proofs/src/arithmetic.rs, src/plonk/permutation/prover.rs,
+// src/poly/kzg/multiopen/shplonk/prover.rs). All are HBM-streaming passes:
+// algorithmic bytes = 64 B/element (read + write), 32 B/element for the reductions.
+//
+// The three scans (grand product, Kate division, batch inversion) are chunked three-phase scans: per-chunk
+// partials on the device, a tiny serial carry pass over the chunk partials on the host (n / 256 elements), and a
+// device fix-up pass. Element order and results are exactly the serial CPU recurrences'.
+#include "common.cuh"
+#include "ntt.cuh"
+#include <string.h>
+
+using namespace spb;
+
+static const uint32_t kChunk = 256;
+
+__global__ void vec_mul_kernel(Fr* a, const Fr* b, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) ntt_stg(a + i, fp_mul(ntt_ld_stream(a + i), ntt_ld_stream(b + i)));
+}
+__global__ void vec_axpy_kernel(Fr* y, Fr alpha, const Fr* x, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) ntt_stg(y + i, fp_add(ntt_ld_stream(y + i), fp_mul(alpha, ntt_ld_stream(x + i))));
+}
+__global__ void vec_scale_kernel(Fr* a, Fr alpha, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) ntt_stg(a + i, fp_mul(alpha, ntt_ld_stream(a + i)));
+}
+
+// ---- grand product -------------------------------------------------------------------------------------------
+__global__ void chunk_product_kernel(const Fr* a, uint64_t n, Fr* partial) {
+  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint64_t lo = c * kChunk;
+  if (lo >= n) return;
+  uint64_t hi = lo + kChunk < n ? lo + kChunk : n;
+  Fr p = fp_one<FrParams>();
+  for (uint64_t i = lo; i < hi; i++) p = fp_mul(p, ntt_ldg(a + i));
+  partial[c] = p;
+}
+// z[i] = carry[c] * prod_{lo <= j < i} a[j]
+__global__ void chunk_product_fix_kernel(const Fr* a, uint64_t n, const Fr* carry, Fr* z) {
+  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint64_t lo = c * kChunk;
+  if (lo >= n) return;
+  uint64_t hi = lo + kChunk < n ? lo + kChunk : n;
+  Fr p = carry[c];
+  for (uint64_t i = lo; i < hi; i++) { Fr v = ntt_ldg(a + i); ntt_stg(z + i, p); p = fp_mul(p, v); }
+}
+
+// ---- Kate division: q[i] = a[i+1] + b*q[i+1], q has n-1 entries ----------------------------------------------
+// with_store = 0: only the chunk head q[lo] (carry-in 0) is produced; 1: full chunk with the true carry-in.
+__global__ void kate_chunk_kernel(const Fr* a, uint64_t nq, Fr b, const Fr* carry_in, Fr* heads, Fr* q, int with_store) {
+  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint64_t lo = c * kChunk;
+  if (lo >= nq) return;
+  uint64_t hi = lo + kChunk < nq ? lo + kChunk : nq;
+  Fr t = with_store ? carry_in[c] : fp_zero<FrParams>();
+  for (uint64_t i = hi; i-- > lo;) {
+    t = fp_add(ntt_ldg(a + i + 1), fp_mul(b, t));
+    if (with_store) ntt_stg(q + i, t);
+  }
+  if (!with_store) heads[c] = t;
+}
+
+// ---- batch inversion (zeros stay zero) ----------------------------------------------------------------------------
+// phase 1: prefix products inside a chunk skipping zeros -> scratch, chunk product -> partial
+__global__ void inv_chunk_prefix_kernel(const Fr* a, uint64_t n, Fr* scratch, Fr* partial) {
+  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint64_t lo = c * kChunk;
+  if (lo >= n) return;
+  uint64_t hi = lo + kChunk < n ? lo + kChunk : n;
+  Fr p = fp_one<FrParams>();
+  for (uint64_t i = lo; i < hi; i++) { ntt_stg(scratch + i, p); Fr v = ntt_ldg(a + i); if (!fp_is_zero(v)) p = fp_mul(p, v); }
+  partial[c] = p;
+}
+// phase 3: inv_total[c] = inverse of the chunk product
+__global__ void inv_chunk_fix_kernel(Fr* a, uint64_t n, const Fr* scratch, const Fr* inv_total) {
+  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint64_t lo = c * kChunk;
+  if (lo >= n) return;
+  uint64_t hi = lo + kChunk < n ? lo + kChunk : n;
+  Fr run = inv_total[c];
+  for (uint64_t i = hi; i-- > lo;) {
+    Fr v = ntt_ldg(a + i);
+    if (fp_is_zero(v)) continue;
+    ntt_stg(a + i, fp_mul(run, ntt_ldg(scratch + i)));
+    run = fp_mul(run, v);
+  }
+}
+// one thread per chunk: plain Fermat inversion of the chunk product (n/256 inversions, fully parallel)
+__global__ void inv_partials_kernel(Fr* partial, uint64_t m) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < m) partial[i] = fp_inv(partial[i]);
+}
+
+// ---- polynomial evaluation: p(x) = sum_t x^t * q_t(x^T), q_t = coefficients t, t+T, ... (coalesced Horner) ------
+__global__ void eval_strided_kernel(const Fr* poly, uint64_t n, Fr x, Fr xT, uint32_t T, Fr* partial) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  Fr acc = fp_zero<FrParams>();
+  if (t < n) {
+    uint64_t last = t + ((n - 1 - t) / T) * T;
+    for (uint64_t i = last;; i -= T) { acc = fp_add(fp_mul(acc, xT), ntt_ldg(poly + i)); if (i < T) break; }
+    acc = fp_mul(acc, fp_pow_u64(x, t));
+  }
+  partial[t] = acc;
+}
+
+extern "C" {
+
+#define SPB_ENTER(ctx)                          \
+  std::lock_guard<std::mutex> lk((ctx)->mu);    \
+  DeviceState& d = (ctx)->dev[0];               \
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+int spb_vec_mul(spb_ctx* ctx, spb_fr* a, const spb_fr* b, size_t n) {
+  if (!ctx || !a || !b) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* db = (Fr*)slot(ctx, d, "poly_b", n * 32);
+  if (!da || !db) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  SPB_CUDA(ctx, cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, d.stream));
+  vec_mul_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(da, db, n);
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_vec_axpy(spb_ctx* ctx, spb_fr* y, const spb_fr* alpha, const spb_fr* x, size_t n) {
+  if (!ctx || !y || !alpha || !x) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  Fr* dy = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dx = (Fr*)slot(ctx, d, "poly_b", n * 32);
+  if (!dy || !dx) return SPB_ERR_OOM;
+  Fr al; memcpy(&al, alpha, 32);
+  SPB_CUDA(ctx, cudaMemcpyAsync(dy, y, n * 32, cudaMemcpyHostToDevice, d.stream));
+  SPB_CUDA(ctx, cudaMemcpyAsync(dx, x, n * 32, cudaMemcpyHostToDevice, d.stream));
+  vec_axpy_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(dy, al, dx, n);
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaMemcpyAsync(y, dy, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_vec_scale(spb_ctx* ctx, spb_fr* a, const spb_fr* alpha, size_t n) {
+  if (!ctx || !a || !alpha) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32);
+  if (!da) return SPB_ERR_OOM;
+  Fr al; memcpy(&al, alpha, 32);
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  vec_scale_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(da, al, n);
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_grand_product(spb_ctx* ctx, const spb_fr* a, size_t n, spb_fr* z) {
+  if (!ctx || !a || !z) return SPB_ERR_ARG;
+  if (!n) return 0;
+  SPB_ENTER(ctx);
+  size_t m = (n + kChunk - 1) / kChunk;
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dz = (Fr*)slot(ctx, d, "poly_b", n * 32);
+  Fr* dp = (Fr*)slot(ctx, d, "poly_partial", m * 32);
+  if (!da || !dz || !dp) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  chunk_product_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, dp);
+  std::vector<Fr> part(m);
+  SPB_CUDA(ctx, cudaMemcpyAsync(part.data(), dp, m * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  Fr run = fp_one<FrParams>();
+  for (size_t c = 0; c < m; c++) { Fr t = part[c]; part[c] = run; run = fp_mul(run, t); }  // exclusive carry
+  SPB_CUDA(ctx, cudaMemcpyAsync(dp, part.data(), m * 32, cudaMemcpyHostToDevice, d.stream));
+  chunk_product_fix_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, dp, dz);
+  ctx->n_kernel_launches += 2;
+  SPB_CUDA(ctx, cudaMemcpyAsync(z, dz, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_kate_division(spb_ctx* ctx, const spb_fr* a, size_t n, const spb_fr* b, spb_fr* q) {
+  if (!ctx || !a || !b || !q || n < 1) return SPB_ERR_ARG;
+  if (n == 1) return 0;
+  SPB_ENTER(ctx);
+  size_t nq = n - 1, m = (nq + kChunk - 1) / kChunk;
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dq = (Fr*)slot(ctx, d, "poly_b", nq * 32);
+  Fr* dh = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32);
+  if (!da || !dq || !dh) return SPB_ERR_OOM;
+  Fr bb; memcpy(&bb, b, 32);
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  kate_chunk_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, nq, bb, nullptr, dh, nullptr, 0);
+  std::vector<Fr> heads(m), carry(m);
+  SPB_CUDA(ctx, cudaMemcpyAsync(heads.data(), dh, m * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  // carry into chunk c = q[hi_c] = true head of chunk c+1; true head_c = head0_c + b^(len_c) * carry_c
+  Fr bch = fp_pow_u64(bb, kChunk);
+  Fr next = fp_zero<FrParams>();
+  for (size_t c = m; c-- > 0;) {
+    carry[c] = next;
+    size_t len = (c == m - 1) ? nq - c * kChunk : kChunk;
+    Fr bl = (len == kChunk) ? bch : fp_pow_u64(bb, len);
+    next = fp_add(heads[c], fp_mul(bl, next));
+  }
+  SPB_CUDA(ctx, cudaMemcpyAsync(dh + m, carry.data(), m * 32, cudaMemcpyHostToDevice, d.stream));
+  kate_chunk_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, nq, bb, dh + m, nullptr, dq, 1);
+  ctx->n_kernel_launches += 2;
+  SPB_CUDA(ctx, cudaMemcpyAsync(q, dq, nq * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_batch_invert(spb_ctx* ctx, spb_fr* a, size_t n) {
+  if (!ctx || !a) return SPB_ERR_ARG;
+  if (!n) return 0;
+  SPB_ENTER(ctx);
+  size_t m = (n + kChunk - 1) / kChunk;
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* ds = (Fr*)slot(ctx, d, "poly_b", n * 32);
+  Fr* dp = (Fr*)slot(ctx, d, "poly_partial", m * 32);
+  if (!da || !ds || !dp) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  inv_chunk_prefix_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, ds, dp);
+  inv_partials_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(dp, m);
+  inv_chunk_fix_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, ds, dp);
+  ctx->n_kernel_launches += 3;
+  SPB_CUDA(ctx, cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_eval_polynomial(spb_ctx* ctx, const spb_fr* poly, size_t n, const spb_fr* point, spb_fr* out) {
+  if (!ctx || !point || !out || (n && !poly)) return SPB_ERR_ARG;
+  Fr acc = fp_zero<FrParams>();
+  if (n) {
+    SPB_ENTER(ctx);
+    const uint32_t T = 4096;
+    Fr* dp = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dpart = (Fr*)slot(ctx, d, "poly_partial", T * 32);
+    if (!dp || !dpart) return SPB_ERR_OOM;
+    Fr x; memcpy(&x, point, 32);
+    SPB_CUDA(ctx, cudaMemcpyAsync(dp, poly, n * 32, cudaMemcpyHostToDevice, d.stream));
+    eval_strided_kernel<<<T / 128, 128, 0, d.stream>>>(dp, n, x, fp_pow_u64(x, T), T, dpart);
+    ctx->n_kernel_launches++;
+    std::vector<Fr> part(T);
+    SPB_CUDA(ctx, cudaMemcpyAsync(part.data(), dpart, T * 32, cudaMemcpyDeviceToHost, d.stream));
+    SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    for (uint32_t t = 0; t < T; t++) acc = fp_add(acc, part[t]);
+  }
+  memcpy(out, &acc, 32);
+  return 0;
+}
+
+}  // extern "C"

@@ -119,6 +119,17 @@ class Backend:
     def last_msm_adds(self):
         return int(self.lib.spb_last_msm_adds(self.ctx))
 
+    @property
+    def last_msm_stage_ms(self):
+        out = (ctypes.c_float * 7)()
+        self.lib.spb_last_msm_stage_ms(self.ctx, out)
+        return dict(zip(("count", "scan", "scatter", "accumulate", "stitch", "segment", "window"), [float(v) for v in out]))
+
+    def msm_geometry(self, n):
+        c = ctypes.c_uint32(); w = ctypes.c_uint32()
+        self.lib.spb_msm_geometry(ctypes.c_size_t(n), ctypes.byref(c), ctypes.byref(w))
+        return c.value, w.value
+
     # ---- arithmetic::best_fft --------------------------------------------------------------------------
     def best_fft(self, a, omega, log_n):
         """In-place on a copy; returns the transformed array. Panics (AssertionError) like upstream when
@@ -320,6 +331,16 @@ class ParamsKZG:
         out = np.empty((count, 8), dtype=np.uint64)
         self.be.check(self.be.lib.spb_srs_download(self.be.ctx, self.h, basis, ctypes.c_size_t(start), ctypes.c_size_t(count), _p(out)), "spb_srs_download")
         return out
+
+
+def g1_sum(points):
+    """Fold Jacobian points (n, 12) on the host: the multi-rank MSM epilogue after all_gather."""
+    pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 12)
+    out = np.empty(12, dtype=np.uint64)
+    rc = load_library().spb_g1_sum(_p(pts), ctypes.c_size_t(pts.shape[0]), _p(out))
+    if rc != 0:
+        raise BackendError("spb_g1_sum failed (%d)" % rc)
+    return out
 
 
 def jacobian_to_affine_ints(j, p_mod=0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47):
