@@ -151,6 +151,9 @@ int spb_test_field_op(spb_ctx* ctx, int field, int op, const spb_fr* a, const sp
 /* modular-multiply throughput microbenchmark: `iters` dependent products per thread over `threads` threads;
  * returns device milliseconds in *ms. */
 int spb_bench_modmul(spb_ctx* ctx, int field, uint32_t threads, uint32_t iters, int ilp, float* ms);
+/* raw issue-rate probe of one pipe (8 independent chains per thread, `iters` x 8 instructions each):
+ * kind 0 IMAD.WIDE, 1 IMAD, 2 DFMA, 3 IMAD.WIDE+DFMA interleaved, 4 IADD, 5 IMAD.WIDE+IADD interleaved. */
+int spb_bench_pipe(spb_ctx* ctx, int kind, uint32_t threads, uint32_t iters, float* ms);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -71,6 +71,31 @@ __global__ void modmul_bench_kernel(Fp<P>* out, uint32_t iters) {
   out[tid] = acc;
 }
 
+// Raw pipe-rate probes (8 independent chains per thread): 0 = IMAD.WIDE.U32, 1 = IMAD (lo), 2 = DFMA,
+// 3 = IMAD.WIDE + DFMA interleaved 1:1, 4 = IADD3, 5 = IMAD.WIDE + IADD3 interleaved 1:1
+template <int KIND>
+__global__ void pipe_probe_kernel(unsigned long long* out, uint32_t iters, uint32_t seed) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long w[8]; uint32_t v[8]; double f[8];
+  uint32_t a = tid * 2654435761u + seed, b = a ^ 0x9e3779b9u;
+  double fa = 1.0 + (double)(tid & 1023) * 1e-9, fb = 0.999999 + (double)(seed & 7) * 1e-9;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { w[j] = a + j; v[j] = b + j; f[j] = fa + j; }
+  for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (KIND == 0 || KIND == 3 || KIND == 5) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(a), "r"(b));
+      if (KIND == 1) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(v[j]) : "r"(a), "r"(b));
+      if (KIND == 2 || KIND == 3) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(f[j]) : "d"(fb), "d"(fa));
+      if (KIND == 4 || KIND == 5) asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(b));
+    }
+  }
+  unsigned long long acc = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc += w[j] + v[j] + (unsigned long long)__double_as_longlong(f[j]);
+  out[tid] = acc;
+}
+
 extern "C" {
 
 int spb_device_count(void) {
@@ -345,6 +370,32 @@ int spb_test_field_op(spb_ctx* ctx, int field, int op, const spb_fr* a, const sp
   ctx->n_kernel_launches++;
   SPB_CUDA(ctx, cudaMemcpyAsync(out, buf + 2 * n, n * 32, cudaMemcpyDeviceToHost, d.stream));
   SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_bench_pipe(spb_ctx* ctx, int kind, uint32_t threads, uint32_t iters, float* ms) {
+  if (!ctx || !ms) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  threads = (threads + 255) / 256 * 256;
+  unsigned long long* buf = (unsigned long long*)slot(ctx, d, "test_io", (size_t)threads * 8);
+  if (!buf) return SPB_ERR_OOM;
+  unsigned blocks = threads / 256;
+  SPB_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+  switch (kind) {
+    case 0: pipe_probe_kernel<0><<<blocks, 256, 0, d.stream>>>(buf, iters, 1); break;
+    case 1: pipe_probe_kernel<1><<<blocks, 256, 0, d.stream>>>(buf, iters, 1); break;
+    case 2: pipe_probe_kernel<2><<<blocks, 256, 0, d.stream>>>(buf, iters, 1); break;
+    case 3: pipe_probe_kernel<3><<<blocks, 256, 0, d.stream>>>(buf, iters, 1); break;
+    case 4: pipe_probe_kernel<4><<<blocks, 256, 0, d.stream>>>(buf, iters, 1); break;
+    default: pipe_probe_kernel<5><<<blocks, 256, 0, d.stream>>>(buf, iters, 1); break;
+  }
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  SPB_CUDA(ctx, cudaEventElapsedTime(ms, d.ev0, d.ev1));
   return 0;
 }
 

@@ -213,6 +213,14 @@ class Backend:
         return ms.value, threads * iters * ilp / (ms.value * 1e-3)
 
 
+    def bench_pipe(self, kind, threads=148 * 2048, iters=4000):
+        """-> (ms, instructions of the probed kind per second; for interleaved kinds: pairs per second)"""
+        ms = ctypes.c_float(0)
+        self.check(self.lib.spb_bench_pipe(self.ctx, kind, ctypes.c_uint32(threads), ctypes.c_uint32(iters), ctypes.byref(ms)), "spb_bench_pipe")
+        threads = (threads + 255) // 256 * 256
+        return ms.value, threads * iters * 8 / (ms.value * 1e-3)
+
+
 class EvaluationDomain:
     """EvaluationDomain::<Fr>::new(j, k) ([UPSTREAM] halo2_proofs/src/poly/domain.rs)."""
 

@@ -30,6 +30,13 @@ def main():
                     be.bench_modmul(field, 148 * tpsm, 200, ilp)
                     ms, rate = be.bench_modmul(field, 148 * tpsm, 2000, ilp)
                     print(json.dumps({"bench": "modmul", "field": field, "ilp": ilp, "threads_per_sm": tpsm, "ms": round(ms, 3), "gmul_per_s": round(rate / 1e9, 2)}), flush=True)
+    if "pipe" in what:
+        names = {0: "IMAD.WIDE.U32", 1: "IMAD", 2: "DFMA", 3: "IMAD.WIDE+DFMA (pairs)", 4: "IADD", 5: "IMAD.WIDE+IADD (pairs)"}
+        for kind in range(6):
+            be.bench_pipe(kind, 148 * 2048, 500)
+            ms, rate = be.bench_pipe(kind, 148 * 2048, 4000)
+            print(json.dumps({"bench": "pipe", "kind": names[kind], "ms": round(ms, 3), "tera_inst_per_s": round(rate / 1e12, 3),
+                              "lanes_per_clk_per_sm_at_1.9GHz": round(rate / 148 / 1.9e9, 1)}), flush=True)
     if "ntt" in what:
         import torch
         root = pow(7, (R_MOD - 1) >> 28, R_MOD)
