@@ -86,14 +86,23 @@ int spb_msm_raw(spb_ctx* ctx, const spb_fr* scalars, const spb_g1_affine* bases,
 int spb_msm(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* scalars, size_t n, spb_g1* out);
 /* same with the scalars already resident on device 0 of the context */
 int spb_msm_dev(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* d_scalars, size_t n, spb_g1* out);
+/* `count` MSMs of n scalars each against the same resident basis (create_proof commits its advice / permutation /
+ * lookup columns back to back against g_lagrange). Consecutive MSMs alternate between two stream lanes so the
+ * latency-bound tail of one overlaps the sort + accumulation of the next; out[i] belongs to scalars[i]. */
+int spb_msm_batch(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* const* scalars, size_t n, size_t count, spb_g1* out);
+int spb_msm_batch_dev(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* const* d_scalars, size_t n, size_t count, spb_g1* out);
+/* Precompute the 2^(c*j) multiples of the resident bases (W x the basis memory, one-time). Afterwards every MSM on
+ * this SRS folds all windows into one bucket set with a wider window (fewer mixed additions, no window Horner).
+ * Results are identical; only the schedule changes. */
+int spb_srs_precompute(spb_ctx* ctx, spb_srs* srs);
 /* number of G1 additions (mixed + full) the last MSM executed on the device(s) */
 uint64_t spb_last_msm_adds(spb_ctx* ctx);
 /* device milliseconds of the last MSM's stages on the context's first device, from CUDA events on the stream the
  * kernels ran on: [0] digit histogram, [1] bucket-offset scan, [2] scatter, [3] bucket accumulation (the dominant
  * kernel), [4] chain stitch, [5] segment running sums, [6] per-window sum. */
 void spb_last_msm_stage_ms(spb_ctx* ctx, float out[7]);
-/* window width c and window count the library uses for an n-pair MSM */
-void spb_msm_geometry(size_t n, uint32_t* c, uint32_t* windows);
+/* window width c and window count the library uses for an n-pair MSM (tables: with spb_srs_precompute) */
+void spb_msm_geometry(size_t n, int tables, uint32_t* c, uint32_t* windows);
 
 /* Sum of n Jacobian points on the host (folding the per-rank / per-device partial results of a sharded MSM after
  * the all-gather; EC addition is not an NCCL reduction). Result normalised to z = 1. No context needed. */

@@ -84,8 +84,9 @@ __global__ void pipe_probe_kernel(unsigned long long* out, uint32_t iters, uint3
   for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      if (KIND == 0 || KIND == 3 || KIND == 5) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(a), "r"(b));
-      if (KIND == 1) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(v[j]) : "r"(a), "r"(b));
+      // one multiplicand is the chain's own low word so the product is not loop-invariant
+      if (KIND == 0 || KIND == 3 || KIND == 5) asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(w[j]) : "r"(b));
+      if (KIND == 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(a), "r"(b));
       if (KIND == 2 || KIND == 3) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(f[j]) : "d"(fb), "d"(fa));
       if (KIND == 4 || KIND == 5) asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(b));
     }
@@ -129,6 +130,7 @@ spb_ctx* spb_init(const int* device_ids, int n_dev) {
 
 void spb_shutdown(spb_ctx* ctx) {
   if (!ctx) return;
+  msm_release_ctx(ctx);
   for (auto& d : ctx->dev) {
     cudaSetDevice(d.device);
     cudaStreamSynchronize(d.stream);

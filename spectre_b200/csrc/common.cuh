@@ -67,6 +67,9 @@ void* slot(spb_ctx* ctx, DeviceState& d, const char* name, size_t bytes);
     if (rc_ != 0) return rc_;    \
   } while (0)
 
+// ---- msm.cu ----
+void msm_release_ctx(spb_ctx* ctx);
+
 // ---- ntt.cu ----
 struct NttOpts {
   uint64_t n_in = 0, n_out = 0;  // 0 = n

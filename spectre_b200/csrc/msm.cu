@@ -10,12 +10,14 @@ using namespace spb;
 struct SrsShard {
   int dev_index = 0;
   size_t start = 0, count = 0;
+  // row 0 = the basis itself; with tables, rows 1..W-1 hold 2^(c*j) * P (row stride = count)
   G1Affine* g = nullptr;
   G1Affine* g_lagrange = nullptr;
 };
 struct spb_srs {
   uint32_t k = 0;
   size_t n = 0;
+  uint32_t table_c = 0;  // 0: no precomputed tables
   std::vector<SrsShard> shards;  // one per device of the context, contiguous point ranges
 };
 
@@ -23,69 +25,127 @@ static uint64_t g_last_adds = 0;
 
 namespace spb {
 
-// Enqueue one MSM on device `d` (no host synchronisation). Window sums land in d.pinned, followed by the
-// 32-bit number of sorted entries.
-static int msm_enqueue(spb_ctx* ctx, DeviceState& d, const Fr* d_scalars, const G1Affine* d_bases, uint64_t n, MsmGeom g) {
-  const uint64_t nb = (uint64_t)g.W * g.B;
-  const uint64_t cap = n * g.W;                 // upper bound on entries
-  const uint64_t Tmax = (cap + g.L - 1) / g.L;  // upper bound on chunks
-  if (cap >= 0xffffffffull) return set_error(ctx, SPB_ERR_ARG, "msm: %llu entries exceed the 32-bit sort index", (unsigned long long)cap);
-  uint32_t* counts = (uint32_t*)slot(ctx, d, "msm_counts", (nb + 1) * 4);
-  uint32_t* offsets = (uint32_t*)slot(ctx, d, "msm_offsets", (nb + 1) * 4);
-  uint32_t* ent_key = (uint32_t*)slot(ctx, d, "msm_ent_key", (cap + 1) * 4);
-  uint32_t* ent_val = (uint32_t*)slot(ctx, d, "msm_ent_val", (cap + 1) * 4);
-  G1Xyzz* buckets = (G1Xyzz*)slot(ctx, d, "msm_buckets", nb * sizeof(G1Xyzz));
-  uint32_t* head_key = (uint32_t*)slot(ctx, d, "msm_head_key", (Tmax + 1) * 4);
-  uint32_t* tail_key = (uint32_t*)slot(ctx, d, "msm_tail_key", (Tmax + 1) * 4);
-  G1Xyzz* head = (G1Xyzz*)slot(ctx, d, "msm_head", (Tmax + 1) * sizeof(G1Xyzz));
-  G1Xyzz* tail = (G1Xyzz*)slot(ctx, d, "msm_tail", (Tmax + 1) * sizeof(G1Xyzz));
-  uint32_t* giant = (uint32_t*)slot(ctx, d, "msm_giant", (Tmax + 2) * 4);  // [0] = count, [1..] = queue
-  const uint32_t s = g.B < 16 ? g.B : 16;
-  const uint32_t segs = g.B / s;
-  G1Xyzz* seg_out = (G1Xyzz*)slot(ctx, d, "msm_seg", (uint64_t)g.W * segs * sizeof(G1Xyzz));
-  G1Xyzz* win_out = (G1Xyzz*)slot(ctx, d, "msm_win", (uint64_t)g.W * sizeof(G1Xyzz));
-  size_t scan_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, offsets, (int)(nb + 1), d.stream);
-  void* scan_tmp = slot(ctx, d, "msm_scan_tmp", scan_bytes ? scan_bytes : 16);
-  if (!counts || !offsets || !ent_key || !ent_val || !buckets || !head_key || !tail_key || !head || !tail || !giant || !seg_out || !win_out || !scan_tmp)
-    return SPB_ERR_OOM;
-  if ((size_t)g.W * sizeof(G1Xyzz) + 16 > d.pinned_cap) return set_error(ctx, SPB_ERR_STATE, "msm: pinned staging too small");
+// Two independent lanes per device (own stream, workspace slots, pinned result area): consecutive MSMs of a batch
+// alternate lanes so the latency-bound tail of one (stitch / running sums / host Horner) overlaps the sort and
+// accumulation of the next.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* pinned = nullptr;
+  bool ready = false;
+};
+static std::map<std::pair<spb_ctx*, int>, std::vector<Lane>> g_lanes;
 
-  SPB_CUDA(ctx, cudaMemsetAsync(counts, 0, (nb + 1) * 4, d.stream));
-  SPB_CUDA(ctx, cudaMemsetAsync(buckets, 0, nb * sizeof(G1Xyzz), d.stream));
-  SPB_CUDA(ctx, cudaMemsetAsync(giant, 0, 4, d.stream));
-  const unsigned tb = 256;
-  cudaEventRecord(d.stage_ev[0], d.stream);
-  msm_count_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, d.stream>>>(n, d_scalars, g, counts);
-  cudaEventRecord(d.stage_ev[1], d.stream);
-  SPB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts, offsets, (int)(nb + 1), d.stream));
-  // cursor := offsets (the counters are dead after the scan; reuse their storage)
-  SPB_CUDA(ctx, cudaMemcpyAsync(counts, offsets, (nb + 1) * 4, cudaMemcpyDeviceToDevice, d.stream));
-  cudaEventRecord(d.stage_ev[2], d.stream);
-  msm_scatter_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, d.stream>>>(n, d_scalars, g, counts, ent_key, ent_val);
-  const uint32_t* total = offsets + nb;  // number of entries M, resident on the device
-  cudaEventRecord(d.stage_ev[3], d.stream);
-  msm_accumulate_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, d.stream>>>(total, g, ent_key, ent_val, d_bases, buckets, head_key, head, tail_key, tail);
-  cudaEventRecord(d.stage_ev[4], d.stream);
-  msm_stitch_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, d.stream>>>(total, g.L, 24, head_key, head, tail_key, tail, buckets, giant, giant + 1);
-  msm_giant_kernel<<<256, 128, 0, d.stream>>>(total, g.L, giant, giant + 1, head_key, head, tail_key, tail, buckets);
-  cudaEventRecord(d.stage_ev[5], d.stream);
-  msm_segment_kernel<<<(unsigned)(((uint64_t)g.W * segs + 127) / 128), 128, 0, d.stream>>>(g, s, buckets, seg_out);
-  cudaEventRecord(d.stage_ev[6], d.stream);
-  msm_window_kernel<<<g.W, 128, 0, d.stream>>>(segs, seg_out, win_out);
-  cudaEventRecord(d.stage_ev[7], d.stream);
-  SPB_CUDA(ctx, cudaGetLastError());
-  ctx->n_kernel_launches += 7;
-  SPB_CUDA(ctx, cudaMemcpyAsync(d.pinned, win_out, (size_t)g.W * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, d.stream));
-  SPB_CUDA(ctx, cudaMemcpyAsync((char*)d.pinned + (size_t)g.W * sizeof(G1Xyzz), total, 4, cudaMemcpyDeviceToHost, d.stream));
+static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
+  auto& v = g_lanes[std::make_pair(ctx, dev_index)];
+  if (v.size() < 2) v.resize(2);
+  Lane& l = v[lane_index];
+  if (!l.ready) {
+    SPB_CUDA(ctx, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 9; i++) SPB_CUDA(ctx, cudaEventCreate(&l.ev[i]));
+    SPB_CUDA(ctx, cudaMallocHost(&l.pinned, 64 * sizeof(G1Xyzz) + 64));
+    l.ready = true;
+  }
+  *out = &l;
   return 0;
 }
 
-static G1Xyzz msm_finish(DeviceState& d, MsmGeom g) {
-  const G1Xyzz* S = (const G1Xyzz*)d.pinned;
-  uint32_t M; memcpy(&M, (const char*)d.pinned + (size_t)g.W * sizeof(G1Xyzz), 4);
-  g_last_adds += (uint64_t)M + 2ull * g.W * g.B;
-  return msm_combine_windows(S, g.W, g.c);
+void msm_release_ctx(spb_ctx* ctx) {
+  for (auto it = g_lanes.begin(); it != g_lanes.end();) {
+    if (it->first.first != ctx) { ++it; continue; }
+    cudaSetDevice(ctx->dev[it->first.second].device);
+    for (auto& l : it->second) {
+      if (!l.ready) continue;
+      cudaStreamSynchronize(l.stream);
+      for (int i = 0; i < 9; i++) cudaEventDestroy(l.ev[i]);
+      cudaFreeHost(l.pinned);
+      cudaStreamDestroy(l.stream);
+    }
+    it = g_lanes.erase(it);
+  }
+}
+
+static void* lane_slot(spb_ctx* ctx, DeviceState& d, int lane, const char* name, size_t bytes) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "%s#%d", name, lane);
+  return slot(ctx, d, buf, bytes);
+}
+
+// chunk length such that the accumulation grid is close to a whole number of waves (148 SMs x 512 resident threads)
+static uint32_t choose_chunk(const DeviceState& d, uint64_t est_entries) {
+  const double wave = (double)d.sm_count * 512.0;
+  double waves = (double)est_entries / 32.0 / wave;
+  if (waves < 1.0) return 32;
+  double w = waves < 1.5 ? 1.0 : (double)(uint64_t)(waves + 0.5);
+  uint32_t L = (uint32_t)((double)est_entries / (w * wave)) + 1;
+  if (L < 24) L = 24;
+  if (L > 48) L = 48;
+  return L;
+}
+
+// Enqueue one MSM on lane `ln` of device `d` (no host synchronisation). The BW window sums land in the lane's
+// pinned area, followed by the 32-bit number of sorted entries.
+static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const Fr* d_scalars, const G1Affine* d_bases, uint64_t n, MsmGeom g) {
+  const uint64_t nb = (uint64_t)g.BW * g.B;
+  const uint64_t cap = n * g.W;                 // upper bound on entries
+  const uint64_t Tmax = (cap + g.L - 1) / g.L;  // upper bound on chunks
+  if (cap >= 0x7fffffffull) return set_error(ctx, SPB_ERR_ARG, "msm: %llu entries exceed the 31-bit sort index", (unsigned long long)cap);
+  uint32_t* counts = (uint32_t*)lane_slot(ctx, d, lane, "msm_counts", (nb + 1) * 4);
+  uint32_t* offsets = (uint32_t*)lane_slot(ctx, d, lane, "msm_offsets", (nb + 1) * 4);
+  MsmEntry* ent = (MsmEntry*)lane_slot(ctx, d, lane, "msm_entries", (cap + 1) * sizeof(MsmEntry));
+  G1Xyzz* buckets = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_buckets", nb * sizeof(G1Xyzz));
+  uint32_t* head_key = (uint32_t*)lane_slot(ctx, d, lane, "msm_head_key", (Tmax + 1) * 4);
+  uint32_t* tail_key = (uint32_t*)lane_slot(ctx, d, lane, "msm_tail_key", (Tmax + 1) * 4);
+  G1Xyzz* head = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_head", (Tmax + 1) * sizeof(G1Xyzz));
+  G1Xyzz* tail = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_tail", (Tmax + 1) * sizeof(G1Xyzz));
+  uint32_t* giant = (uint32_t*)lane_slot(ctx, d, lane, "msm_giant", (Tmax + 2) * 4);  // [0] = count, [1..] = queue
+  const uint32_t s = g.B < 16 ? g.B : 16;
+  const uint32_t segs = g.B / s;
+  G1Xyzz* seg_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_seg", (uint64_t)g.BW * segs * sizeof(G1Xyzz));
+  G1Xyzz* win_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_win", (uint64_t)g.BW * sizeof(G1Xyzz));
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, offsets, (int)(nb + 1), ln.stream);
+  void* scan_tmp = lane_slot(ctx, d, lane, "msm_scan_tmp", scan_bytes ? scan_bytes : 16);
+  if (!counts || !offsets || !ent || !buckets || !head_key || !tail_key || !head || !tail || !giant || !seg_out || !win_out || !scan_tmp)
+    return SPB_ERR_OOM;
+  if (g.BW > 64) return set_error(ctx, SPB_ERR_STATE, "msm: %u bucket windows exceed the pinned staging area", g.BW);
+
+  cudaStream_t st = ln.stream;
+  SPB_CUDA(ctx, cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
+  SPB_CUDA(ctx, cudaMemsetAsync(buckets, 0, nb * sizeof(G1Xyzz), st));
+  SPB_CUDA(ctx, cudaMemsetAsync(giant, 0, 4, st));
+  const unsigned tb = 256;
+  cudaEventRecord(ln.ev[0], st);
+  msm_count_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(n, d_scalars, g, counts);
+  cudaEventRecord(ln.ev[1], st);
+  SPB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts, offsets, (int)(nb + 1), st));
+  // cursor := offsets (the counters are dead after the scan; reuse their storage)
+  SPB_CUDA(ctx, cudaMemcpyAsync(counts, offsets, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  cudaEventRecord(ln.ev[2], st);
+  msm_scatter_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(n, d_scalars, g, counts, ent);
+  const uint32_t* total = offsets + nb;  // number of entries M, resident on the device
+  cudaEventRecord(ln.ev[3], st);
+  msm_accumulate_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g, ent, d_bases, buckets, head_key, head, tail_key, tail);
+  cudaEventRecord(ln.ev[4], st);
+  msm_stitch_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g.L, 24, head_key, head, tail_key, tail, buckets, giant, giant + 1);
+  msm_giant_kernel<<<256, 128, 0, st>>>(total, g.L, giant, giant + 1, head_key, head, tail_key, tail, buckets);
+  cudaEventRecord(ln.ev[5], st);
+  msm_segment_kernel<<<(unsigned)(((uint64_t)g.BW * segs + 127) / 128), 128, 0, st>>>(g, s, buckets, seg_out);
+  cudaEventRecord(ln.ev[6], st);
+  msm_window_kernel<<<g.BW, 128, 0, st>>>(segs, seg_out, win_out);
+  cudaEventRecord(ln.ev[7], st);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches += 7;
+  SPB_CUDA(ctx, cudaMemcpyAsync(ln.pinned, win_out, (size_t)g.BW * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(ctx, cudaMemcpyAsync((char*)ln.pinned + (size_t)g.BW * sizeof(G1Xyzz), total, 4, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+static G1Xyzz msm_finish(Lane& ln, MsmGeom g) {
+  const G1Xyzz* S = (const G1Xyzz*)ln.pinned;
+  uint32_t M; memcpy(&M, (const char*)ln.pinned + (size_t)g.BW * sizeof(G1Xyzz), 4);
+  g_last_adds += (uint64_t)M + 2ull * g.BW * g.B;
+  return msm_combine_windows(S, g.BW, g.c);
 }
 
 static void write_result(const G1Xyzz& r, spb_g1* out) {
@@ -96,36 +156,50 @@ static void write_result(const G1Xyzz& r, spb_g1* out) {
 
 struct MsmPart {
   int dev_index;
-  const Fr* d_scalars;      // device pointer on that device
+  const Fr* d_scalars;      // device pointer on that device (nullptr: copy from h_scalars on the lane's stream)
+  const Fr* h_scalars;      // host pointer for this part, or nullptr
+  int peer_src_device;      // >= 0: d_scalars lives on that device and must be peer-copied
   const G1Affine* d_bases;  // device pointer on that device
   uint64_t n;
+  MsmGeom g;
 };
 
-// Run the parts (one per device) concurrently and fold the partial sums on the host.
-static int msm_run_parts(spb_ctx* ctx, const std::vector<MsmPart>& parts, spb_g1* out) {
-  g_last_adds = 0;
-  std::vector<MsmGeom> geoms(parts.size());
-  for (size_t i = 0; i < parts.size(); i++) {
-    if (!parts[i].n) continue;
-    DeviceState& d = ctx->dev[parts[i].dev_index];
+// One job = one MSM = one part per device, all on lane `lane`. enqueue -> (later) collect.
+static int job_enqueue(spb_ctx* ctx, int lane, std::vector<MsmPart>& parts) {
+  for (auto& p : parts) {
+    if (!p.n) continue;
+    DeviceState& d = ctx->dev[p.dev_index];
     SPB_CUDA(ctx, cudaSetDevice(d.device));
-    geoms[i] = msm_choose_geometry(parts[i].n);
-    SPB_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
-    SPB_TRY(msm_enqueue(ctx, d, parts[i].d_scalars, parts[i].d_bases, parts[i].n, geoms[i]));
-    SPB_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+    Lane* ln; SPB_TRY(get_lane(ctx, p.dev_index, lane, &ln));
+    p.g.L = choose_chunk(d, p.n * p.g.W);
+    const Fr* ds = p.d_scalars;
+    SPB_CUDA(ctx, cudaEventRecord(ln->ev[8], ln->stream));
+    if (p.h_scalars || p.peer_src_device >= 0) {
+      Fr* buf = (Fr*)lane_slot(ctx, d, lane, "msm_scalars", p.n * sizeof(Fr));
+      if (!buf) return SPB_ERR_OOM;
+      if (p.h_scalars) SPB_CUDA(ctx, cudaMemcpyAsync(buf, p.h_scalars, p.n * sizeof(Fr), cudaMemcpyHostToDevice, ln->stream));
+      else SPB_CUDA(ctx, cudaMemcpyPeerAsync(buf, d.device, p.d_scalars, p.peer_src_device, p.n * sizeof(Fr), ln->stream));
+      ds = buf;
+    }
+    SPB_TRY(msm_enqueue(ctx, d, lane, *ln, ds, p.d_bases, p.n, p.g));
   }
+  return 0;
+}
+
+static int job_collect(spb_ctx* ctx, int lane, const std::vector<MsmPart>& parts, spb_g1* out) {
   G1Xyzz acc = xyzz_identity();
   float worst = 0.f;
-  for (size_t i = 0; i < parts.size(); i++) {
-    if (!parts[i].n) continue;
-    DeviceState& d = ctx->dev[parts[i].dev_index];
+  for (auto& p : parts) {
+    if (!p.n) continue;
+    DeviceState& d = ctx->dev[p.dev_index];
     SPB_CUDA(ctx, cudaSetDevice(d.device));
-    SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    Lane* ln; SPB_TRY(get_lane(ctx, p.dev_index, lane, &ln));
+    SPB_CUDA(ctx, cudaStreamSynchronize(ln->stream));
     float ms = 0.f;
-    SPB_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+    SPB_CUDA(ctx, cudaEventElapsedTime(&ms, ln->ev[8], ln->ev[7]));
     if (ms > worst) worst = ms;
-    if (parts[i].dev_index == 0) for (int e = 0; e < 7; e++) cudaEventElapsedTime(&ctx->msm_stage_ms[e], d.stage_ev[e], d.stage_ev[e + 1]);
-    G1Xyzz r = msm_finish(d, geoms[i]);
+    if (p.dev_index == 0) for (int e = 0; e < 7; e++) cudaEventElapsedTime(&ctx->msm_stage_ms[e], ln->ev[e], ln->ev[e + 1]);
+    G1Xyzz r = msm_finish(*ln, p.g);
     xyzz_add(acc, r);
   }
   ctx->last_kernel_ms = worst;
@@ -139,7 +213,7 @@ extern "C" {
 
 uint64_t spb_last_msm_adds(spb_ctx* ctx) { (void)ctx; return g_last_adds; }
 void spb_last_msm_stage_ms(spb_ctx* ctx, float out[7]) { for (int i = 0; i < 7; i++) out[i] = ctx ? ctx->msm_stage_ms[i] : 0.f; }
-void spb_msm_geometry(size_t n, uint32_t* c, uint32_t* windows) { MsmGeom g = msm_choose_geometry(n ? n : 1); *c = g.c; *windows = g.W; }
+void spb_msm_geometry(size_t n, int tables, uint32_t* c, uint32_t* windows) { MsmGeom g = msm_make_geometry(msm_choose_c(n ? n : 1, tables != 0), tables != 0, 0); *c = g.c; *windows = g.W; }
 
 // ---- ParamsKZG ---------------------------------------------------------------------------------------------
 static spb_srs* srs_alloc(spb_ctx* ctx, uint32_t k) {
@@ -253,6 +327,7 @@ int spb_srs_download(spb_ctx* ctx, const spb_srs* srs, int basis, size_t start, 
 int spb_msm_raw(spb_ctx* ctx, const spb_fr* scalars, const spb_g1_affine* bases, size_t n, spb_g1* out) {
   if (!ctx || !out || (n && (!scalars || !bases))) return SPB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  g_last_adds = 0;
   std::vector<MsmPart> parts;
   size_t D = ctx->dev.size();
   for (size_t i = 0; i < D; i++) {
@@ -260,49 +335,101 @@ int spb_msm_raw(spb_ctx* ctx, const spb_fr* scalars, const spb_g1_affine* bases,
     if (!cnt) continue;
     DeviceState& d = ctx->dev[i];
     SPB_CUDA(ctx, cudaSetDevice(d.device));
-    Fr* ds = (Fr*)slot(ctx, d, "msm_scalars", cnt * sizeof(Fr));
-    G1Affine* db = (G1Affine*)slot(ctx, d, "msm_bases", cnt * sizeof(G1Affine));
-    if (!ds || !db) return SPB_ERR_OOM;
-    SPB_CUDA(ctx, cudaMemcpyAsync(ds, (const Fr*)scalars + lo, cnt * sizeof(Fr), cudaMemcpyHostToDevice, d.stream));
-    SPB_CUDA(ctx, cudaMemcpyAsync(db, (const G1Affine*)bases + lo, cnt * sizeof(G1Affine), cudaMemcpyHostToDevice, d.stream));
-    parts.push_back(MsmPart{(int)i, ds, db, cnt});
+    Lane* ln; SPB_TRY(get_lane(ctx, (int)i, 0, &ln));
+    G1Affine* db = (G1Affine*)slot(ctx, d, "msm_raw_bases", cnt * sizeof(G1Affine));
+    if (!db) return SPB_ERR_OOM;
+    SPB_CUDA(ctx, cudaMemcpyAsync(db, (const G1Affine*)bases + lo, cnt * sizeof(G1Affine), cudaMemcpyHostToDevice, ln->stream));
+    MsmPart p; p.dev_index = (int)i; p.d_scalars = nullptr; p.h_scalars = (const Fr*)scalars + lo; p.peer_src_device = -1;
+    p.d_bases = db; p.n = cnt; p.g = msm_choose_geometry(cnt);
+    parts.push_back(p);
   }
-  return msm_run_parts(ctx, parts, out);
+  SPB_TRY(job_enqueue(ctx, 0, parts));
+  return job_collect(ctx, 0, parts, out);
 }
 
-static int msm_srs_common(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* scalars, bool scalars_on_device, size_t n, spb_g1* out) {
-  if (!ctx || !srs || !out || (n && !scalars)) return SPB_ERR_ARG;
+// parts of one SRS-backed MSM (one per shard that intersects [0, n))
+static int srs_parts(spb_ctx* ctx, const spb_srs* srs, int basis, const Fr* scalars, bool on_device, size_t n, std::vector<MsmPart>& parts) {
   if (n > srs->n) return set_error(ctx, SPB_ERR_ARG, "spb_msm: %zu scalars but the SRS has %zu points", n, srs->n);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  std::vector<MsmPart> parts;
   for (auto& sh : srs->shards) {
     if (sh.start >= n) continue;
     size_t cnt = (n - sh.start) < sh.count ? (n - sh.start) : sh.count;
     const G1Affine* b = basis == SPB_BASIS_G ? sh.g : sh.g_lagrange;
     if (!b) return set_error(ctx, SPB_ERR_STATE, "spb_msm: basis %d not resident", basis);
-    DeviceState& d = ctx->dev[sh.dev_index];
-    SPB_CUDA(ctx, cudaSetDevice(d.device));
-    const Fr* ds;
-    if (scalars_on_device && sh.dev_index == 0) {
-      ds = (const Fr*)scalars + sh.start;
-    } else {
-      Fr* buf = (Fr*)slot(ctx, d, "msm_scalars", cnt * sizeof(Fr));
-      if (!buf) return SPB_ERR_OOM;
-      // device-resident scalars live on device 0: peer copy for the other shards
-      if (scalars_on_device) SPB_CUDA(ctx, cudaMemcpyPeerAsync(buf, d.device, (const Fr*)scalars + sh.start, ctx->dev[0].device, cnt * sizeof(Fr), d.stream));
-      else SPB_CUDA(ctx, cudaMemcpyAsync(buf, (const Fr*)scalars + sh.start, cnt * sizeof(Fr), cudaMemcpyHostToDevice, d.stream));
-      ds = buf;
-    }
-    parts.push_back(MsmPart{sh.dev_index, ds, b, cnt});
+    MsmPart p; p.dev_index = sh.dev_index; p.d_bases = b; p.n = cnt; p.h_scalars = nullptr; p.d_scalars = nullptr; p.peer_src_device = -1;
+    if (!on_device) p.h_scalars = scalars + sh.start;
+    else { p.d_scalars = scalars + sh.start; if (sh.dev_index != 0) p.peer_src_device = ctx->dev[0].device; }
+    p.g = srs->table_c ? msm_make_geometry(srs->table_c, true, (uint32_t)sh.count) : msm_choose_geometry(cnt);
+    parts.push_back(p);
   }
-  return msm_run_parts(ctx, parts, out);
+  return 0;
+}
+
+static int msm_batch_common(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* const* scalars, bool on_device, size_t n, size_t count, spb_g1* out) {
+  if (!ctx || !srs || !out || (count && !scalars)) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  g_last_adds = 0;
+  std::vector<MsmPart> jobs[2];
+  for (size_t i = 0; i < count; i++) {
+    int lane = (int)(i & 1);
+    if (i >= 2) SPB_TRY(job_collect(ctx, lane, jobs[lane], &out[i - 2]));  // MSM i-2 ran on this lane
+    if (n && !scalars[i]) return SPB_ERR_ARG;
+    jobs[lane].clear();
+    SPB_TRY(srs_parts(ctx, srs, basis, (const Fr*)scalars[i], on_device, n, jobs[lane]));
+    SPB_TRY(job_enqueue(ctx, lane, jobs[lane]));
+  }
+  for (size_t i = count >= 2 ? count - 2 : 0; i < count; i++) SPB_TRY(job_collect(ctx, (int)(i & 1), jobs[i & 1], &out[i]));
+  return 0;
 }
 
 int spb_msm(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* scalars, size_t n, spb_g1* out) {
-  return msm_srs_common(ctx, srs, basis, scalars, false, n, out);
+  const spb_fr* one[1] = {scalars};
+  if (n && !scalars) return SPB_ERR_ARG;
+  return msm_batch_common(ctx, srs, basis, one, false, n, 1, out);
 }
 int spb_msm_dev(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* d_scalars, size_t n, spb_g1* out) {
-  return msm_srs_common(ctx, srs, basis, d_scalars, true, n, out);
+  const spb_fr* one[1] = {d_scalars};
+  if (n && !d_scalars) return SPB_ERR_ARG;
+  return msm_batch_common(ctx, srs, basis, one, true, n, 1, out);
+}
+int spb_msm_batch(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* const* scalars, size_t n, size_t count, spb_g1* out) {
+  return msm_batch_common(ctx, srs, basis, scalars, false, n, count, out);
+}
+int spb_msm_batch_dev(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* const* d_scalars, size_t n, size_t count, spb_g1* out) {
+  return msm_batch_common(ctx, srs, basis, d_scalars, true, n, count, out);
+}
+
+// Build the 2^(c*j) multiples of both resident bases (c chosen for the full SRS length). Costs W x the basis
+// memory; every later spb_msm* on this SRS then uses ONE bucket set for all windows (fewer, larger windows:
+// W = 13 instead of 16 at k = 20) and needs no window Horner.
+int spb_srs_precompute(spb_ctx* ctx, spb_srs* srs) {
+  if (!ctx || !srs) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (srs->table_c) return 0;
+  size_t per_dev = srs->shards.empty() ? srs->n : srs->shards[0].count;
+  uint32_t c = msm_choose_c(per_dev ? per_dev : 1, true);
+  uint32_t W = (255 + c - 1) / c;
+  for (auto& sh : srs->shards) {
+    if (!sh.count) continue;
+    DeviceState& d = ctx->dev[sh.dev_index];
+    SPB_CUDA(ctx, cudaSetDevice(d.device));
+    if ((uint64_t)W * sh.count >= 0x7fffffffull) return set_error(ctx, SPB_ERR_ARG, "spb_srs_precompute: table index exceeds 31 bits");
+    for (int which = 0; which < 2; which++) {
+      G1Affine** slotp = which == 0 ? &sh.g : &sh.g_lagrange;
+      if (!*slotp) continue;
+      G1Affine* tab = nullptr;
+      cudaError_t e = cudaMalloc(&tab, (size_t)W * sh.count * sizeof(G1Affine));
+      if (e != cudaSuccess) return set_error(ctx, SPB_ERR_OOM, "spb_srs_precompute: cudaMalloc(%zu): %s", (size_t)W * sh.count * sizeof(G1Affine), cudaGetErrorString(e));
+      SPB_CUDA(ctx, cudaMemcpyAsync(tab, *slotp, sh.count * sizeof(G1Affine), cudaMemcpyDeviceToDevice, d.stream));
+      msm_precompute_kernel<<<(unsigned)((sh.count + 127) / 128), 128, 0, d.stream>>>(sh.count, c, W, tab);
+      ctx->n_kernel_launches++;
+      SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+      SPB_CUDA(ctx, cudaGetLastError());
+      cudaFree(*slotp);
+      *slotp = tab;
+    }
+  }
+  srs->table_c = c;
+  return 0;
 }
 
 int spb_g1_fixed_base_mul(spb_ctx* ctx, const spb_fr* scalars, size_t n, spb_g1_affine* out) {

@@ -37,10 +37,15 @@ namespace spb {
 
 struct MsmGeom {
   uint32_t c;        // window bits
-  uint32_t W;        // windows
-  uint32_t B;        // buckets per window = 2^(c-1)
+  uint32_t W;        // scalar windows
+  uint32_t B;        // buckets per bucket-window = 2^(c-1)
   uint32_t L;        // entries per accumulation chunk
+  uint32_t BW;       // bucket windows: W normally, 1 when the basis carries precomputed 2^(c*w) multiples
+  uint32_t precomp;  // 1: window w of point i uses table point w*tab_stride + i and ALL windows share one bucket set
+  uint32_t tab_stride;
 };
+
+struct alignas(8) MsmEntry { uint32_t key, val; };
 
 static const uint32_t kNoKey = 0xffffffffu;
 
@@ -86,13 +91,12 @@ SPB_HD void msm_count_thread(uint64_t tid, uint64_t n, const Fr* scalars, MsmGeo
     int32_t d = it.next();
     if (d == 0) continue;
     uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    spb_atomic_inc(&counts[w * g.B + mag - 1]);
+    spb_atomic_inc(&counts[(g.precomp ? 0u : w * g.B) + mag - 1]);
   }
 }
 
 // ---- step 3: scatter -----------------------------------------------------------------------------------
-SPB_HD void msm_scatter_thread(uint64_t tid, uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* cursor,
-                               uint32_t* ent_key, uint32_t* ent_val) {
+SPB_HD void msm_scatter_thread(uint64_t tid, uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* cursor, MsmEntry* ent) {
   if (tid >= n) return;
   Fr s = fp_from_mont(scalars[tid]);
   if (fp_is_zero(s)) return;
@@ -101,10 +105,10 @@ SPB_HD void msm_scatter_thread(uint64_t tid, uint64_t n, const Fr* scalars, MsmG
     int32_t d = it.next();
     if (d == 0) continue;
     uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    uint32_t key = w * g.B + mag - 1;
+    uint32_t key = (g.precomp ? 0u : w * g.B) + mag - 1;
     uint32_t pos = spb_atomic_inc(&cursor[key]);
-    ent_key[pos] = key;
-    ent_val[pos] = (uint32_t)tid | (d < 0 ? 0x80000000u : 0u);
+    MsmEntry e; e.key = key; e.val = ((uint32_t)tid + (g.precomp ? w * g.tab_stride : 0u)) | (d < 0 ? 0x80000000u : 0u);
+    ent[pos] = e;
   }
 }
 
@@ -128,19 +132,30 @@ SPB_HD G1Affine msm_load_point(const G1Affine* bases, uint32_t val) {
 //   head_key/head[tid]  first run when it started in an earlier chunk (kNoKey if none)
 //   tail_key/tail[tid]  last run when it continues into the next chunk, or a single-run chunk whose bucket
 //                       starts here and continues (chain start)                      (kNoKey if none)
-SPB_HD void msm_accumulate_thread(uint64_t tid, uint64_t M, MsmGeom g, const uint32_t* ent_key, const uint32_t* ent_val,
+SPB_HD MsmEntry msm_load_entry(const MsmEntry* p) {
+#if defined(__CUDA_ARCH__)
+  uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  MsmEntry e; e.key = v.x; e.val = v.y; return e;
+#else
+  return *p;
+#endif
+}
+
+SPB_HD void msm_accumulate_thread(uint64_t tid, uint64_t M, MsmGeom g, const MsmEntry* ent,
                                   const G1Affine* bases, G1Xyzz* buckets, uint32_t* head_key, G1Xyzz* head,
                                   uint32_t* tail_key, G1Xyzz* tail) {
   uint64_t lo = tid * g.L;
   if (lo >= M) return;
   uint64_t hi = lo + g.L < M ? lo + g.L : M;
   uint32_t hk = kNoKey, tk = kNoKey;
-  uint32_t cur = ent_key[lo];
-  bool run_started_before = lo > 0 && ent_key[lo - 1] == cur;  // the current run began in an earlier chunk
-  G1Xyzz acc = xyzz_from_affine(msm_load_point(bases, ent_val[lo]));
+  MsmEntry first = msm_load_entry(ent + lo);
+  uint32_t cur = first.key;
+  bool run_started_before = lo > 0 && msm_load_entry(ent + lo - 1).key == cur;  // the current run began in an earlier chunk
+  G1Xyzz acc = xyzz_from_affine(msm_load_point(bases, first.val));
   for (uint64_t e = lo + 1; e < hi; e++) {
-    uint32_t k = ent_key[e];
-    G1Affine p = msm_load_point(bases, ent_val[e]);
+    MsmEntry en = msm_load_entry(ent + e);
+    uint32_t k = en.key;
+    G1Affine p = msm_load_point(bases, en.val);
     if (k == cur) {
       xyzz_add_mixed(acc, p);
     } else {
@@ -152,7 +167,7 @@ SPB_HD void msm_accumulate_thread(uint64_t tid, uint64_t M, MsmGeom g, const uin
       acc = xyzz_from_affine(p);
     }
   }
-  bool continues = hi < M && ent_key[hi] == cur;
+  bool continues = hi < M && msm_load_entry(ent + hi).key == cur;
   if (continues) {
     if (run_started_before) { hk = cur; head[tid] = acc; }  // middle link of a chain
     else { tk = cur; tail[tid] = acc; }                     // chain start
@@ -185,7 +200,7 @@ SPB_HD void msm_stitch_thread(uint64_t tid, uint64_t T, uint32_t cap, const uint
 // segment `seg` of window `w` covers bucket values b = seg*s + 1 .. seg*s + s; output = sum_b b * bucket[b]
 SPB_HD void msm_segment_thread(uint64_t tid, MsmGeom g, uint32_t s, const G1Xyzz* buckets, G1Xyzz* seg_out) {
   uint32_t segs = g.B / s;
-  if (tid >= (uint64_t)g.W * segs) return;
+  if (tid >= (uint64_t)g.BW * segs) return;
   uint32_t w = (uint32_t)(tid / segs), seg = (uint32_t)(tid % segs);
   const G1Xyzz* bk = buckets + (uint64_t)w * g.B + (uint64_t)seg * s;  // bk[j] holds value seg*s + j + 1
   G1Xyzz run = xyzz_identity(), res = xyzz_identity();
@@ -205,13 +220,13 @@ SPB_HD void msm_segment_thread(uint64_t tid, MsmGeom g, uint32_t s, const G1Xyzz
 __global__ void msm_count_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* counts) {
   msm_count_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, n, scalars, g, counts);
 }
-__global__ void msm_scatter_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* cursor, uint32_t* ent_key, uint32_t* ent_val) {
-  msm_scatter_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, n, scalars, g, cursor, ent_key, ent_val);
+__global__ void msm_scatter_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* cursor, MsmEntry* ent) {
+  msm_scatter_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, n, scalars, g, cursor, ent);
 }
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* total, MsmGeom g, const uint32_t* ent_key, const uint32_t* ent_val,
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* total, MsmGeom g, const MsmEntry* ent,
                                                              const G1Affine* bases, G1Xyzz* buckets, uint32_t* head_key, G1Xyzz* head,
                                                              uint32_t* tail_key, G1Xyzz* tail) {
-  msm_accumulate_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, *total, g, ent_key, ent_val, bases, buckets, head_key, head, tail_key, tail);
+  msm_accumulate_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, *total, g, ent, bases, buckets, head_key, head, tail_key, tail);
 }
 __global__ void __launch_bounds__(128) msm_stitch_kernel(const uint32_t* total, uint32_t L, uint32_t cap, const uint32_t* head_key, const G1Xyzz* head,
                                                          const uint32_t* tail_key, const G1Xyzz* tail, G1Xyzz* buckets, uint32_t* giant_count, uint32_t* giant_list) {
@@ -287,27 +302,50 @@ __global__ void srs_scalars_kernel(int mode, Fr s, Fr w, Fr coef, uint64_t start
 }
 #endif
 
-// ---- step 7 (host): Horner over windows ------------------------------------------------------------------
-inline G1Xyzz msm_combine_windows(const G1Xyzz* S, uint32_t W, uint32_t c) {
+// ---- step 7 (host): Horner over the bucket windows ------------------------------------------------------
+inline G1Xyzz msm_combine_windows(const G1Xyzz* S, uint32_t BW, uint32_t c) {
   G1Xyzz acc = xyzz_identity();
-  for (int w = (int)W - 1; w >= 0; w--) {
-    for (uint32_t i = 0; i < c; i++) acc = xyzz_dbl(acc);
+  for (int w = (int)BW - 1; w >= 0; w--) {
+    if (w != (int)BW - 1) for (uint32_t i = 0; i < c; i++) acc = xyzz_dbl(acc);
     xyzz_add(acc, S[w]);
   }
   return acc;
 }
 
-// window width minimising  n*W + 3.5 * W * 2^(c-1)  (mixed adds + weighted bucket-reduction adds)
-inline MsmGeom msm_choose_geometry(uint64_t n) {
-  MsmGeom best; best.c = 0; double best_cost = 0;
-  for (uint32_t c = 3; c <= 20; c++) {
+inline MsmGeom msm_make_geometry(uint32_t c, bool precomp, uint32_t tab_stride) {
+  MsmGeom g;
+  g.c = c; g.W = (255 + c - 1) / c; g.B = 1u << (c - 1); g.L = 32;
+  g.precomp = precomp ? 1 : 0; g.BW = precomp ? 1 : g.W; g.tab_stride = tab_stride;
+  return g;
+}
+
+// Window width minimising the modelled work in Montgomery products:
+//   10 * n * W  (mixed additions)  +  2 * 14 * BW * 2^(c-1)  (running sums over the buckets, full additions)
+// BW = W without precomputed tables, 1 with them (all windows share one bucket set).
+inline uint32_t msm_choose_c(uint64_t n, bool precomp) {
+  uint32_t best = 0; double best_cost = 0;
+  for (uint32_t c = 3; c <= 22; c++) {
     uint32_t W = (255 + c - 1) / c;
-    double cost = (double)n * W + 3.5 * W * (double)(1u << (c - 1));
-    if (!best.c || cost < best_cost) { best.c = c; best.W = W; best_cost = cost; }
+    double cost = 10.0 * (double)n * W + 28.0 * (precomp ? 1.0 : (double)W) * (double)(1u << (c - 1));
+    if (!best || cost < best_cost) { best = c; best_cost = cost; }
   }
-  best.B = 1u << (best.c - 1);
-  best.L = 32;
   return best;
 }
+inline MsmGeom msm_choose_geometry(uint64_t n) { return msm_make_geometry(msm_choose_c(n, false), false, 0); }
+
+// W-1 further table rows for point p: row j = 2^(c*j) * p, affine. Thread i handles base i.
+SPB_HD void msm_precompute_thread(uint64_t tid, uint64_t count, uint32_t c, uint32_t W, G1Affine* table /* W rows of `count` */) {
+  if (tid >= count) return;
+  G1Xyzz p = xyzz_from_affine(table[tid]);
+  for (uint32_t j = 1; j < W; j++) {
+    for (uint32_t i = 0; i < c; i++) p = xyzz_dbl(p);
+    table[(uint64_t)j * count + tid] = xyzz_to_affine(p);
+  }
+}
+#if defined(__CUDACC__) && defined(SPB_MSM_KERNELS)
+__global__ void __launch_bounds__(128) msm_precompute_kernel(uint64_t count, uint32_t c, uint32_t W, G1Affine* table) {
+  msm_precompute_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, count, c, W, table);
+}
+#endif
 
 }  // namespace spb

@@ -125,9 +125,9 @@ class Backend:
         self.lib.spb_last_msm_stage_ms(self.ctx, out)
         return dict(zip(("count", "scan", "scatter", "accumulate", "stitch", "segment", "window"), [float(v) for v in out]))
 
-    def msm_geometry(self, n):
+    def msm_geometry(self, n, tables=False):
         c = ctypes.c_uint32(); w = ctypes.c_uint32()
-        self.lib.spb_msm_geometry(ctypes.c_size_t(n), ctypes.byref(c), ctypes.byref(w))
+        self.lib.spb_msm_geometry(ctypes.c_size_t(n), ctypes.c_int(1 if tables else 0), ctypes.byref(c), ctypes.byref(w))
         return c.value, w.value
 
     # ---- arithmetic::best_fft --------------------------------------------------------------------------
@@ -328,6 +328,27 @@ class ParamsKZG:
 
     def commit_lagrange(self, poly, blind=None):
         return self._commit(BASIS_G_LAGRANGE, poly)
+
+    def precompute(self):
+        """Build the 2^(c*j) window tables of both bases (one-time, W x memory); later commits use one bucket set."""
+        self.be.check(self.be.lib.spb_srs_precompute(self.be.ctx, self.h), "spb_srs_precompute")
+        return self
+
+    def commit_batch(self, basis, polys):
+        """count commitments against one basis, pipelined on two stream lanes. polys: list of (n,4) host arrays."""
+        polys = [_fr_array(p) for p in polys]
+        n = polys[0].shape[0]
+        assert all(p.shape[0] == n for p in polys) and n <= self.n
+        ptrs = (ctypes.c_void_p * len(polys))(*[p.ctypes.data for p in polys])
+        out = np.empty((len(polys), 12), dtype=np.uint64)
+        self.be.check(self.be.lib.spb_msm_batch(self.be.ctx, self.h, basis, ptrs, ctypes.c_size_t(n), ctypes.c_size_t(len(polys)), _p(out)), "spb_msm_batch")
+        return out
+
+    def commit_batch_dev(self, basis, d_ptrs, n):
+        ptrs = (ctypes.c_void_p * len(d_ptrs))(*d_ptrs)
+        out = np.empty((len(d_ptrs), 12), dtype=np.uint64)
+        self.be.check(self.be.lib.spb_msm_batch_dev(self.be.ctx, self.h, basis, ptrs, ctypes.c_size_t(n), ctypes.c_size_t(len(d_ptrs)), _p(out)), "spb_msm_batch_dev")
+        return out
 
     def commit_dev(self, basis, d_ptr, n):
         out = np.empty(12, dtype=np.uint64)

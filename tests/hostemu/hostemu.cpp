@@ -37,26 +37,35 @@ void he_jac_roundtrip(G1Affine* out, const G1Affine* p) { G1Jac j = jac_from_aff
 #include "../../spectre_b200/csrc/msm.cuh"
 #include <vector>
 extern "C" {
-// c = 0: library's own geometry choice. Returns the number of sorted entries; *giants = number of chains that took
-// the block path.
-uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t n, uint32_t c, uint32_t L, uint32_t cap, uint32_t* giants) {
-  MsmGeom g = msm_choose_geometry(n ? n : 1);
-  if (c) { g.c = c; g.W = (255 + c - 1) / c; g.B = 1u << (c - 1); }
+// c = 0: library's own geometry choice. precomp = 1: build the 2^(c*j) tables first and use one bucket set.
+// Returns the number of sorted entries; *giants = number of chains that took the block path.
+uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t n, uint32_t c, uint32_t L, uint32_t cap, uint32_t* giants, int precomp) {
+  if (!c) c = msm_choose_c(n ? n : 1, precomp != 0);
+  MsmGeom g = msm_make_geometry(c, precomp != 0, (uint32_t)n);
   if (L) g.L = L;
-  uint64_t nb = (uint64_t)g.W * g.B;
+  std::vector<G1Affine> table;
+  const G1Affine* pts = bases;
+  if (precomp) {
+    table.resize((size_t)g.W * n);
+    for (size_t i = 0; i < n; i++) table[i] = bases[i];
+    for (uint64_t t = 0; t < n; t++) msm_precompute_thread(t, n, g.c, g.W, table.data());
+    pts = table.data();
+  }
+  uint64_t nb = (uint64_t)g.BW * g.B;
   std::vector<uint32_t> counts(nb + 1, 0), offsets(nb + 1, 0);
   for (uint64_t t = 0; t < n; t++) msm_count_thread(t, n, scalars, g, counts.data());
   uint64_t run = 0;
   for (uint64_t i = 0; i <= nb; i++) { offsets[i] = (uint32_t)run; run += counts[i]; }
   uint64_t M = offsets[nb];
-  std::vector<uint32_t> cursor(offsets), ek(M + 1), ev(M + 1);
-  for (uint64_t t = 0; t < n; t++) msm_scatter_thread(t, n, scalars, g, cursor.data(), ek.data(), ev.data());
+  std::vector<uint32_t> cursor(offsets);
+  std::vector<MsmEntry> ent(M + 1);
+  for (uint64_t t = 0; t < n; t++) msm_scatter_thread(t, n, scalars, g, cursor.data(), ent.data());
   std::vector<G1Xyzz> buckets(nb);
   memset(buckets.data(), 0, nb * sizeof(G1Xyzz));
   uint64_t T = (M + g.L - 1) / g.L;
   std::vector<uint32_t> hk(T + 1, 0x12345678u), tk(T + 1, 0x12345678u), glist(T + 2);
   std::vector<G1Xyzz> head(T + 1), tail(T + 1);
-  for (uint64_t t = 0; t < T; t++) msm_accumulate_thread(t, M, g, ek.data(), ev.data(), bases, buckets.data(), hk.data(), head.data(), tk.data(), tail.data());
+  for (uint64_t t = 0; t < T; t++) msm_accumulate_thread(t, M, g, ent.data(), pts, buckets.data(), hk.data(), head.data(), tk.data(), tail.data());
   uint32_t gcount = 0;
   for (uint64_t t = 0; t < T; t++) msm_stitch_thread(t, T, cap, hk.data(), head.data(), tk.data(), tail.data(), buckets.data(), &gcount, glist.data());
   for (uint32_t gi = 0; gi < gcount; gi++) {  // what msm_giant_kernel does, serially
@@ -68,11 +77,11 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
   }
   if (giants) *giants = gcount;
   uint32_t s = g.B < 16 ? g.B : 16, segs = g.B / s;
-  std::vector<G1Xyzz> seg((uint64_t)g.W * segs), win(g.W);
-  for (uint64_t t = 0; t < (uint64_t)g.W * segs; t++) msm_segment_thread(t, g, s, buckets.data(), seg.data());
-  for (uint32_t w = 0; w < g.W; w++) { G1Xyzz a = xyzz_identity(); for (uint32_t j = 0; j < segs; j++) xyzz_add(a, seg[(uint64_t)w * segs + j]); win[w] = a; }
-  *out = xyzz_to_affine(msm_combine_windows(win.data(), g.W, g.c));
+  std::vector<G1Xyzz> seg((uint64_t)g.BW * segs), win(g.BW);
+  for (uint64_t t = 0; t < (uint64_t)g.BW * segs; t++) msm_segment_thread(t, g, s, buckets.data(), seg.data());
+  for (uint32_t w = 0; w < g.BW; w++) { G1Xyzz a = xyzz_identity(); for (uint32_t j = 0; j < segs; j++) xyzz_add(a, seg[(uint64_t)w * segs + j]); win[w] = a; }
+  *out = xyzz_to_affine(msm_combine_windows(win.data(), g.BW, g.c));
   return M;
 }
-void he_geometry(uint64_t n, uint32_t* c, uint32_t* W) { MsmGeom g = msm_choose_geometry(n); *c = g.c; *W = g.W; }
+void he_geometry(uint64_t n, int precomp, uint32_t* c, uint32_t* W) { MsmGeom g = msm_make_geometry(msm_choose_c(n, precomp != 0), precomp != 0, 0); *c = g.c; *W = g.W; }
 }

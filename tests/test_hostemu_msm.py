@@ -14,12 +14,12 @@ def he():
     return _build("libhostemu_ptx.so", ["-DSPB_EMULATE_PTX"])
 
 
-def he_msm(he, scalars, bases, c=0, L=0, cap=24):
+def he_msm(he, scalars, bases, c=0, L=0, cap=24, precomp=0):
     scalars = np.ascontiguousarray(scalars, dtype=np.uint64); bases = np.ascontiguousarray(bases, dtype=np.uint64)
     out = np.empty(8, dtype=np.uint64)
     giants = ctypes.c_uint32(0)
     he.he_msm.restype = ctypes.c_uint64
-    M = he.he_msm(_p(out), _p(scalars), _p(bases), ctypes.c_size_t(scalars.shape[0]), ctypes.c_uint32(c), ctypes.c_uint32(L), ctypes.c_uint32(cap), ctypes.byref(giants))
+    M = he.he_msm(_p(out), _p(scalars), _p(bases), ctypes.c_size_t(scalars.shape[0]), ctypes.c_uint32(c), ctypes.c_uint32(L), ctypes.c_uint32(cap), ctypes.byref(giants), ctypes.c_int(precomp))
     return out, int(M), giants.value
 
 
@@ -36,8 +36,12 @@ def points(orc):
 @pytest.mark.parametrize("n,c,L", [(1, 0, 0), (2, 3, 2), (7, 4, 3), (33, 5, 4), (100, 8, 32), (257, 7, 5), (600, 10, 32), (600, 0, 0), (600, 16, 32), (64, 20, 8)])
 def test_uniform_scalars(he, orc, points, n, c, L):
     sc = orc.fr_random_chacha(n, 0x5eed0003 + n)
+    want = oracle_affine(orc, sc, points[:n])
     got, M, _ = he_msm(he, sc, points[:n], c, L)
-    assert np.array_equal(got, oracle_affine(orc, sc, points[:n]))
+    assert np.array_equal(got, want)
+    if c <= 12:  # precomputed 2^(c*j) tables, single bucket set
+        got, M, _ = he_msm(he, sc, points[:n], c, L, precomp=1)
+        assert np.array_equal(got, want)
 
 
 def test_against_python_ec(he, orc, points):
@@ -80,9 +84,9 @@ def test_edge_distributions(he, orc, points, label):
             ks.append(0 if u < 0.7 else int(rng.integers(0, 1 << 16)) if u < 0.9 else int(rng.integers(0, 1 << 62)) ** 2 % (1 << 104) if u < 0.99 else int(rng.integers(1, 1 << 62)) ** 4 % pyref.R_MOD)
     sc = orc.fr(ks)
     want = oracle_affine(orc, sc, bases)
-    for c, L, cap in ((0, 0, 24), (4, 3, 2), (9, 8, 1)):
-        got, M, giants = he_msm(he, sc, bases, c, L, cap)
-        assert np.array_equal(got, want), (label, c, L)
+    for c, L, cap, pre in ((0, 0, 24, 0), (4, 3, 2, 0), (9, 8, 1, 0), (6, 5, 3, 1), (0, 0, 24, 1)):
+        got, M, giants = he_msm(he, sc, bases, c, L, cap, pre)
+        assert np.array_equal(got, want), (label, c, L, pre)
     if label == "all_zero":
         assert M == 0 and not got.any()
     if label == "all_one":
@@ -93,7 +97,8 @@ def test_edge_distributions(he, orc, points, label):
 
 def test_geometry_choice(he):
     c = ctypes.c_uint32(); W = ctypes.c_uint32()
-    for n, lo, hi in ((1, 3, 8), (1 << 10, 6, 12), (1 << 20, 15, 17), (1 << 23, 16, 20), (1 << 24, 17, 20)):
-        he.he_geometry(ctypes.c_uint64(n), ctypes.byref(c), ctypes.byref(W))
+    for n, pre, lo, hi in ((1, 0, 3, 8), (1 << 10, 0, 6, 12), (1 << 20, 0, 15, 17), (1 << 23, 0, 16, 20), (1 << 24, 0, 17, 20),
+                           (1 << 20, 1, 19, 21), (1 << 23, 1, 21, 22)):
+        he.he_geometry(ctypes.c_uint64(n), ctypes.c_int(pre), ctypes.byref(c), ctypes.byref(W))
         # W*c >= 255 keeps one spare bit above the 254-bit scalar so the signed-digit carry never leaves the top window
         assert lo <= c.value <= hi and W.value * c.value >= 255 and (W.value - 1) * c.value < 255
