@@ -99,7 +99,7 @@ int spb_srs_precompute(spb_ctx* ctx, spb_srs* srs);
 uint64_t spb_last_msm_adds(spb_ctx* ctx);
 /* device milliseconds of the last MSM's stages on the context's first device, from CUDA events on the stream the
  * kernels ran on: [0] digit histogram, [1] bucket-offset scan, [2] scatter, [3] bucket accumulation (the dominant
- * kernel), [4] chain stitch, [5] segment running sums, [6] per-window sum. */
+ * kernel), [4] chain stitch, [5] row/column tree sums of the buckets, [6] weighted partial sums. */
 void spb_last_msm_stage_ms(spb_ctx* ctx, float out[7]);
 /* window width c and window count the library uses for an n-pair MSM (tables: with spb_srs_precompute) */
 void spb_msm_geometry(size_t n, int tables, uint32_t* c, uint32_t* windows);

@@ -135,7 +135,7 @@ void spb_shutdown(spb_ctx* ctx) {
     cudaSetDevice(d.device);
     cudaStreamSynchronize(d.stream);
     for (auto& kv : d.slots) if (kv.second.ptr) cudaFree(kv.second.ptr);
-    for (auto& t : d.ntt_tables) { cudaFree(t.tw_lo); cudaFree(t.tw_hi); }
+    for (auto& t : d.ntt_tables) { cudaFree(t.tw_lo); cudaFree(t.tw_hi); if (t.tw_full) cudaFree(t.tw_full); }
     if (d.pinned) cudaFreeHost(d.pinned);
     cudaEventDestroy(d.ev0); cudaEventDestroy(d.ev1);
     for (int e = 0; e < 8; e++) cudaEventDestroy(d.stage_ev[e]);

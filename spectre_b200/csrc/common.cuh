@@ -24,6 +24,7 @@ struct NttTables {
   uint32_t k, h;
   Fr* tw_lo = nullptr;  // 2^h
   Fr* tw_hi = nullptr;  // 2^(k-h)
+  Fr* tw_full = nullptr;  // 2^k (optional)
 };
 
 struct DeviceState {

@@ -152,7 +152,9 @@ SPB_HD G1Xyzz xyzz_from_jac(const G1Jac& p) {
 // k*P for a small non-negative integer k (double-and-add, MSB first)
 SPB_HD G1Xyzz xyzz_mul_u32(const G1Xyzz& p, uint32_t k) {
   G1Xyzz r = xyzz_identity();
-  for (int i = 31; i >= 0; i--) {
+  int top = 31;
+  while (top >= 0 && !((k >> top) & 1)) top--;
+  for (int i = top; i >= 0; i--) {
     r = xyzz_dbl(r);
     if ((k >> i) & 1) xyzz_add(r, p);
   }

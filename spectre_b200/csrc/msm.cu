@@ -35,6 +35,7 @@ struct Lane {
   bool ready = false;
 };
 static std::map<std::pair<spb_ctx*, int>, std::vector<Lane>> g_lanes;
+static const size_t kLanePinnedBytes = 256 * 1024;  // window partials of one MSM (<= 128 windows x a few points)
 
 static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
   auto& v = g_lanes[std::make_pair(ctx, dev_index)];
@@ -43,7 +44,7 @@ static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
   if (!l.ready) {
     SPB_CUDA(ctx, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 9; i++) SPB_CUDA(ctx, cudaEventCreate(&l.ev[i]));
-    SPB_CUDA(ctx, cudaMallocHost(&l.pinned, 64 * sizeof(G1Xyzz) + 64));
+    SPB_CUDA(ctx, cudaMallocHost(&l.pinned, kLanePinnedBytes));
     l.ready = true;
   }
   *out = &l;
@@ -99,16 +100,16 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   G1Xyzz* head = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_head", (Tmax + 1) * sizeof(G1Xyzz));
   G1Xyzz* tail = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_tail", (Tmax + 1) * sizeof(G1Xyzz));
   uint32_t* giant = (uint32_t*)lane_slot(ctx, d, lane, "msm_giant", (Tmax + 2) * 4);  // [0] = count, [1..] = queue
-  const uint32_t s = g.B < 16 ? g.B : 16;
-  const uint32_t segs = g.B / s;
-  G1Xyzz* seg_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_seg", (uint64_t)g.BW * segs * sizeof(G1Xyzz));
-  G1Xyzz* win_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_win", (uint64_t)g.BW * sizeof(G1Xyzz));
+  const MsmTail tl = msm_tail_shape(g.c);
+  const uint32_t R = 1u << tl.r_log, C = 1u << tl.c_log, per = 2 * tl.nbr + tl.nbc;
+  G1Xyzz* seg_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_rowcol", (uint64_t)g.BW * (R + C) * sizeof(G1Xyzz));
+  G1Xyzz* win_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_partials", (uint64_t)g.BW * per * sizeof(G1Xyzz));
   size_t scan_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, offsets, (int)(nb + 1), ln.stream);
   void* scan_tmp = lane_slot(ctx, d, lane, "msm_scan_tmp", scan_bytes ? scan_bytes : 16);
   if (!counts || !offsets || !ent || !buckets || !head_key || !tail_key || !head || !tail || !giant || !seg_out || !win_out || !scan_tmp)
     return SPB_ERR_OOM;
-  if (g.BW > 64) return set_error(ctx, SPB_ERR_STATE, "msm: %u bucket windows exceed the pinned staging area", g.BW);
+  if ((size_t)g.BW * per * sizeof(G1Xyzz) + 16 > kLanePinnedBytes) return set_error(ctx, SPB_ERR_STATE, "msm: %u window partials exceed the pinned staging area", g.BW * per);
 
   cudaStream_t st = ln.stream;
   SPB_CUDA(ctx, cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
@@ -130,22 +131,26 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   msm_stitch_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g.L, 24, head_key, head, tail_key, tail, buckets, giant, giant + 1);
   msm_giant_kernel<<<256, 128, 0, st>>>(total, g.L, giant, giant + 1, head_key, head, tail_key, tail, buckets);
   cudaEventRecord(ln.ev[5], st);
-  msm_segment_kernel<<<(unsigned)(((uint64_t)g.BW * segs + 127) / 128), 128, 0, st>>>(g, s, buckets, seg_out);
+  msm_rowcol_kernel<<<g.BW * (R + C), 128, 0, st>>>(g, tl, buckets, seg_out, seg_out + (uint64_t)g.BW * R);
   cudaEventRecord(ln.ev[6], st);
-  msm_window_kernel<<<g.BW, 128, 0, st>>>(segs, seg_out, win_out);
+  msm_weighted_kernel<<<g.BW * (tl.nbr + tl.nbc), 128, 0, st>>>(g, tl, seg_out, seg_out + (uint64_t)g.BW * R, win_out);
   cudaEventRecord(ln.ev[7], st);
   SPB_CUDA(ctx, cudaGetLastError());
   ctx->n_kernel_launches += 7;
-  SPB_CUDA(ctx, cudaMemcpyAsync(ln.pinned, win_out, (size_t)g.BW * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
-  SPB_CUDA(ctx, cudaMemcpyAsync((char*)ln.pinned + (size_t)g.BW * sizeof(G1Xyzz), total, 4, cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(ctx, cudaMemcpyAsync(ln.pinned, win_out, (size_t)g.BW * per * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(ctx, cudaMemcpyAsync((char*)ln.pinned + (size_t)g.BW * per * sizeof(G1Xyzz), total, 4, cudaMemcpyDeviceToHost, st));
   return 0;
 }
 
 static G1Xyzz msm_finish(Lane& ln, MsmGeom g) {
-  const G1Xyzz* S = (const G1Xyzz*)ln.pinned;
-  uint32_t M; memcpy(&M, (const char*)ln.pinned + (size_t)g.BW * sizeof(G1Xyzz), 4);
+  const MsmTail tl = msm_tail_shape(g.c);
+  const uint32_t per = 2 * tl.nbr + tl.nbc;
+  const G1Xyzz* P = (const G1Xyzz*)ln.pinned;
+  uint32_t M; memcpy(&M, (const char*)ln.pinned + (size_t)g.BW * per * sizeof(G1Xyzz), 4);
   g_last_adds += (uint64_t)M + 2ull * g.BW * g.B;
-  return msm_combine_windows(S, g.BW, g.c);
+  std::vector<G1Xyzz> S(g.BW);
+  for (uint32_t w = 0; w < g.BW; w++) S[w] = msm_tail_finish(g, P + (size_t)w * per);
+  return msm_combine_windows(S.data(), g.BW, g.c);
 }
 
 static void write_result(const G1Xyzz& r, spb_g1* out) {

@@ -196,21 +196,53 @@ SPB_HD void msm_stitch_thread(uint64_t tid, uint64_t T, uint32_t cap, const uint
   buckets[key] = acc;
 }
 
-// ---- step 6a: per-segment running sums -----------------------------------------------------------------
-// segment `seg` of window `w` covers bucket values b = seg*s + 1 .. seg*s + s; output = sum_b b * bucket[b]
-SPB_HD void msm_segment_thread(uint64_t tid, MsmGeom g, uint32_t s, const G1Xyzz* buckets, G1Xyzz* seg_out) {
-  uint32_t segs = g.B / s;
-  if (tid >= (uint64_t)g.BW * segs) return;
-  uint32_t w = (uint32_t)(tid / segs), seg = (uint32_t)(tid % segs);
-  const G1Xyzz* bk = buckets + (uint64_t)w * g.B + (uint64_t)seg * s;  // bk[j] holds value seg*s + j + 1
-  G1Xyzz run = xyzz_identity(), res = xyzz_identity();
-  for (int j = (int)s - 1; j >= 0; j--) {
-    xyzz_add(run, bk[j]);
-    xyzz_add(res, run);
+// ---- step 6: weighted bucket sum  S_w = sum_b (b+1) * bucket[w][b] ---------------------------------------------
+// The B buckets of a window are viewed as an R x C matrix (b = r*C + c). Then
+//   S_w = C * sum_r r*Row_r + sum_r Row_r + sum_c c*Col_c,   Row_r = sum_c X[r][c],  Col_c = sum_r X[r][c]
+// so the whole reduction is tree sums (log depth, fully parallel) plus scalar multiples by weights < 2^10 --
+// no running sum over tens of buckets and no 19-bit scalar multiple on the critical path.
+struct MsmTail {
+  uint32_t r_log, c_log;  // R = 2^r_log rows, C = 2^c_log columns, R*C = B
+  uint32_t nbr, nbc;      // blocks (of 128 items) covering the rows / the columns in the weighted pass
+};
+inline MsmTail msm_tail_shape(uint32_t c) {
+  MsmTail t; uint32_t bits = c - 1;
+  t.c_log = bits / 2; t.r_log = bits - t.c_log;
+  t.nbr = ((1u << t.r_log) + 127) / 128; t.nbc = ((1u << t.c_log) + 127) / 128;
+  return t;
+}
+// host-side reference of the two kernels below (tests/hostemu): partial layout per window = [A.., S.., D..]
+inline void msm_tail_host(const MsmGeom& g, const G1Xyzz* buckets, G1Xyzz* partials) {
+  MsmTail t = msm_tail_shape(g.c);
+  uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = 2 * t.nbr + t.nbc;
+  for (uint32_t w = 0; w < g.BW; w++) {
+    const G1Xyzz* X = buckets + (uint64_t)w * g.B;
+    G1Xyzz* out = partials + (uint64_t)w * per;
+    for (uint32_t i = 0; i < per; i++) out[i] = xyzz_identity();
+    for (uint32_t r = 0; r < R; r++) {
+      G1Xyzz row = xyzz_identity();
+      for (uint32_t c = 0; c < C; c++) xyzz_add(row, X[(uint64_t)r * C + c]);
+      G1Xyzz wr = xyzz_mul_u32(row, r);
+      xyzz_add(out[r / 128], wr);
+      xyzz_add(out[t.nbr + r / 128], row);
+    }
+    for (uint32_t c = 0; c < C; c++) {
+      G1Xyzz col = xyzz_identity();
+      for (uint32_t r = 0; r < R; r++) xyzz_add(col, X[(uint64_t)r * C + c]);
+      G1Xyzz wc = xyzz_mul_u32(col, c);
+      xyzz_add(out[2 * t.nbr + c / 128], wc);
+    }
   }
-  // res = sum (j+1) bk[j];  add (seg*s) * run
-  if (seg) { G1Xyzz off = xyzz_mul_u32(run, seg * s); xyzz_add(res, off); }
-  seg_out[tid] = res;
+}
+// host: window sum from its partials
+inline G1Xyzz msm_tail_finish(const MsmGeom& g, const G1Xyzz* part) {
+  MsmTail t = msm_tail_shape(g.c);
+  G1Xyzz A = xyzz_identity(), S = xyzz_identity(), D = xyzz_identity();
+  for (uint32_t i = 0; i < t.nbr; i++) { xyzz_add(A, part[i]); xyzz_add(S, part[t.nbr + i]); }
+  for (uint32_t i = 0; i < t.nbc; i++) xyzz_add(D, part[2 * t.nbr + i]);
+  for (uint32_t i = 0; i < t.c_log; i++) A = xyzz_dbl(A);
+  xyzz_add(A, S); xyzz_add(A, D);
+  return A;
 }
 
 #if defined(__CUDACC__) && defined(SPB_MSM_KERNELS)
@@ -264,18 +296,40 @@ __global__ void __launch_bounds__(128) msm_giant_kernel(const uint32_t* total, u
   }
 }
 
-__global__ void __launch_bounds__(128) msm_segment_kernel(MsmGeom g, uint32_t s, const G1Xyzz* buckets, G1Xyzz* seg_out) {
-  msm_segment_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, g, s, buckets, seg_out);
-}
-
-// one block per window: S_w = sum of its `segs` segment results
-__global__ void __launch_bounds__(128) msm_window_kernel(uint32_t segs, const G1Xyzz* seg_out, G1Xyzz* window_out) {
+// block (w, idx): idx < R -> row sum, else column sum
+__global__ void __launch_bounds__(128) msm_rowcol_kernel(MsmGeom g, MsmTail t, const G1Xyzz* buckets, G1Xyzz* row_out, G1Xyzz* col_out) {
   __shared__ G1Xyzz sh[64];
-  const G1Xyzz* p = seg_out + (uint64_t)blockIdx.x * segs;
+  const uint32_t R = 1u << t.r_log, C = 1u << t.c_log;
+  const uint32_t w = blockIdx.x / (R + C), idx = blockIdx.x % (R + C);
+  const G1Xyzz* X = buckets + (uint64_t)w * g.B;
   G1Xyzz acc = xyzz_identity();
-  for (uint32_t j = threadIdx.x; j < segs; j += 128) xyzz_add(acc, p[j]);
+  if (idx < R) { for (uint32_t c = threadIdx.x; c < C; c += 128) xyzz_add(acc, X[(uint64_t)idx * C + c]); }
+  else { const uint32_t col = idx - R; for (uint32_t r = threadIdx.x; r < R; r += 128) xyzz_add(acc, X[(uint64_t)r * C + col]); }
   block_sum_xyzz<128>(acc, sh);
-  if (threadIdx.x == 0) window_out[blockIdx.x] = acc;
+  if (threadIdx.x == 0) { if (idx < R) row_out[(uint64_t)w * R + idx] = acc; else col_out[(uint64_t)w * C + (idx - R)] = acc; }
+}
+// block (w, j): j < nbr -> rows [128 j, 128 j + 128): A partial (weights r) and S partial (plain); else columns: D partial
+__global__ void __launch_bounds__(128) msm_weighted_kernel(MsmGeom g, MsmTail t, const G1Xyzz* row_out, const G1Xyzz* col_out, G1Xyzz* partials) {
+  __shared__ G1Xyzz sh[64];
+  const uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = 2 * t.nbr + t.nbc;
+  const uint32_t w = blockIdx.x / (t.nbr + t.nbc), j = blockIdx.x % (t.nbr + t.nbc);
+  G1Xyzz* out = partials + (uint64_t)w * per;
+  if (j < t.nbr) {
+    uint32_t r = j * 128 + threadIdx.x;
+    G1Xyzz x = r < R ? row_out[(uint64_t)w * R + r] : xyzz_identity();
+    G1Xyzz wx = xyzz_mul_u32(x, r);
+    block_sum_xyzz<128>(wx, sh);
+    if (threadIdx.x == 0) out[j] = wx;
+    __syncthreads();
+    block_sum_xyzz<128>(x, sh);
+    if (threadIdx.x == 0) out[t.nbr + j] = x;
+  } else {
+    uint32_t c = (j - t.nbr) * 128 + threadIdx.x;
+    G1Xyzz x = c < C ? col_out[(uint64_t)w * C + c] : xyzz_identity();
+    G1Xyzz wx = xyzz_mul_u32(x, c);
+    block_sum_xyzz<128>(wx, sh);
+    if (threadIdx.x == 0) out[2 * t.nbr + (j - t.nbr)] = wx;
+  }
 }
 
 // out[i] = scalars[i] * G1 (affine): plain double-and-add per thread + one inversion. Setup / test utility.

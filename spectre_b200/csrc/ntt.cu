@@ -2,12 +2,24 @@
 #define SPB_NTT_KERNELS 1
 #include "common.cuh"
 #include "ntt.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace spb {
 
-static const uint32_t kMaxDigitBits = 10;     // largest sub-NTT held in one shared-memory tile
 static const uint32_t kTileElemsLog = 12;     // 4096 elements (~135 KB of limb planes) per tile
+// largest sub-NTT held in one shared-memory tile (11: two passes up to 2^22; the tile is then 2048 x 2 columns)
+static uint32_t max_digit_bits() {
+  static uint32_t v = 0;
+  if (!v) { const char* e = getenv("SPB_NTT_MAX_DIGIT"); v = e ? (uint32_t)atoi(e) : 11; if (v < 4) v = 4; if (v > 12) v = 12; }
+  return v;
+}
+// full omega^i tables are kept while their total stays under this many bytes per device (else two-level tables)
+static size_t full_table_budget() {
+  static size_t v = 0;
+  if (!v) { const char* e = getenv("SPB_NTT_FULL_TABLE_MB"); v = (e ? (size_t)atoll(e) : 6144) << 20; if (!v) v = 1; }
+  return v;
+}
 
 struct NttPlan {
   uint32_t npass;
@@ -16,6 +28,7 @@ struct NttPlan {
 
 static NttPlan make_plan(uint32_t k) {
   NttPlan p; memset(&p, 0, sizeof p);
+  const uint32_t kMaxDigitBits = max_digit_bits();
   if (k <= kMaxDigitBits) { p.npass = 1; p.s[0] = k; return p; }
   p.npass = (k + kMaxDigitBits - 1) / kMaxDigitBits;
   uint32_t rem = k;
@@ -38,10 +51,22 @@ static int get_tables(spb_ctx* ctx, DeviceState& d, uint32_t k, const Fr& omega,
   fr_pow_table_kernel<<<(unsigned)((nhi + 127) / 128), 128, 0, d.stream>>>(t.tw_hi, omega, nhi, h);
   SPB_CUDA(ctx, cudaGetLastError());
   ctx->n_kernel_launches += 2;
+  {
+    size_t used = 0;
+    for (auto& o : d.ntt_tables) if (o.tw_full) used += ((size_t)1 << o.k) * sizeof(Fr);
+    size_t need = ((size_t)1 << k) * sizeof(Fr);
+    if (k >= 12 && used + need <= full_table_budget() && cudaMalloc(&t.tw_full, need) == cudaSuccess) {
+      fr_pow_table_kernel<<<(unsigned)((((size_t)1 << k) + 127) / 128), 128, 0, d.stream>>>(t.tw_full, omega, (uint64_t)1 << k, 0);
+      ctx->n_kernel_launches++;
+    } else {
+      t.tw_full = nullptr;
+      cudaGetLastError();
+    }
+  }
   // a long-lived prover touches a handful of (k, omega) pairs; cap the cache anyway
   if (d.ntt_tables.size() >= 32) {
     cudaStreamSynchronize(d.stream);
-    cudaFree(d.ntt_tables.front().tw_lo); cudaFree(d.ntt_tables.front().tw_hi);
+    cudaFree(d.ntt_tables.front().tw_lo); cudaFree(d.ntt_tables.front().tw_hi); if (d.ntt_tables.front().tw_full) cudaFree(d.ntt_tables.front().tw_full);
     d.ntt_tables.erase(d.ntt_tables.begin());
   }
   d.ntt_tables.push_back(t);
@@ -72,7 +97,7 @@ int ntt_device(spb_ctx* ctx, DeviceState& d, const Fr* d_src, Fr* d_dst, uint32_
   uint32_t a = 0;
   for (uint32_t pi = 0; pi < plan.npass; pi++) {
     NttPassParams p; memset(&p, 0, sizeof p);
-    p.k = k; p.h = h; p.tw_lo = tb->tw_lo; p.tw_hi = tb->tw_hi;
+    p.k = k; p.h = h; p.tw_lo = tb->tw_lo; p.tw_hi = tb->tw_hi; p.tw_full = tb->tw_full;
     p.s = plan.s[pi]; p.a = a; p.b = k - a - p.s; p.s1 = plan.s[0];
     p.first = (pi == 0); p.last = (pi == plan.npass - 1);
     p.b_next = p.last ? 0 : p.b - plan.s[pi + 1];

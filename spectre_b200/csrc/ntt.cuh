@@ -34,6 +34,7 @@ struct NttPassParams {
   Fr* dst;
   const Fr* tw_lo;   // omega^i,           i < 2^h
   const Fr* tw_hi;   // omega^(i * 2^h),   i < 2^(k-h)
+  const Fr* tw_full; // omega^i, i < 2^k, or nullptr: every twiddle is then one load instead of a two-level product
   uint32_t k;        // log2 n
   uint32_t h;        // split of the two-level power table
   uint32_t s;        // log2 length of this pass's sub-NTT
@@ -97,6 +98,7 @@ __device__ __forceinline__ void ntt_stg(Fr* p, const Fr& v) {
 
 // omega^E through the two-level table (one product unless a level is trivial)
 __device__ __forceinline__ Fr ntt_omega_pow(const NttPassParams& p, uint64_t e) {
+  if (p.tw_full) return ntt_ldg(p.tw_full + e);
   uint64_t hi = e >> p.h, lo = e & ((1ull << p.h) - 1);
   if (lo == 0) return ntt_ldg(p.tw_hi + hi);
   Fr wl = ntt_ldg(p.tw_lo + lo);

@@ -123,7 +123,7 @@ class Backend:
     def last_msm_stage_ms(self):
         out = (ctypes.c_float * 7)()
         self.lib.spb_last_msm_stage_ms(self.ctx, out)
-        return dict(zip(("count", "scan", "scatter", "accumulate", "stitch", "segment", "window"), [float(v) for v in out]))
+        return dict(zip(("count", "scan", "scatter", "accumulate", "stitch", "rowcol", "weighted"), [float(v) for v in out]))
 
     def msm_geometry(self, n, tables=False):
         c = ctypes.c_uint32(); w = ctypes.c_uint32()

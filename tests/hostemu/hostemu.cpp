@@ -76,10 +76,11 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
     buckets[key] = acc;
   }
   if (giants) *giants = gcount;
-  uint32_t s = g.B < 16 ? g.B : 16, segs = g.B / s;
-  std::vector<G1Xyzz> seg((uint64_t)g.BW * segs), win(g.BW);
-  for (uint64_t t = 0; t < (uint64_t)g.BW * segs; t++) msm_segment_thread(t, g, s, buckets.data(), seg.data());
-  for (uint32_t w = 0; w < g.BW; w++) { G1Xyzz a = xyzz_identity(); for (uint32_t j = 0; j < segs; j++) xyzz_add(a, seg[(uint64_t)w * segs + j]); win[w] = a; }
+  MsmTail tl = msm_tail_shape(g.c);
+  uint32_t per = 2 * tl.nbr + tl.nbc;
+  std::vector<G1Xyzz> partials((uint64_t)g.BW * per), win(g.BW);
+  msm_tail_host(g, buckets.data(), partials.data());
+  for (uint32_t w = 0; w < g.BW; w++) win[w] = msm_tail_finish(g, partials.data() + (uint64_t)w * per);
   *out = xyzz_to_affine(msm_combine_windows(win.data(), g.BW, g.c));
   return M;
 }

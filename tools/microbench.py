@@ -40,7 +40,8 @@ def main():
     if "ntt" in what:
         import torch
         root = pow(7, (R_MOD - 1) >> 28, R_MOD)
-        for k in (12, 16, 18, 20, 22, 23, 24, 25, 26):
+        sizes = [int(a.split("=")[1]) for a in what if a.startswith("k=")] or [12, 16, 18, 20, 21, 22, 23, 24, 25, 26]
+        for k in sizes:
             w = pow(root, 1 << (28 - k), R_MOD) * (1 << 256) % R_MOD
             omega = np.array([[(w >> (64 * j)) & (2**64 - 1) for j in range(4)]], dtype=np.uint64)
             t = torch.from_numpy(rand_fr(1 << k, k).view(np.int64)).cuda()
