@@ -151,6 +151,19 @@ int spb_vec_mul(spb_ctx* ctx, spb_fr* a, const spb_fr* b, size_t n);            
 int spb_vec_axpy(spb_ctx* ctx, spb_fr* y, const spb_fr* alpha, const spb_fr* x, size_t n); /* y[i] += alpha*x[i] */
 int spb_vec_scale(spb_ctx* ctx, spb_fr* a, const spb_fr* alpha, size_t n);           /* a[i] *= alpha       */
 
+/* device-resident variants of the batch ops (pointers on device 0 of the context; scalars / results on the host) */
+int spb_batch_invert_dev(spb_ctx* ctx, spb_fr* d_a, size_t n);
+int spb_eval_polynomial_dev(spb_ctx* ctx, const spb_fr* d_poly, size_t n, const spb_fr* point, spb_fr* out);
+int spb_kate_division_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, const spb_fr* b, spb_fr* d_q);
+int spb_grand_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* d_z);
+int spb_vec_mul_dev(spb_ctx* ctx, spb_fr* d_a, const spb_fr* d_b, size_t n);
+int spb_vec_axpy_dev(spb_ctx* ctx, spb_fr* d_y, const spb_fr* alpha, const spb_fr* d_x, size_t n);
+int spb_vec_scale_dev(spb_ctx* ctx, spb_fr* d_a, const spb_fr* alpha, size_t n);
+/* d_out[i] = sum_p y^p * d_polys[p][i]: the fold-with-powers-of-y that evaluate_h, vanishing::evaluate and the
+ * SHPLONK opener apply to sets of polynomials. d_polys is a HOST array of `count` device pointers; d_out may alias
+ * none of them. One streaming pass over every input. */
+int spb_lincomb_dev(spb_ctx* ctx, const spb_fr* const* d_polys, size_t count, const spb_fr* y, spb_fr* d_out, size_t n);
+
 /* ---- test / bench utilities -------------------------------------------------------------------------------- */
 /* out[i] = scalars[i] * G1 (affine), computed on the device */
 int spb_g1_fixed_base_mul(spb_ctx* ctx, const spb_fr* scalars, size_t n, spb_g1_affine* out);

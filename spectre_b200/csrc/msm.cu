@@ -131,7 +131,7 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   msm_stitch_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g.L, 24, head_key, head, tail_key, tail, buckets, giant, giant + 1);
   msm_giant_kernel<<<256, 128, 0, st>>>(total, g.L, giant, giant + 1, head_key, head, tail_key, tail, buckets);
   cudaEventRecord(ln.ev[5], st);
-  msm_rowcol_kernel<<<g.BW * (R + C), 128, 0, st>>>(g, tl, buckets, seg_out, seg_out + (uint64_t)g.BW * R);
+  msm_rowcol_kernel<<<g.BW * (R + C), 64, 0, st>>>(g, tl, buckets, seg_out, seg_out + (uint64_t)g.BW * R);
   cudaEventRecord(ln.ev[6], st);
   msm_weighted_kernel<<<g.BW * (tl.nbr + tl.nbc), 128, 0, st>>>(g, tl, seg_out, seg_out + (uint64_t)g.BW * R, win_out);
   cudaEventRecord(ln.ev[7], st);

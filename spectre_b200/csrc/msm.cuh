@@ -31,6 +31,7 @@
 // Every function below is written per thread (`tid`) so that tests/hostemu can run the identical code
 // serially on the CPU (-DSPB_EMULATE_PTX) against the oracle.
 #pragma once
+#include <stdlib.h>
 #include "curve.cuh"
 
 namespace spb {
@@ -278,6 +279,18 @@ __device__ void block_sum_xyzz(G1Xyzz& v, G1Xyzz* sh) {
   }
 }
 
+// same for two points per thread at once (one pass of barriers instead of two)
+template <int NT>
+__device__ void block_sum2_xyzz(G1Xyzz& a, G1Xyzz& b, G1Xyzz* sh /* NT entries */) {
+  const int tid = threadIdx.x;
+  for (int stride = NT / 2; stride >= 1; stride >>= 1) {
+    if (tid >= stride && tid < 2 * stride) { sh[2 * (tid - stride)] = a; sh[2 * (tid - stride) + 1] = b; }
+    __syncthreads();
+    if (tid < stride) { xyzz_add(a, sh[2 * tid]); xyzz_add(b, sh[2 * tid + 1]); }
+    __syncthreads();
+  }
+}
+
 // giant chains (queued by the stitch kernel): one block per chain, grid-stride over the queue
 __global__ void __launch_bounds__(128) msm_giant_kernel(const uint32_t* total, uint32_t L, const uint32_t* giant_count, const uint32_t* giant_list,
                                                         const uint32_t* head_key, const G1Xyzz* head, const uint32_t* tail_key, const G1Xyzz* tail,
@@ -297,20 +310,21 @@ __global__ void __launch_bounds__(128) msm_giant_kernel(const uint32_t* total, u
 }
 
 // block (w, idx): idx < R -> row sum, else column sum
-__global__ void __launch_bounds__(128) msm_rowcol_kernel(MsmGeom g, MsmTail t, const G1Xyzz* buckets, G1Xyzz* row_out, G1Xyzz* col_out) {
-  __shared__ G1Xyzz sh[64];
+// 64 threads per vector: more serial additions per thread and a shorter tree keep more lanes busy than 128 would
+__global__ void __launch_bounds__(64) msm_rowcol_kernel(MsmGeom g, MsmTail t, const G1Xyzz* buckets, G1Xyzz* row_out, G1Xyzz* col_out) {
+  __shared__ G1Xyzz sh[32];
   const uint32_t R = 1u << t.r_log, C = 1u << t.c_log;
   const uint32_t w = blockIdx.x / (R + C), idx = blockIdx.x % (R + C);
   const G1Xyzz* X = buckets + (uint64_t)w * g.B;
   G1Xyzz acc = xyzz_identity();
-  if (idx < R) { for (uint32_t c = threadIdx.x; c < C; c += 128) xyzz_add(acc, X[(uint64_t)idx * C + c]); }
-  else { const uint32_t col = idx - R; for (uint32_t r = threadIdx.x; r < R; r += 128) xyzz_add(acc, X[(uint64_t)r * C + col]); }
-  block_sum_xyzz<128>(acc, sh);
+  if (idx < R) { for (uint32_t c = threadIdx.x; c < C; c += 64) xyzz_add(acc, X[(uint64_t)idx * C + c]); }
+  else { const uint32_t col = idx - R; for (uint32_t r = threadIdx.x; r < R; r += 64) xyzz_add(acc, X[(uint64_t)r * C + col]); }
+  block_sum_xyzz<64>(acc, sh);
   if (threadIdx.x == 0) { if (idx < R) row_out[(uint64_t)w * R + idx] = acc; else col_out[(uint64_t)w * C + (idx - R)] = acc; }
 }
 // block (w, j): j < nbr -> rows [128 j, 128 j + 128): A partial (weights r) and S partial (plain); else columns: D partial
 __global__ void __launch_bounds__(128) msm_weighted_kernel(MsmGeom g, MsmTail t, const G1Xyzz* row_out, const G1Xyzz* col_out, G1Xyzz* partials) {
-  __shared__ G1Xyzz sh[64];
+  __shared__ G1Xyzz sh[128];
   const uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = 2 * t.nbr + t.nbc;
   const uint32_t w = blockIdx.x / (t.nbr + t.nbc), j = blockIdx.x % (t.nbr + t.nbc);
   G1Xyzz* out = partials + (uint64_t)w * per;
@@ -318,11 +332,8 @@ __global__ void __launch_bounds__(128) msm_weighted_kernel(MsmGeom g, MsmTail t,
     uint32_t r = j * 128 + threadIdx.x;
     G1Xyzz x = r < R ? row_out[(uint64_t)w * R + r] : xyzz_identity();
     G1Xyzz wx = xyzz_mul_u32(x, r);
-    block_sum_xyzz<128>(wx, sh);
-    if (threadIdx.x == 0) out[j] = wx;
-    __syncthreads();
-    block_sum_xyzz<128>(x, sh);
-    if (threadIdx.x == 0) out[t.nbr + j] = x;
+    block_sum2_xyzz<128>(wx, x, sh);
+    if (threadIdx.x == 0) { out[j] = wx; out[t.nbr + j] = x; }
   } else {
     uint32_t c = (j - t.nbr) * 128 + threadIdx.x;
     G1Xyzz x = c < C ? col_out[(uint64_t)w * C + c] : xyzz_identity();
@@ -377,6 +388,7 @@ inline MsmGeom msm_make_geometry(uint32_t c, bool precomp, uint32_t tab_stride) 
 //   10 * n * W  (mixed additions)  +  2 * 14 * BW * 2^(c-1)  (running sums over the buckets, full additions)
 // BW = W without precomputed tables, 1 with them (all windows share one bucket set).
 inline uint32_t msm_choose_c(uint64_t n, bool precomp) {
+  if (const char* e = getenv(precomp ? "SPB_MSM_C_TABLES" : "SPB_MSM_C")) { int v = atoi(e); if (v >= 3 && v <= 22) return (uint32_t)v; }
   uint32_t best = 0; double best_cost = 0;
   for (uint32_t c = 3; c <= 22; c++) {
     uint32_t W = (255 + c - 1) / c;

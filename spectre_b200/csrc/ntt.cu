@@ -117,9 +117,7 @@ int ntt_device(spb_ctx* ctx, DeviceState& d, const Fr* d_src, Fr* d_dst, uint32_
     uint32_t S = 1u << p.s, C = 1u << logc;
     uint32_t quads = (S * C) / 4; if (quads < 32) quads = 32;
     uint32_t threads = quads < 512 ? quads : 512;
-    uint32_t cs = (S - 1) + ((S - 1) >> 5) + 1;
-    { uint32_t want = (C >= 32) ? 1u : 32u / C; uint32_t r = cs & 31u; cs += (want + 32u - r) & 31u; }
-    size_t smem = (size_t)8 * 4 * ((size_t)cs * C + ((S >> 1) ? (S >> 1) : 1));
+    size_t smem = (size_t)8 * 4 * ((size_t)ntt_col_stride(S, C) * C + ntt_tw_words(S));
     if (smem > 227 * 1024) return set_error(ctx, SPB_ERR_STATE, "ntt: tile needs %zu B of shared memory", smem);
     ntt_pass_kernel<<<(unsigned)tiles, threads, smem, d.stream>>>(p);
     SPB_CUDA(ctx, cudaGetLastError());

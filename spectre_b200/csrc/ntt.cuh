@@ -53,27 +53,39 @@ struct NttPassParams {
 
 #if defined(__CUDACC__)
 
+// Shared-memory index maps. Data: XOR swizzle of the low five bits with bits 2..6 -- a warp that touches, at any
+// butterfly level, 2^a consecutive elements from each of 32/2^a groups spaced 4*2^a apart (and any 32 aligned
+// consecutive elements) then hits 32 distinct banks. Twiddles: one pad word per 32 makes every power-of-two stride
+// the levels use conflict-free.
+__device__ __forceinline__ uint32_t ntt_swz(uint32_t i) { return i ^ ((i >> 2) & 31u); }
 __device__ __forceinline__ uint32_t ntt_pad(uint32_t i) { return i + (i >> 5); }
+
+__host__ __device__ __forceinline__ uint32_t ntt_col_stride(uint32_t S, uint32_t C) {
+  uint32_t base = S < 32 ? 32 : S;  // the swizzle may touch indices up to the next multiple of 32
+  return base + ((C >= 32) ? 1u : (32u / C) & 31u);
+}
+__host__ __device__ __forceinline__ uint32_t ntt_tw_words(uint32_t S) { uint32_t h = S >> 1; return h ? h + (h >> 5) + 1 : 1; }
 
 struct NttSmem {
   uint32_t* data;   // 8 planes of plane_words
   uint32_t* tw;     // 8 planes of tw_words
   uint32_t plane_words, tw_words, col_stride;
   __device__ __forceinline__ Fr load(uint32_t col, uint32_t i) const {
-    Fr r; uint32_t o = col * col_stride + ntt_pad(i);
+    Fr r; uint32_t o = col * col_stride + ntt_swz(i);
 #pragma unroll
     for (int l = 0; l < 8; l++) r.l[l] = data[l * plane_words + o];
     return r;
   }
   __device__ __forceinline__ void store(uint32_t col, uint32_t i, const Fr& v) const {
-    uint32_t o = col * col_stride + ntt_pad(i);
+    uint32_t o = col * col_stride + ntt_swz(i);
 #pragma unroll
     for (int l = 0; l < 8; l++) data[l * plane_words + o] = v.l[l];
   }
   __device__ __forceinline__ Fr twiddle(uint32_t j) const {
     Fr r;
+    uint32_t o = ntt_pad(j);
 #pragma unroll
-    for (int l = 0; l < 8; l++) r.l[l] = tw[l * tw_words + j];
+    for (int l = 0; l < 8; l++) r.l[l] = tw[l * tw_words + o];
     return r;
   }
 };
@@ -112,11 +124,10 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
   extern __shared__ uint32_t smem_raw[];
   const uint32_t S = 1u << p.s, C = 1u << p.logc, T = blockDim.x, tid = threadIdx.x;
   NttSmem sm;
-  sm.col_stride = ntt_pad(S - 1) + 1;
-  // make the column stride == 32/C (mod 32) so that a warp touching C columns x 32/C rows is conflict-free
-  { uint32_t want = (C >= 32) ? 1u : 32u / C; uint32_t r = sm.col_stride & 31u; sm.col_stride += (want + 32u - r) & 31u; }
+  // column stride == 32/C (mod 32): a warp touching C columns x 32/C consecutive rows is conflict-free
+  sm.col_stride = ntt_col_stride(S, C);
   sm.plane_words = sm.col_stride * C;
-  sm.tw_words = (S >> 1) ? (S >> 1) : 1;
+  sm.tw_words = ntt_tw_words(S);
   sm.data = smem_raw;
   sm.tw = smem_raw + 8 * sm.plane_words;
 
@@ -139,8 +150,9 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
   // ---- stage sub-NTT twiddles omega_{2^s}^j = omega^(j << (k-s)) into shared memory -----------------
   for (uint32_t j = tid; j < (S >> 1); j += T) {
     Fr w = ntt_omega_pow(p, (uint64_t)j << (p.k - p.s));
+    uint32_t o = ntt_pad(j);
 #pragma unroll
-    for (int l = 0; l < 8; l++) sm.tw[l * sm.tw_words + j] = w.l[l];
+    for (int l = 0; l < 8; l++) sm.tw[l * sm.tw_words + o] = w.l[l];
   }
 
   // ---- load tile (natural order), fusing zero padding and the zeta-coset pre-scale -----------------

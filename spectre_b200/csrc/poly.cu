@@ -107,67 +107,26 @@ __global__ void eval_strided_kernel(const Fr* poly, uint64_t n, Fr x, Fr xT, uin
   partial[t] = acc;
 }
 
-extern "C" {
 
-#define SPB_ENTER(ctx)                          \
-  std::lock_guard<std::mutex> lk((ctx)->mu);    \
-  DeviceState& d = (ctx)->dev[0];               \
-  SPB_CUDA(ctx, cudaSetDevice(d.device));
-
-static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
-
-int spb_vec_mul(spb_ctx* ctx, spb_fr* a, const spb_fr* b, size_t n) {
-  if (!ctx || !a || !b) return SPB_ERR_ARG;
-  SPB_ENTER(ctx);
-  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* db = (Fr*)slot(ctx, d, "poly_b", n * 32);
-  if (!da || !db) return SPB_ERR_OOM;
-  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
-  SPB_CUDA(ctx, cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, d.stream));
-  vec_mul_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(da, db, n);
-  ctx->n_kernel_launches++;
-  SPB_CUDA(ctx, cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, d.stream));
-  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
-  return 0;
+// out[i] = sum_p y^p * polys[p][i]  evaluated as Horner over p from the last polynomial down (the "fold with powers
+// of y" that evaluate_h, vanishing::evaluate and the SHPLONK opener all do): reads each polynomial once.
+__global__ void lincomb_kernel(const Fr* const* polys, uint32_t count, Fr y, Fr* out, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr acc = ntt_ld_stream(polys[count - 1] + i);
+  for (int p = (int)count - 2; p >= 0; p--) acc = fp_add(fp_mul(acc, y), ntt_ld_stream(polys[p] + i));
+  ntt_stg(out + i, acc);
 }
 
-int spb_vec_axpy(spb_ctx* ctx, spb_fr* y, const spb_fr* alpha, const spb_fr* x, size_t n) {
-  if (!ctx || !y || !alpha || !x) return SPB_ERR_ARG;
-  SPB_ENTER(ctx);
-  Fr* dy = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dx = (Fr*)slot(ctx, d, "poly_b", n * 32);
-  if (!dy || !dx) return SPB_ERR_OOM;
-  Fr al; memcpy(&al, alpha, 32);
-  SPB_CUDA(ctx, cudaMemcpyAsync(dy, y, n * 32, cudaMemcpyHostToDevice, d.stream));
-  SPB_CUDA(ctx, cudaMemcpyAsync(dx, x, n * 32, cudaMemcpyHostToDevice, d.stream));
-  vec_axpy_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(dy, al, dx, n);
-  ctx->n_kernel_launches++;
-  SPB_CUDA(ctx, cudaMemcpyAsync(y, dy, n * 32, cudaMemcpyDeviceToHost, d.stream));
-  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
-  return 0;
-}
+namespace {
 
-int spb_vec_scale(spb_ctx* ctx, spb_fr* a, const spb_fr* alpha, size_t n) {
-  if (!ctx || !a || !alpha) return SPB_ERR_ARG;
-  SPB_ENTER(ctx);
-  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32);
-  if (!da) return SPB_ERR_OOM;
-  Fr al; memcpy(&al, alpha, 32);
-  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
-  vec_scale_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(da, al, n);
-  ctx->n_kernel_launches++;
-  SPB_CUDA(ctx, cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, d.stream));
-  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
-  return 0;
-}
+inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
-int spb_grand_product(spb_ctx* ctx, const spb_fr* a, size_t n, spb_fr* z) {
-  if (!ctx || !a || !z) return SPB_ERR_ARG;
-  if (!n) return 0;
-  SPB_ENTER(ctx);
+// ---- device-resident cores (all pointers on device d, work enqueued on d.stream; no final synchronisation unless noted)
+int dev_grand_product(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, Fr* dz) {
   size_t m = (n + kChunk - 1) / kChunk;
-  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dz = (Fr*)slot(ctx, d, "poly_b", n * 32);
-  Fr* dp = (Fr*)slot(ctx, d, "poly_partial", m * 32);
-  if (!da || !dz || !dp) return SPB_ERR_OOM;
-  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  Fr* dp = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32);
+  if (!dp) return SPB_ERR_OOM;
   chunk_product_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, dp);
   std::vector<Fr> part(m);
   SPB_CUDA(ctx, cudaMemcpyAsync(part.data(), dp, m * 32, cudaMemcpyDeviceToHost, d.stream));
@@ -176,22 +135,15 @@ int spb_grand_product(spb_ctx* ctx, const spb_fr* a, size_t n, spb_fr* z) {
   for (size_t c = 0; c < m; c++) { Fr t = part[c]; part[c] = run; run = fp_mul(run, t); }  // exclusive carry
   SPB_CUDA(ctx, cudaMemcpyAsync(dp, part.data(), m * 32, cudaMemcpyHostToDevice, d.stream));
   chunk_product_fix_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, dp, dz);
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));  // `part` must outlive the H2D copy
   ctx->n_kernel_launches += 2;
-  SPB_CUDA(ctx, cudaMemcpyAsync(z, dz, n * 32, cudaMemcpyDeviceToHost, d.stream));
-  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
   return 0;
 }
 
-int spb_kate_division(spb_ctx* ctx, const spb_fr* a, size_t n, const spb_fr* b, spb_fr* q) {
-  if (!ctx || !a || !b || !q || n < 1) return SPB_ERR_ARG;
-  if (n == 1) return 0;
-  SPB_ENTER(ctx);
+int dev_kate_division(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, const Fr& bb, Fr* dq) {
   size_t nq = n - 1, m = (nq + kChunk - 1) / kChunk;
-  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dq = (Fr*)slot(ctx, d, "poly_b", nq * 32);
   Fr* dh = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32);
-  if (!da || !dq || !dh) return SPB_ERR_OOM;
-  Fr bb; memcpy(&bb, b, 32);
-  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  if (!dh) return SPB_ERR_OOM;
   kate_chunk_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, nq, bb, nullptr, dh, nullptr, 0);
   std::vector<Fr> heads(m), carry(m);
   SPB_CUDA(ctx, cudaMemcpyAsync(heads.data(), dh, m * 32, cudaMemcpyDeviceToHost, d.stream));
@@ -207,46 +159,211 @@ int spb_kate_division(spb_ctx* ctx, const spb_fr* a, size_t n, const spb_fr* b, 
   }
   SPB_CUDA(ctx, cudaMemcpyAsync(dh + m, carry.data(), m * 32, cudaMemcpyHostToDevice, d.stream));
   kate_chunk_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, nq, bb, dh + m, nullptr, dq, 1);
-  ctx->n_kernel_launches += 2;
-  SPB_CUDA(ctx, cudaMemcpyAsync(q, dq, nq * 32, cudaMemcpyDeviceToHost, d.stream));
   SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  ctx->n_kernel_launches += 2;
   return 0;
 }
 
-int spb_batch_invert(spb_ctx* ctx, spb_fr* a, size_t n) {
-  if (!ctx || !a) return SPB_ERR_ARG;
-  if (!n) return 0;
-  SPB_ENTER(ctx);
+int dev_batch_invert(spb_ctx* ctx, DeviceState& d, Fr* da, size_t n) {
   size_t m = (n + kChunk - 1) / kChunk;
-  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* ds = (Fr*)slot(ctx, d, "poly_b", n * 32);
-  Fr* dp = (Fr*)slot(ctx, d, "poly_partial", m * 32);
-  if (!da || !ds || !dp) return SPB_ERR_OOM;
-  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  Fr* ds = (Fr*)slot(ctx, d, "poly_scratch", n * 32);
+  Fr* dp = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32);
+  if (!ds || !dp) return SPB_ERR_OOM;
   inv_chunk_prefix_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, ds, dp);
   inv_partials_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(dp, m);
   inv_chunk_fix_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, ds, dp);
   ctx->n_kernel_launches += 3;
+  return 0;
+}
+
+int dev_eval_polynomial(spb_ctx* ctx, DeviceState& d, const Fr* dp, size_t n, const Fr& x, Fr* out_host) {
+  const uint32_t T = 4096;
+  Fr* dpart = (Fr*)slot(ctx, d, "poly_partial", (size_t)T * 32 > 0 ? (size_t)T * 32 : 32);
+  if (!dpart) return SPB_ERR_OOM;
+  eval_strided_kernel<<<T / 128, 128, 0, d.stream>>>(dp, n, x, fp_pow_u64(x, T), T, dpart);
+  ctx->n_kernel_launches++;
+  std::vector<Fr> part(T);
+  SPB_CUDA(ctx, cudaMemcpyAsync(part.data(), dpart, T * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  Fr acc = fp_zero<FrParams>();
+  for (uint32_t t = 0; t < T; t++) acc = fp_add(acc, part[t]);
+  *out_host = acc;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+#define SPB_ENTER(ctx)                          \
+  std::lock_guard<std::mutex> lk((ctx)->mu);    \
+  DeviceState& d = (ctx)->dev[0];               \
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+
+// ---- element-wise -------------------------------------------------------------------------------------------------
+int spb_vec_mul_dev(spb_ctx* ctx, spb_fr* d_a, const spb_fr* d_b, size_t n) {
+  if (!ctx || !d_a || !d_b) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  vec_mul_kernel<<<nblk(n, 256), 256, 0, d.stream>>>((Fr*)d_a, (const Fr*)d_b, n);
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+int spb_vec_axpy_dev(spb_ctx* ctx, spb_fr* d_y, const spb_fr* alpha, const spb_fr* d_x, size_t n) {
+  if (!ctx || !d_y || !alpha || !d_x) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  Fr al; memcpy(&al, alpha, 32);
+  vec_axpy_kernel<<<nblk(n, 256), 256, 0, d.stream>>>((Fr*)d_y, al, (const Fr*)d_x, n);
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+int spb_vec_scale_dev(spb_ctx* ctx, spb_fr* d_a, const spb_fr* alpha, size_t n) {
+  if (!ctx || !d_a || !alpha) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  Fr al; memcpy(&al, alpha, 32);
+  vec_scale_kernel<<<nblk(n, 256), 256, 0, d.stream>>>((Fr*)d_a, al, n);
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+int spb_lincomb_dev(spb_ctx* ctx, const spb_fr* const* d_polys, size_t count, const spb_fr* y, spb_fr* d_out, size_t n) {
+  if (!ctx || !d_polys || !count || !y || !d_out) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  const Fr** dptrs = (const Fr**)slot(ctx, d, "poly_ptrs", count * sizeof(void*));
+  if (!dptrs) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(dptrs, d_polys, count * sizeof(void*), cudaMemcpyHostToDevice, d.stream));
+  Fr yy; memcpy(&yy, y, 32);
+  lincomb_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(dptrs, (uint32_t)count, yy, (Fr*)d_out, n);
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_vec_mul(spb_ctx* ctx, spb_fr* a, const spb_fr* b, size_t n) {
+  if (!ctx || !a || !b) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* db = (Fr*)slot(ctx, d, "poly_b", n * 32);
+  if (!da || !db) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  SPB_CUDA(ctx, cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, d.stream));
+  vec_mul_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(da, db, n);
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+int spb_vec_axpy(spb_ctx* ctx, spb_fr* y, const spb_fr* alpha, const spb_fr* x, size_t n) {
+  if (!ctx || !y || !alpha || !x) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  Fr* dy = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dx = (Fr*)slot(ctx, d, "poly_b", n * 32);
+  if (!dy || !dx) return SPB_ERR_OOM;
+  Fr al; memcpy(&al, alpha, 32);
+  SPB_CUDA(ctx, cudaMemcpyAsync(dy, y, n * 32, cudaMemcpyHostToDevice, d.stream));
+  SPB_CUDA(ctx, cudaMemcpyAsync(dx, x, n * 32, cudaMemcpyHostToDevice, d.stream));
+  vec_axpy_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(dy, al, dx, n);
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaMemcpyAsync(y, dy, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+int spb_vec_scale(spb_ctx* ctx, spb_fr* a, const spb_fr* alpha, size_t n) {
+  if (!ctx || !a || !alpha) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32);
+  if (!da) return SPB_ERR_OOM;
+  Fr al; memcpy(&al, alpha, 32);
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  vec_scale_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(da, al, n);
+  ctx->n_kernel_launches++;
   SPB_CUDA(ctx, cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, d.stream));
   SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
   return 0;
 }
 
+// ---- scans --------------------------------------------------------------------------------------------------------
+int spb_grand_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* d_z) {
+  if (!ctx || !d_a || !d_z) return SPB_ERR_ARG;
+  if (!n) return 0;
+  SPB_ENTER(ctx);
+  return dev_grand_product(ctx, d, (const Fr*)d_a, n, (Fr*)d_z);
+}
+int spb_grand_product(spb_ctx* ctx, const spb_fr* a, size_t n, spb_fr* z) {
+  if (!ctx || !a || !z) return SPB_ERR_ARG;
+  if (!n) return 0;
+  SPB_ENTER(ctx);
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dz = (Fr*)slot(ctx, d, "poly_b", n * 32);
+  if (!da || !dz) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  SPB_TRY(dev_grand_product(ctx, d, da, n, dz));
+  SPB_CUDA(ctx, cudaMemcpyAsync(z, dz, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_kate_division_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, const spb_fr* b, spb_fr* d_q) {
+  if (!ctx || !d_a || !b || !d_q || n < 1) return SPB_ERR_ARG;
+  if (n == 1) return 0;
+  SPB_ENTER(ctx);
+  Fr bb; memcpy(&bb, b, 32);
+  return dev_kate_division(ctx, d, (const Fr*)d_a, n, bb, (Fr*)d_q);
+}
+int spb_kate_division(spb_ctx* ctx, const spb_fr* a, size_t n, const spb_fr* b, spb_fr* q) {
+  if (!ctx || !a || !b || !q || n < 1) return SPB_ERR_ARG;
+  if (n == 1) return 0;
+  SPB_ENTER(ctx);
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dq = (Fr*)slot(ctx, d, "poly_b", n * 32);
+  if (!da || !dq) return SPB_ERR_OOM;
+  Fr bb; memcpy(&bb, b, 32);
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  SPB_TRY(dev_kate_division(ctx, d, da, n, bb, dq));
+  SPB_CUDA(ctx, cudaMemcpyAsync(q, dq, (n - 1) * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_batch_invert_dev(spb_ctx* ctx, spb_fr* d_a, size_t n) {
+  if (!ctx || !d_a) return SPB_ERR_ARG;
+  if (!n) return 0;
+  SPB_ENTER(ctx);
+  SPB_TRY(dev_batch_invert(ctx, d, (Fr*)d_a, n));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+int spb_batch_invert(spb_ctx* ctx, spb_fr* a, size_t n) {
+  if (!ctx || !a) return SPB_ERR_ARG;
+  if (!n) return 0;
+  SPB_ENTER(ctx);
+  Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32);
+  if (!da) return SPB_ERR_OOM;
+  SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
+  SPB_TRY(dev_batch_invert(ctx, d, da, n));
+  SPB_CUDA(ctx, cudaMemcpyAsync(a, da, n * 32, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_eval_polynomial_dev(spb_ctx* ctx, const spb_fr* d_poly, size_t n, const spb_fr* point, spb_fr* out) {
+  if (!ctx || !point || !out || (n && !d_poly)) return SPB_ERR_ARG;
+  Fr acc = fp_zero<FrParams>();
+  if (n) {
+    SPB_ENTER(ctx);
+    Fr x; memcpy(&x, point, 32);
+    SPB_TRY(dev_eval_polynomial(ctx, d, (const Fr*)d_poly, n, x, &acc));
+  }
+  memcpy(out, &acc, 32);
+  return 0;
+}
 int spb_eval_polynomial(spb_ctx* ctx, const spb_fr* poly, size_t n, const spb_fr* point, spb_fr* out) {
   if (!ctx || !point || !out || (n && !poly)) return SPB_ERR_ARG;
   Fr acc = fp_zero<FrParams>();
   if (n) {
     SPB_ENTER(ctx);
-    const uint32_t T = 4096;
-    Fr* dp = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dpart = (Fr*)slot(ctx, d, "poly_partial", T * 32);
-    if (!dp || !dpart) return SPB_ERR_OOM;
+    Fr* dp = (Fr*)slot(ctx, d, "poly_a", n * 32);
+    if (!dp) return SPB_ERR_OOM;
     Fr x; memcpy(&x, point, 32);
     SPB_CUDA(ctx, cudaMemcpyAsync(dp, poly, n * 32, cudaMemcpyHostToDevice, d.stream));
-    eval_strided_kernel<<<T / 128, 128, 0, d.stream>>>(dp, n, x, fp_pow_u64(x, T), T, dpart);
-    ctx->n_kernel_launches++;
-    std::vector<Fr> part(T);
-    SPB_CUDA(ctx, cudaMemcpyAsync(part.data(), dpart, T * 32, cudaMemcpyDeviceToHost, d.stream));
-    SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
-    for (uint32_t t = 0; t < T; t++) acc = fp_add(acc, part[t]);
+    SPB_TRY(dev_eval_polynomial(ctx, d, dp, n, x, &acc));
   }
   memcpy(out, &acc, 32);
   return 0;

@@ -192,6 +192,31 @@ class Backend:
         self.check(self.lib.spb_vec_scale(self.ctx, _p(a), _p(alpha), ctypes.c_size_t(a.shape[0])), "spb_vec_scale")
         return a
 
+    # ---- device-resident batch ops (pointers are ints: addresses on device 0 of the context) ----------
+    def lincomb_dev(self, d_ptrs, y, d_out, n):
+        ptrs = (ctypes.c_void_p * len(d_ptrs))(*d_ptrs)
+        self.check(self.lib.spb_lincomb_dev(self.ctx, ptrs, ctypes.c_size_t(len(d_ptrs)), _p(_fr_array(y, 1)), _p(d_out), ctypes.c_size_t(n)), "spb_lincomb_dev")
+
+    def eval_polynomial_dev(self, d_poly, n, point):
+        out = np.empty(4, dtype=np.uint64)
+        self.check(self.lib.spb_eval_polynomial_dev(self.ctx, _p(d_poly), ctypes.c_size_t(n), _p(_fr_array(point, 1)), _p(out)), "spb_eval_polynomial_dev")
+        return out
+
+    def kate_division_dev(self, d_a, n, b, d_q):
+        self.check(self.lib.spb_kate_division_dev(self.ctx, _p(d_a), ctypes.c_size_t(n), _p(_fr_array(b, 1)), _p(d_q)), "spb_kate_division_dev")
+
+    def batch_invert_dev(self, d_a, n):
+        self.check(self.lib.spb_batch_invert_dev(self.ctx, _p(d_a), ctypes.c_size_t(n)), "spb_batch_invert_dev")
+
+    def grand_product_dev(self, d_a, n, d_z):
+        self.check(self.lib.spb_grand_product_dev(self.ctx, _p(d_a), ctypes.c_size_t(n), _p(d_z)), "spb_grand_product_dev")
+
+    def vec_mul_dev(self, d_a, d_b, n):
+        self.check(self.lib.spb_vec_mul_dev(self.ctx, _p(d_a), _p(d_b), ctypes.c_size_t(n)), "spb_vec_mul_dev")
+
+    def vec_scale_dev(self, d_a, alpha, n):
+        self.check(self.lib.spb_vec_scale_dev(self.ctx, _p(d_a), _p(_fr_array(alpha, 1)), ctypes.c_size_t(n)), "spb_vec_scale_dev")
+
     # ---- utilities -------------------------------------------------------------------------------------
     def g1_fixed_base_mul(self, scalars):
         scalars = _fr_array(scalars)
@@ -274,6 +299,19 @@ class EvaluationDomain:
         out = np.empty(((1 << self.k) * (self.j - 1), 4), dtype=np.uint64)
         self.be.check(self.be.lib.spb_extended_to_coeff(self.be.ctx, self.h, _p(a), _p(out)), "spb_extended_to_coeff")
         return out
+
+    # device-resident forms (int device addresses)
+    def lagrange_to_coeff_dev(self, d_a):
+        self.be.check(self.be.lib.spb_lagrange_to_coeff_dev(self.be.ctx, self.h, _p(d_a)), "spb_lagrange_to_coeff_dev")
+
+    def coeff_to_extended_dev(self, d_in, d_out):
+        self.be.check(self.be.lib.spb_coeff_to_extended_dev(self.be.ctx, self.h, _p(d_in), _p(d_out)), "spb_coeff_to_extended_dev")
+
+    def extended_to_coeff_dev(self, d_in, d_out):
+        self.be.check(self.be.lib.spb_extended_to_coeff_dev(self.be.ctx, self.h, _p(d_in), _p(d_out)), "spb_extended_to_coeff_dev")
+
+    def divide_by_vanishing_poly_dev(self, d_a):
+        self.be.check(self.be.lib.spb_divide_by_vanishing_dev(self.be.ctx, self.h, _p(d_a)), "spb_divide_by_vanishing_dev")
 
     def divide_by_vanishing_poly(self, a):
         a = _fr_array(a).copy()
