@@ -123,6 +123,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--replay", action="store_true", help="also run the proof-shaped replays (sync-step k=20, aggregation K=23) on rank 0")
     ap.add_argument("--no-tables", action="store_true", help="skip spb_srs_precompute (W separate bucket sets, Horner over windows)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -290,6 +291,20 @@ def main():
             del t
         line["ntt"] = ntt
 
+    # ---- proof-shaped replay (BASELINE configs 3/5 shapes; see spectre_b200/replay.py for what it is and is not) ----
+    if args.replay and world == 1:
+        from spectre_b200 import replay
+        from oracle import oracle as orc_
+        orc_.build(); orc_.lib()
+        del dev_sets, params
+        torch.cuda.empty_cache()
+        rep = {}
+        for shape in ("sync_step_k20", "aggregation_K23"):
+            rep[shape] = replay.replay(be, shape, orc_.srs_tau())
+            torch.cuda.empty_cache()
+        rep["sync_step_compressed_total_s"] = rep["sync_step_k20"]["total_s"] + rep["aggregation_K23"]["total_s"]
+        line["proof_replay"] = rep
+
     # ---- CPU baseline (oracle port of best_multiexp) on this box's cores, bounded sample ----------------------
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle as orc
@@ -299,7 +314,8 @@ def main():
         t0 = time.perf_counter()
         cpu_res = orc.best_multiexp(sc, pts, threads=threads)
         dt = time.perf_counter() - t0
-        gpu_res = params.commit_lagrange(sc)
+        params2 = halo2.ParamsKZG.from_parts(be, LOG_N, g_lagrange=pts) if args.replay else params
+        gpu_res = params2.commit_lagrange(sc)
         same = bool(np.array_equal(orc.g1_to_affine(cpu_res), orc.g1_to_affine(gpu_res)))
         line["cpu_baseline"] = {"value": N_PAIRS / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
                                 "sample": "one full 2^20-pair MSM (same scalars and bases as the GPU step), C port of halo2 best_multiexp",

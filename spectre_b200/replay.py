@@ -17,6 +17,7 @@ from . import halo2
 
 # (k, advice A, lookups L, permutation polys P, quotient pieces Q, max degree j, fixed+sigma+l polys F, evaluations)
 SHAPES = {
+    "tiny_k10": dict(k=10, A=3, L=1, P=2, Q=3, j=4, F=4, evals=5),   # test-sized
     # lightclient-circuits/config/sync_step_20.json + sha256_flex spread config (estimate)
     "sync_step_k20": dict(k=20, A=19, L=3, P=11, Q=3, j=4, F=40, evals=110),
     # config/sync_step_verifier_23.json, verified against the committed verifier contract (row 4)

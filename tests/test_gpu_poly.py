@@ -46,3 +46,37 @@ def test_vec_ops(be, orc):
     assert orc.fr_ints(be.vec_mul(a, b)) == [x * y % pyref.R_MOD for x, y in zip(ai, bi)]
     assert orc.fr_ints(be.vec_axpy(a, al, b)) == [(x + ali * y) % pyref.R_MOD for x, y in zip(ai, bi)]
     assert orc.fr_ints(be.vec_scale(a, al)) == [x * ali % pyref.R_MOD for x in ai]
+
+
+def test_device_resident_variants_and_lincomb(be, orc):
+    """_dev entry points on torch device buffers; lincomb = fold with powers of y (Horner over the polynomials)."""
+    import torch
+    n = 5000
+    polys = [orc.fr_random_chacha(n, 80 + i) for i in range(4)]
+    y = orc.fr_random_chacha(1, 90)[0]
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(p.view(np.int64)).to(dev) for p in polys]
+    out = torch.empty((n, 4), dtype=torch.int64, device=dev)
+    be.lincomb_dev([t.data_ptr() for t in d], y, out.data_ptr(), n)
+    pi = [orc.fr_ints(p) for p in polys]; yi = orc.fr_ints(y)[0]
+    want = [sum(pi[k][i] * pow(yi, k, pyref.R_MOD) for k in range(4)) % pyref.R_MOD for i in range(n)]
+    assert orc.fr_ints(out.cpu().numpy().view(np.uint64)) == want
+    x = orc.fr_random_chacha(1, 91)[0]
+    assert np.array_equal(be.eval_polynomial_dev(d[0].data_ptr(), n, x), orc.eval_polynomial(polys[0], x))
+    q = torch.empty((n - 1, 4), dtype=torch.int64, device=dev)
+    be.kate_division_dev(d[0].data_ptr(), n, x, q.data_ptr())
+    assert np.array_equal(q.cpu().numpy().view(np.uint64), orc.kate_division(polys[0], x))
+    a = d[1].clone()
+    be.batch_invert_dev(a.data_ptr(), n)
+    assert np.array_equal(a.cpu().numpy().view(np.uint64), orc.batch_invert(polys[1]))
+    z = torch.empty((n, 4), dtype=torch.int64, device=dev)
+    be.grand_product_dev(d[2].data_ptr(), n, z.data_ptr())
+    assert np.array_equal(z.cpu().numpy().view(np.uint64), be.grand_product(polys[2]))
+
+
+def test_proof_replay_tiny_runs(be, orc):
+    """The proof-shaped replay (tools for BASELINE configs 3-5) executes every stage on a test-sized shape."""
+    from spectre_b200 import replay
+    out = replay.replay(be, "tiny_k10", orc.srs_tau())
+    assert out["msm_count"] == 3 + 2 + 3 + 1 + 3 + 2 and out["total_s"] > 0
+    assert set(out["stages_s"]) >= {"3_advice_commit", "7_lagrange_to_coeff", "8a_coeff_to_extended", "9_vanishing_construct_commit", "11_shplonk"}
