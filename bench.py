@@ -166,6 +166,16 @@ def main():
         dist.all_gather(out, t)
         return halo2.g1_sum(torch.stack(out).cpu().numpy().view(np.uint64))
 
+    def fold_batch(partials):
+        """one all_gather for the whole batch of (count, 12) partial sums, then `count` host folds"""
+        if world == 1:
+            return partials
+        t = torch.from_numpy(np.ascontiguousarray(partials).view(np.int64)).to(dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        allp = torch.stack(out).cpu().numpy().view(np.uint64)          # (world, count, 12)
+        return np.stack([halo2.g1_sum(allp[:, i, :]) for i in range(allp.shape[1])])
+
     def step_dev(i):
         s = dev_sets[i % N_SCALAR_SETS]
         return fold_partials(params.commit_dev(halo2.BASIS_G_LAGRANGE, s.data_ptr(), N_PAIRS))
@@ -180,17 +190,13 @@ def main():
         """`count` steps through the batch entry point (two stream lanes), scalars resident in HBM."""
         ptrs = [dev_sets[(first + i) % N_SCALAR_SETS].data_ptr() for i in range(count)]
         res = params.commit_batch_dev(halo2.BASIS_G_LAGRANGE, ptrs, N_PAIRS)
-        if world > 1:
-            res = np.stack([fold_partials(r) for r in res])
-        return res
+        return fold_batch(res)
 
     def run_e2e(first, count):
         """same from pinned host buffers: H2D of every step's scalars and D2H of its result inside the call"""
         polys = [host_np[(first + i) % N_SCALAR_SETS] for i in range(count)]
         res = params.commit_batch(halo2.BASIS_G_LAGRANGE, polys)
-        if world > 1:
-            res = np.stack([fold_partials(r) for r in res])
-        return res
+        return fold_batch(res)
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,9 +254,14 @@ def main():
     achieved = algo_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
     # INT32 multiply-pipe view: a mixed XYZZ addition is 8M+2S = 10 Montgomery products; measured product peak 68 G/s
     modmul_per_launch = 10.0 * (adds - 2 * (1 if not args.no_tables else W) * (1 << (c - 1)))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and not args.no_tables:
+        with open(tpath) as f:
+            traffic = json.load(f)["msm_accumulate_kernel"]["dram_bytes_per_launch"]
     roofline = {
         "kernel": "msm_accumulate_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": acc_ms,
         "note": "integer-ALU bound, not HBM bound (SURVEY.md finding 6): see int32_pipe",
         "int32_pipe": {"achieved_gmodmul_per_s": modmul_per_launch / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
