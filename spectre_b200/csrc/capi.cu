@@ -125,6 +125,15 @@ spb_ctx* spb_init(const int* device_ids, int n_dev) {
     if (cudaMallocHost(&d.pinned, d.pinned_cap) != cudaSuccess) { delete ctx; return nullptr; }
     ctx->dev.push_back(d);
   }
+  // several devices: direct NVLink peer copies for the NTT all-to-all and the sharded-MSM scalar scatter
+  for (size_t i = 0; i < ctx->dev.size(); i++)
+    for (size_t j = 0; j < ctx->dev.size(); j++) {
+      if (i == j) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, ctx->dev[i].device, ctx->dev[j].device);
+      if (can) { cudaSetDevice(ctx->dev[i].device); cudaError_t e = cudaDeviceEnablePeerAccess(ctx->dev[j].device, 0); if (e != cudaSuccess) cudaGetLastError(); }
+    }
+  if (!ctx->dev.empty()) cudaSetDevice(ctx->dev[0].device);
   return ctx;
 }
 
@@ -188,6 +197,12 @@ int spb_ntt_dev(spb_ctx* ctx, spb_fr* d_a, uint32_t log_n, const spb_fr* omega) 
 
 // host-buffer transform through a device staging slot
 static int ntt_host(spb_ctx* ctx, const Fr* in, size_t n_in_copy, Fr* out, size_t n_out_copy, uint32_t k, const Fr& omega, const NttOpts& o) {
+  if (ntt_multi_applicable(ctx, k)) {
+    NttOpts o2 = o;
+    if (!o2.n_in) o2.n_in = n_in_copy;
+    if (!o2.n_out) o2.n_out = n_out_copy;
+    return ntt_multi_host(ctx, in, out, k, omega, o2, nullptr);
+  }
   DeviceState& d = ctx->dev[0];
   SPB_CUDA(ctx, cudaSetDevice(d.device));
   size_t n = (size_t)1 << k;

@@ -79,6 +79,9 @@ struct NttOpts {
 };
 // d_src/d_dst device pointers (may alias); omega host value (Montgomery)
 int ntt_device(spb_ctx* ctx, DeviceState& d, const Fr* d_src, Fr* d_dst, uint32_t log_n, const Fr& omega, const NttOpts& opts);
+// several devices in the context: six-step across devices with one all-to-all (host buffers)
+bool ntt_multi_applicable(spb_ctx* ctx, uint32_t log_n);
+int ntt_multi_host(spb_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, const Fr& omega, const NttOpts& opts, float* ev_ms);
 
 // ---- host field helpers (64-bit path) ----
 inline Fr fr_from_u64(uint64_t v) {

@@ -74,56 +74,163 @@ static int get_tables(spb_ctx* ctx, DeviceState& d, uint32_t k, const Fr& omega,
   return 0;
 }
 
+// Fill the geometry of pass `pi` of `plan` (global view) and launch it. `sh` describes the device's share:
+// g_log = log2(#devices) (0 on one device), q = this device's index, mode: 0 = whole problem on this device,
+// 1 = first pass sharded by columns, 2 = later pass sharded by the first digit.
+struct NttShare { uint32_t g_log = 0, q = 0, mode = 0; };
+
+static int launch_pass(spb_ctx* ctx, DeviceState& d, const NttPlan& plan, uint32_t pi, uint32_t k, const NttTables* tb, uint32_t h,
+                       const Fr* src, Fr* dst, const NttOpts& opts, const NttShare& sh) {
+  const uint64_t n = 1ull << k;
+  NttPassParams p; memset(&p, 0, sizeof p);
+  uint32_t a = 0; for (uint32_t i = 0; i < pi; i++) a += plan.s[i];
+  p.k = k; p.h = h; p.tw_lo = tb->tw_lo; p.tw_hi = tb->tw_hi; p.tw_full = tb->tw_full;
+  p.s = plan.s[pi]; p.a = a; p.b = k - a - p.s; p.s1 = plan.s[0];
+  p.first = (pi == 0); p.last = (pi == plan.npass - 1);
+  p.b_next = p.last ? 0 : p.b - plan.s[pi + 1];
+  p.n_in = opts.n_in ? opts.n_in : n;
+  p.n_out = opts.n_out ? opts.n_out : n;
+  if (p.first && opts.pre3) { p.use_pre = 1; for (int i = 0; i < 3; i++) p.pre[i] = opts.pre3[i]; }
+  if (p.last && opts.post3) { p.use_post = 1; for (int i = 0; i < 3; i++) p.post[i] = opts.post3[i]; }
+  p.b_addr = p.b;
+  // columns per tile: as many as fit, bounded by what the direction offers on this device
+  uint32_t avail = p.last ? (p.a ? p.s1 : 0) : p.b;
+  if (sh.mode == 1) { avail = p.b - sh.g_log; p.b_addr = p.b - sh.g_log; p.lo_base = (uint64_t)sh.q << p.b_addr; }
+  if (sh.mode == 2 && p.last) avail = p.s1 - sh.g_log;
+  uint32_t logc = kTileElemsLog > p.s ? kTileElemsLog - p.s : 0;
+  if (logc > avail) logc = avail;
+  if (logc > 5) logc = 5;
+  p.logc = logc;
+  uint64_t tiles = (n >> (p.s + logc)) >> sh.g_log;   // this device's tiles
+  if (sh.mode == 2) {
+    p.tile_base = tiles * sh.q;
+    if (p.last) { p.out_local = 1; p.out_cols_log = p.s1 - sh.g_log; p.i1_base = sh.q << (p.s1 - sh.g_log); }
+  }
+  p.src = src; p.dst = dst;
+  uint32_t S = 1u << p.s, C = 1u << logc;
+  uint32_t quads = (S * C) / 4; if (quads < 32) quads = 32;
+  uint32_t threads = quads < 512 ? quads : 512;
+  size_t smem = (size_t)8 * 4 * ((size_t)ntt_col_stride(S, C) * C + ntt_tw_words(S));
+  if (smem > 227 * 1024) return set_error(ctx, SPB_ERR_STATE, "ntt: tile needs %zu B of shared memory", smem);
+  ntt_pass_kernel<<<(unsigned)tiles, threads, smem, d.stream>>>(p);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches++;
+  return 0;
+}
+
+static int set_smem_attr(spb_ctx* ctx, DeviceState& d) {
+  static std::map<int, bool> done;
+  if (!done[d.device]) {
+    SPB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done[d.device] = true;
+  }
+  return 0;
+}
+
 int ntt_device(spb_ctx* ctx, DeviceState& d, const Fr* d_src, Fr* d_dst, uint32_t k, const Fr& omega, const NttOpts& opts) {
   if (k > 28) return set_error(ctx, SPB_ERR_ARG, "ntt: log_n = %u exceeds the two-adicity (28) of Fr", k);
   const uint64_t n = 1ull << k;
   NttPlan plan = make_plan(k);
-  uint32_t smax = plan.s[0];
-  uint32_t h = k - smax;
+  uint32_t h = k - plan.s[0];
   NttTables* tb = nullptr;
   SPB_TRY(get_tables(ctx, d, k, omega, h, &tb));
-
   Fr* tmp = nullptr;
   if (plan.npass > 1) {
     tmp = (Fr*)slot(ctx, d, "ntt_tmp", n * sizeof(Fr));
     if (!tmp) return SPB_ERR_OOM;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SPB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-
-  uint32_t a = 0;
+  SPB_TRY(set_smem_attr(ctx, d));
   for (uint32_t pi = 0; pi < plan.npass; pi++) {
-    NttPassParams p; memset(&p, 0, sizeof p);
-    p.k = k; p.h = h; p.tw_lo = tb->tw_lo; p.tw_hi = tb->tw_hi; p.tw_full = tb->tw_full;
-    p.s = plan.s[pi]; p.a = a; p.b = k - a - p.s; p.s1 = plan.s[0];
-    p.first = (pi == 0); p.last = (pi == plan.npass - 1);
-    p.b_next = p.last ? 0 : p.b - plan.s[pi + 1];
-    p.n_in = opts.n_in ? opts.n_in : n;
-    p.n_out = opts.n_out ? opts.n_out : n;
-    if (p.first && opts.pre3) { p.use_pre = 1; for (int i = 0; i < 3; i++) p.pre[i] = opts.pre3[i]; }
-    if (p.last && opts.post3) { p.use_post = 1; for (int i = 0; i < 3; i++) p.post[i] = opts.post3[i]; }
-    // columns per tile: as many as fit, bounded by what the direction offers
-    uint32_t avail = p.last ? (p.a ? p.s1 : 0) : p.b;
-    uint32_t logc = kTileElemsLog > p.s ? kTileElemsLog - p.s : 0;
-    if (logc > avail) logc = avail;
-    if (logc > 5) logc = 5;
-    p.logc = logc;
-    p.src = (pi == 0) ? d_src : tmp;
-    p.dst = p.last ? d_dst : tmp;
-    uint64_t tiles = n >> (p.s + logc);
-    uint32_t S = 1u << p.s, C = 1u << logc;
-    uint32_t quads = (S * C) / 4; if (quads < 32) quads = 32;
-    uint32_t threads = quads < 512 ? quads : 512;
-    size_t smem = (size_t)8 * 4 * ((size_t)ntt_col_stride(S, C) * C + ntt_tw_words(S));
-    if (smem > 227 * 1024) return set_error(ctx, SPB_ERR_STATE, "ntt: tile needs %zu B of shared memory", smem);
-    ntt_pass_kernel<<<(unsigned)tiles, threads, smem, d.stream>>>(p);
-    SPB_CUDA(ctx, cudaGetLastError());
-    ctx->n_kernel_launches++;
-    a += p.s;
+    const Fr* src = (pi == 0) ? d_src : tmp;
+    Fr* dst = (pi == plan.npass - 1) ? d_dst : tmp;
+    SPB_TRY(launch_pass(ctx, d, plan, pi, k, tb, h, src, dst, opts, NttShare()));
   }
+  return 0;
+}
+
+bool ntt_multi_applicable(spb_ctx* ctx, uint32_t k) {
+  size_t G = ctx->dev.size();
+  if (G < 2 || (G & (G - 1))) return false;
+  if (getenv("SPB_NTT_SINGLE_DEVICE")) return false;
+  if (k < 16) return false;
+  NttPlan plan = make_plan(k);
+  uint32_t g = 0; while ((1u << g) < G) g++;
+  return plan.npass >= 2 && plan.s[0] > g && (k - plan.s[0]) > g + 1;
+}
+
+// Six-step NTT across the devices of the context, host buffers in and out (natural order both sides):
+//   1. each device receives a block of COLUMNS of the n1 x (n/n1) input matrix (strided 2-D H2D copy),
+//   2. first-digit pass + inter-digit twiddle locally,
+//   3. ONE all-to-all over NVLink (peer 2-D copies) so that each device owns a block of first-digit values i_1 with all
+//      remaining digits -- which is a contiguous slice of the positional intermediate array,
+//   4. remaining passes locally; the last pass writes a (n/n1) x (n1/G) block,
+//   5. strided 2-D D2H copy of that block into the natural-order result.
+// ev_ms (optional): device milliseconds between the end of the H2D copies and the start of the D2H copies.
+int ntt_multi_host(spb_ctx* ctx, const Fr* in, Fr* out, uint32_t k, const Fr& omega, const NttOpts& opts, float* ev_ms) {
+  const size_t G = ctx->dev.size();
+  uint32_t g = 0; while ((1u << g) < G) g++;
+  const uint64_t n = 1ull << k;
+  NttPlan plan = make_plan(k);
+  const uint32_t s1 = plan.s[0], rest = k - s1, h = k - s1;
+  const uint64_t n1 = 1ull << s1, lo_count = 1ull << rest, lo_loc = lo_count >> g, rows_loc = n1 >> g, per = n >> g;
+  const uint64_t n_in = opts.n_in ? opts.n_in : n, n_out = opts.n_out ? opts.n_out : n;
+  const uint64_t rows_in = (n_in + lo_count - 1) / lo_count;          // input rows that exist in the caller's buffer
+  const uint64_t rows_out = (n_out + n1 - 1) / n1;                    // output rows (of n1 elements) to return
+  std::vector<Fr*> A(G), B(G);
+  std::vector<NttTables*> tbs(G);
+  for (size_t q = 0; q < G; q++) {
+    DeviceState& d = ctx->dev[q];
+    SPB_CUDA(ctx, cudaSetDevice(d.device));
+    A[q] = (Fr*)slot(ctx, d, "ntt_md_a", per * sizeof(Fr));
+    B[q] = (Fr*)slot(ctx, d, "ntt_md_b", per * sizeof(Fr));
+    if (!A[q] || !B[q]) return SPB_ERR_OOM;
+    SPB_TRY(get_tables(ctx, d, k, omega, h, &tbs[q]));
+    SPB_TRY(set_smem_attr(ctx, d));
+    // 1. column block q of the first rows_in rows
+    if (rows_in) SPB_CUDA(ctx, cudaMemcpy2DAsync(A[q], lo_loc * sizeof(Fr), in + q * lo_loc, lo_count * sizeof(Fr), lo_loc * sizeof(Fr), rows_in, cudaMemcpyHostToDevice, d.stream));
+    SPB_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+    // 2. first pass
+    NttShare sh; sh.g_log = g; sh.q = (uint32_t)q; sh.mode = 1;
+    SPB_TRY(launch_pass(ctx, d, plan, 0, k, tbs[q], h, A[q], A[q], opts, sh));
+    SPB_CUDA(ctx, cudaEventRecord(d.stage_ev[0], d.stream));   // "pass 1 done on q"
+  }
+  // 3. all-to-all: block (rows of q', columns of q) goes from A[q] to B[q'] at column offset q
+  for (size_t qd = 0; qd < G; qd++) {
+    DeviceState& dd = ctx->dev[qd];
+    SPB_CUDA(ctx, cudaSetDevice(dd.device));
+    for (size_t qs = 0; qs < G; qs++) {
+      DeviceState& ds = ctx->dev[qs];
+      SPB_CUDA(ctx, cudaStreamWaitEvent(dd.stream, ds.stage_ev[0], 0));
+      SPB_CUDA(ctx, cudaMemcpy2DAsync(B[qd] + qs * lo_loc, lo_count * sizeof(Fr), A[qs] + qd * rows_loc * lo_loc, lo_loc * sizeof(Fr),
+                                      lo_loc * sizeof(Fr), rows_loc, cudaMemcpyDefault, dd.stream));
+    }
+    SPB_CUDA(ctx, cudaEventRecord(dd.stage_ev[1], dd.stream));  // "B[qd] complete": A[qs] blocks for qd have been read
+  }
+  // 4. remaining passes on the slice; the result block goes back into A[q] once every reader of A[q] is done
+  for (size_t q = 0; q < G; q++) {
+    DeviceState& d = ctx->dev[q];
+    SPB_CUDA(ctx, cudaSetDevice(d.device));
+    for (size_t o = 0; o < G; o++) SPB_CUDA(ctx, cudaStreamWaitEvent(d.stream, ctx->dev[o].stage_ev[1], 0));
+    NttShare sh; sh.g_log = g; sh.q = (uint32_t)q; sh.mode = 2;
+    Fr* vbase = B[q] - q * per;   // virtual base: the slice sits at its global position
+    for (uint32_t pi = 1; pi < plan.npass; pi++) {
+      bool last = pi == plan.npass - 1;
+      SPB_TRY(launch_pass(ctx, d, plan, pi, k, tbs[q], h, vbase, last ? A[q] : vbase, opts, sh));
+    }
+    SPB_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+    // 5. (rows_out) x (n1/G) block -> natural-order host result
+    if (rows_out) SPB_CUDA(ctx, cudaMemcpy2DAsync(out + q * rows_loc, n1 * sizeof(Fr), A[q], rows_loc * sizeof(Fr), rows_loc * sizeof(Fr), rows_out, cudaMemcpyDeviceToHost, d.stream));
+  }
+  float worst = 0.f;
+  for (size_t q = 0; q < G; q++) {
+    DeviceState& d = ctx->dev[q];
+    SPB_CUDA(ctx, cudaSetDevice(d.device));
+    SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    float ms = 0.f; cudaEventElapsedTime(&ms, d.ev0, d.ev1);
+    if (ms > worst) worst = ms;
+  }
+  if (ev_ms) *ev_ms = worst;
+  ctx->last_kernel_ms = worst;
   return 0;
 }
 

@@ -44,6 +44,13 @@ struct NttPassParams {
   uint32_t s1;       // bits of the first digit (== s when a == 0)
   uint32_t b_next;   // bits below the NEXT digit (passes before the last)
   uint32_t first, last;
+  // ---- multi-device (six-step across devices); all zero / equal to the global values on one device ----------
+  uint64_t tile_base;   // added to blockIdx.x: this device's first tile (passes sharded by the first digit)
+  uint64_t lo_base;     // global index of this device's first column (first pass, sharded by columns)
+  uint32_t b_addr;      // bits below the digit in THIS device's buffer (== b unless sharded by columns)
+  uint32_t out_local;   // last pass: store at (o >> s1) * 2^out_cols_log + (i_1 - i1_base) instead of o
+  uint32_t out_cols_log;
+  uint32_t i1_base;
   uint32_t use_pre, use_post;
   uint64_t n_in;     // elements >= n_in of the input are zero (not read)
   uint64_t n_out;    // only outputs < n_out are stored
@@ -134,11 +141,11 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
   // ---- tile coordinates ---------------------------------------------------------------------------
   // not last: tile = (hi, lo chunk);           element (r, c) at ((hi << s) + r) << b  +  lo0 + c
   // last    : tile = (hi-with-i_1-chunk, all);  column c is the row whose first digit is i1_0 + c
-  const uint64_t tile = blockIdx.x;
+  const uint64_t tile = blockIdx.x + p.tile_base;
   uint64_t hi = 0, lo0 = 0, i1_0 = 0, hi_rest = 0;
   const uint32_t rest_bits = p.a > p.s1 ? p.a - p.s1 : 0;  // bits of hi that are not the first digit (last pass, P = 3)
   if (!p.last) {
-    const uint32_t chunks_log = p.b - p.logc;
+    const uint32_t chunks_log = p.b_addr - p.logc;
     hi = tile >> chunks_log;
     lo0 = (tile & ((1ull << chunks_log) - 1)) << p.logc;
   } else if (p.a > 0) {
@@ -159,14 +166,17 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
   for (uint32_t e = tid; e < S * C; e += T) {
     // lanes run along the contiguous global direction: columns for strided passes, the row for the last one
     uint32_t c, r;
-    uint64_t gi;
-    if (!p.last) { c = e & (C - 1); r = e >> p.logc; gi = ((((hi << p.s) + r) << p.b) + lo0 + c); }
-    else { r = e & (S - 1); c = e >> p.s; gi = ((((i1_0 + c) << rest_bits) + hi_rest) << p.s) + r; }
+    uint64_t gi, gglob;   // address in this device's buffer, and the global element index
+    if (!p.last) {
+      c = e & (C - 1); r = e >> p.logc;
+      gi = ((((hi << p.s) + r) << p.b_addr) + lo0 + c);
+      gglob = ((((hi << p.s) + r) << p.b) + p.lo_base + lo0 + c);
+    } else { r = e & (S - 1); c = e >> p.s; gi = ((((i1_0 + c) << rest_bits) + hi_rest) << p.s) + r; gglob = gi; }
     Fr v;
-    if (p.first && gi >= p.n_in) v = fp_zero<FrParams>();
+    if (p.first && gglob >= p.n_in) v = fp_zero<FrParams>();
     else {
       v = ntt_ld_stream(p.src + gi);
-      if (p.first && p.use_pre) { uint32_t m = (uint32_t)(gi % 3); if (m) v = fp_mul(v, p.pre[m]); }
+      if (p.first && p.use_pre) { uint32_t m = (uint32_t)(gglob % 3); if (m) v = fp_mul(v, p.pre[m]); }
     }
     sm.store(c, r, v);
   }
@@ -215,18 +225,19 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
       // K' = i_1 + 2^{s_1} i_2 + ... restricted to the digits done so far. With P <= 3 the digits above the
       // current one are just i_1 (= hi), so K' = hi + 2^a * kd.
       uint64_t kprime = hi + ((uint64_t)kd << p.a);
-      uint64_t lo = lo0 + c;
+      uint64_t lo = lo0 + c, lo_glob = p.lo_base + lo;
       // exponent of omega_n: j_next * K' * 2^(bits below the next digit)
-      uint64_t jn = lo >> p.b_next;
+      uint64_t jn = lo_glob >> p.b_next;
       uint64_t ex = (jn * kprime) << p.b_next;
       if (ex) v = fp_mul(v, ntt_omega_pow(p, ex));
-      uint64_t go = ((((hi << p.s) + kd) << p.b) + lo);
+      uint64_t go = ((((hi << p.s) + kd) << p.b_addr) + lo);
       ntt_stg(p.dst + go, v);
     } else {
       uint64_t o = (i1_0 + c) + (hi_rest << p.s1) + ((uint64_t)kd << p.a);
       if (o < p.n_out) {
         if (p.use_post) v = fp_mul(v, p.post[o % 3]);
-        ntt_stg(p.dst + o, v);
+        uint64_t addr = p.out_local ? (((o >> p.s1) << p.out_cols_log) + (i1_0 + c - p.i1_base)) : o;
+        ntt_stg(p.dst + addr, v);
       }
     }
   }
