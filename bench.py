@@ -241,6 +241,32 @@ def main():
     value = total_pairs / (ms_per_step * 1e-3)
     e2e_value = total_pairs / (e2e_wall_ms / e2e_steps * 1e-3)
 
+    # ---- multi-GPU NTT: one process drives all N devices (six-step across devices, one all-to-all over NVLink) ----
+    ntt_multi = None
+    if world > 1 and not args.no_ntt:
+        barrier()
+        if rank == 0:
+            ntt_multi = {}
+            be_all = halo2.Backend(list(range(world)))
+            root = pow(7, (R_MOD - 1) >> 28, R_MOD)
+            for k in (22, 24):
+                w = pow(root, 1 << (28 - k), R_MOD) * (1 << 256) % R_MOD
+                omega = np.array([[(w >> (64 * j)) & (2**64 - 1) for j in range(4)]], dtype=np.uint64)
+                host = torch.from_numpy(rand_fr(1 << k, k).view(np.int64)).pin_memory()
+                arr = host.numpy().view(np.uint64)
+                dev_ms, wall = [], []
+                for _ in range(4):
+                    t0 = time.perf_counter()
+                    rc = be_all.lib.spb_ntt(be_all.ctx, arr.ctypes.data_as(__import__("ctypes").c_void_p), k, omega.ctypes.data_as(__import__("ctypes").c_void_p))
+                    wall.append((time.perf_counter() - t0) * 1e3)
+                    be_all.check(rc, "spb_ntt (multi-device)")
+                    dev_ms.append(be_all.last_device_ms)
+                ntt_multi["2^%d" % k] = {"devices": world, "device_ms": float(np.median(dev_ms[1:])), "elems_per_s_device": (1 << k) / (float(np.median(dev_ms[1:])) * 1e-3),
+                                         "e2e_ms_pinned_host": float(np.median(wall[1:])),
+                                         "note": "device_ms = first pass + peer all-to-all + remaining passes (max over devices); e2e includes the strided H2D/D2H copies"}
+            be_all.close()
+        barrier()
+
     if rank != 0:
         be.close()
         if world > 1:
@@ -300,6 +326,8 @@ def main():
             ntt["2^%d" % k] = {"ms": ms, "elems_per_s": (1 << k) / (ms * 1e-3), "algo_GBps": (1 << k) * 64 / (ms * 1e-3) / 1e9,
                                "hbm_frac": (1 << k) * 64 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
             del t
+        if ntt_multi:
+            ntt["multi_gpu"] = ntt_multi
         line["ntt"] = ntt
 
     # ---- proof-shaped replay (BASELINE configs 3/5 shapes; see spectre_b200/replay.py for what it is and is not) ----

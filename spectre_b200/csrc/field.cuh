@@ -250,8 +250,11 @@ template <class P> SPB_HD Fp<P> fp_pow(const Fp<P>& a, const uint32_t* e) {
   return r;
 }
 template <class P> SPB_HD Fp<P> fp_pow_u64(const Fp<P>& a, uint64_t e) {
-  Fp<P> r = fp_one<P>();
-  for (int i = 63; i >= 0; i--) {
+  if (e == 0) return fp_one<P>();
+  int top = 63;
+  while (!((e >> top) & 1)) top--;
+  Fp<P> r = a;
+  for (int i = top - 1; i >= 0; i--) {
     r = fp_sqr(r);
     if ((e >> i) & 1) r = fp_mul(r, a);
   }

@@ -7,7 +7,13 @@
 
 namespace spb {
 
-static const uint32_t kTileElemsLog = 12;     // 4096 elements (~135 KB of limb planes) per tile
+// log2 elements per shared-memory tile: 12 = 4096 elements (~135 KB of limb planes, one CTA per SM)
+static uint32_t tile_elems_log() {
+  static uint32_t v = 0;
+  if (!v) { const char* e = getenv("SPB_NTT_TILE_LOG"); v = e ? (uint32_t)atoi(e) : 12; if (v < 6) v = 6; if (v > 12) v = 12; }
+  return v;
+}
+#define kTileElemsLog tile_elems_log()
 // largest sub-NTT held in one shared-memory tile (11: two passes up to 2^22; the tile is then 2048 x 2 columns)
 static uint32_t max_digit_bits() {
   static uint32_t v = 0;
@@ -109,7 +115,9 @@ static int launch_pass(spb_ctx* ctx, DeviceState& d, const NttPlan& plan, uint32
   p.src = src; p.dst = dst;
   uint32_t S = 1u << p.s, C = 1u << logc;
   uint32_t quads = (S * C) / 4; if (quads < 32) quads = 32;
-  uint32_t threads = quads < 512 ? quads : 512;
+  static uint32_t max_threads = 0;
+  if (!max_threads) { const char* e = getenv("SPB_NTT_THREADS"); max_threads = e ? (uint32_t)atoi(e) : 512; if (max_threads < 32 || max_threads > 512) max_threads = 512; }
+  uint32_t threads = quads < max_threads ? quads : max_threads;
   size_t smem = (size_t)8 * 4 * ((size_t)ntt_col_stride(S, C) * C + ntt_tw_words(S));
   if (smem > 227 * 1024) return set_error(ctx, SPB_ERR_STATE, "ntt: tile needs %zu B of shared memory", smem);
   ntt_pass_kernel<<<(unsigned)tiles, threads, smem, d.stream>>>(p);

@@ -95,16 +95,23 @@ __global__ void inv_partials_kernel(Fr* partial, uint64_t m) {
 }
 
 // ---- polynomial evaluation: p(x) = sum_t x^t * q_t(x^T), q_t = coefficients t, t+T, ... (coalesced Horner) ------
-__global__ void eval_strided_kernel(const Fr* poly, uint64_t n, Fr x, Fr xT, uint32_t T, Fr* partial) {
+// T threads in blocks of 256; each block folds its 256 terms with a shared-memory tree and writes one partial.
+__global__ void __launch_bounds__(256) eval_strided_kernel(const Fr* poly, uint64_t n, Fr x, Fr xT, uint32_t T, Fr* partial) {
+  __shared__ Fr sh[128];
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
   Fr acc = fp_zero<FrParams>();
-  if (t < n) {
+  if (t < T && t < n) {
     uint64_t last = t + ((n - 1 - t) / T) * T;
     for (uint64_t i = last;; i -= T) { acc = fp_add(fp_mul(acc, xT), ntt_ldg(poly + i)); if (i < T) break; }
     acc = fp_mul(acc, fp_pow_u64(x, t));
   }
-  partial[t] = acc;
+  for (int stride = 128; stride >= 1; stride >>= 1) {
+    if ((int)threadIdx.x >= stride && (int)threadIdx.x < 2 * stride) sh[threadIdx.x - stride] = acc;
+    __syncthreads();
+    if ((int)threadIdx.x < stride) acc = fp_add(acc, sh[threadIdx.x]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
 
@@ -177,16 +184,19 @@ int dev_batch_invert(spb_ctx* ctx, DeviceState& d, Fr* da, size_t n) {
 }
 
 int dev_eval_polynomial(spb_ctx* ctx, DeviceState& d, const Fr* dp, size_t n, const Fr& x, Fr* out_host) {
-  const uint32_t T = 4096;
-  Fr* dpart = (Fr*)slot(ctx, d, "poly_partial", (size_t)T * 32 > 0 ? (size_t)T * 32 : 32);
+  // enough threads that each runs a short Horner chain (16 steps at n = 2^20), a multiple of the block size
+  uint32_t T = 256;
+  while (T < 65536 && (uint64_t)T * 16 < n) T <<= 1;
+  const uint32_t blocks = T / 256;
+  Fr* dpart = (Fr*)slot(ctx, d, "poly_partial", (size_t)blocks * 32 > 64 ? (size_t)blocks * 32 : 64);
   if (!dpart) return SPB_ERR_OOM;
-  eval_strided_kernel<<<T / 128, 128, 0, d.stream>>>(dp, n, x, fp_pow_u64(x, T), T, dpart);
+  eval_strided_kernel<<<blocks, 256, 0, d.stream>>>(dp, n, x, fp_pow_u64(x, T), T, dpart);
   ctx->n_kernel_launches++;
-  std::vector<Fr> part(T);
-  SPB_CUDA(ctx, cudaMemcpyAsync(part.data(), dpart, T * 32, cudaMemcpyDeviceToHost, d.stream));
+  std::vector<Fr> part(blocks);
+  SPB_CUDA(ctx, cudaMemcpyAsync(part.data(), dpart, (size_t)blocks * 32, cudaMemcpyDeviceToHost, d.stream));
   SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
   Fr acc = fp_zero<FrParams>();
-  for (uint32_t t = 0; t < T; t++) acc = fp_add(acc, part[t]);
+  for (uint32_t t = 0; t < blocks; t++) acc = fp_add(acc, part[t]);
   *out_host = acc;
   return 0;
 }
