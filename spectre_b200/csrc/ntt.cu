@@ -7,13 +7,16 @@
 
 namespace spb {
 
-// log2 elements per shared-memory tile: 12 = 4096 elements (~135 KB of limb planes, one CTA per SM)
-static uint32_t tile_elems_log() {
-  static uint32_t v = 0;
-  if (!v) { const char* e = getenv("SPB_NTT_TILE_LOG"); v = e ? (uint32_t)atoi(e) : 12; if (v < 6) v = 6; if (v > 12) v = 12; }
-  return v;
+// log2 elements per shared-memory tile. 2^11 elements (~68 KB of limb planes + twiddles) with 256 threads lets two
+// CTAs share an SM, so one tile's global load/store phases overlap the other's butterflies: measured 8-15 % faster
+// than one 2^12-element CTA per SM (profiles/r01_bench_progress.md, NTT knob sweep); 2^10 is best up to 2^20.
+static uint32_t g_tile_log_override = 0;
+static uint32_t tile_elems_log(uint32_t k) {
+  static bool init = false;
+  if (!init) { const char* e = getenv("SPB_NTT_TILE_LOG"); if (e) { g_tile_log_override = (uint32_t)atoi(e); if (g_tile_log_override < 6) g_tile_log_override = 6; if (g_tile_log_override > 12) g_tile_log_override = 12; } init = true; }
+  if (g_tile_log_override) return g_tile_log_override;
+  return k <= 20 ? 10 : 11;
 }
-#define kTileElemsLog tile_elems_log()
 // largest sub-NTT held in one shared-memory tile (11: two passes up to 2^22; the tile is then 2048 x 2 columns)
 static uint32_t max_digit_bits() {
   static uint32_t v = 0;
@@ -103,7 +106,8 @@ static int launch_pass(spb_ctx* ctx, DeviceState& d, const NttPlan& plan, uint32
   uint32_t avail = p.last ? (p.a ? p.s1 : 0) : p.b;
   if (sh.mode == 1) { avail = p.b - sh.g_log; p.b_addr = p.b - sh.g_log; p.lo_base = (uint64_t)sh.q << p.b_addr; }
   if (sh.mode == 2 && p.last) avail = p.s1 - sh.g_log;
-  uint32_t logc = kTileElemsLog > p.s ? kTileElemsLog - p.s : 0;
+  const uint32_t tile_log = tile_elems_log(k);
+  uint32_t logc = tile_log > p.s ? tile_log - p.s : 0;
   if (logc > avail) logc = avail;
   if (logc > 5) logc = 5;
   p.logc = logc;
@@ -116,7 +120,7 @@ static int launch_pass(spb_ctx* ctx, DeviceState& d, const NttPlan& plan, uint32
   uint32_t S = 1u << p.s, C = 1u << logc;
   uint32_t quads = (S * C) / 4; if (quads < 32) quads = 32;
   static uint32_t max_threads = 0;
-  if (!max_threads) { const char* e = getenv("SPB_NTT_THREADS"); max_threads = e ? (uint32_t)atoi(e) : 512; if (max_threads < 32 || max_threads > 512) max_threads = 512; }
+  if (!max_threads) { const char* e = getenv("SPB_NTT_THREADS"); max_threads = e ? (uint32_t)atoi(e) : 256; if (max_threads < 32 || max_threads > 512) max_threads = 512; }
   uint32_t threads = quads < max_threads ? quads : max_threads;
   size_t smem = (size_t)8 * 4 * ((size_t)ntt_col_stride(S, C) * C + ntt_tw_words(S));
   if (smem > 227 * 1024) return set_error(ctx, SPB_ERR_STATE, "ntt: tile needs %zu B of shared memory", smem);
