@@ -164,6 +164,37 @@ int spb_vec_scale_dev(spb_ctx* ctx, spb_fr* d_a, const spb_fr* alpha, size_t n);
  * none of them. One streaming pass over every input. */
 int spb_lincomb_dev(spb_ctx* ctx, const spb_fr* const* d_polys, size_t count, const spb_fr* y, spb_fr* d_out, size_t n);
 
+/* ---- quotient numerator ([UPSTREAM] halo2_proofs/src/plonk/evaluation.rs: GraphEvaluator, Evaluator::evaluate_h) ---- */
+/* The gate graph in the flat encoding the Rust shim emits from GraphEvaluator's `calculations`:
+ *   per calculation: word0 = op | nparts << 8  (op: 0 Add 1 Sub 2 Mul 3 Square 4 Double 5 Negate 6 Horner 7 Store),
+ *                    word1 = target intermediate, then sources of two words each: kind, idx | rot_idx << 16
+ *   kind: 0 Constant 1 Intermediate 2 Fixed 3 Advice 4 Instance 5 Challenge 6 Beta 7 Gamma 8 Theta 9 Y 10 PreviousValue
+ *   Add/Sub/Mul: a, b.  Square/Double/Negate/Store: a.  Horner: start, factor, then nparts parts. */
+typedef struct {
+  const uint32_t* program;
+  size_t program_words;
+  uint32_t num_calculations, num_intermediates;
+  const spb_fr* constants;
+  uint32_t num_constants;
+  const int32_t* rotations;
+  uint32_t num_rotations;
+} spb_graph;
+/* values[idx] <- graph(idx) for every extended row idx < size (PreviousValue = the old values[idx]); column arrays are
+ * HOST arrays of device pointers to extended-coset polynomials; rot_scale = 2^(extended_k - k). */
+int spb_graph_evaluate_dev(spb_ctx* ctx, const spb_graph* g, const spb_fr* const* d_fixed, uint32_t n_fixed, const spb_fr* const* d_advice, uint32_t n_advice,
+                           const spb_fr* const* d_instance, uint32_t n_instance, const spb_fr* challenges, uint32_t n_challenges, const spb_fr* beta,
+                           const spb_fr* gamma, const spb_fr* theta, const spb_fr* y, spb_fr* d_values, uint64_t size, int32_t rot_scale);
+/* permutation-argument terms of evaluate_h folded into values with powers of y. d_z: n_sets product cosets; d_col_values /
+ * d_sigma: the n_cols permuted columns' value and sigma cosets in permutation order (chunk_len per set). */
+int spb_permutation_constraints_dev(spb_ctx* ctx, spb_fr* d_values, uint64_t size, int32_t rot_scale, int32_t last_rotation, uint32_t n_sets, uint32_t chunk_len,
+                                    const spb_fr* const* d_z, uint32_t n_cols, const spb_fr* const* d_col_values, const spb_fr* const* d_sigma,
+                                    const spb_fr* d_l0, const spb_fr* d_l_last, const spb_fr* d_l_active, const spb_fr* beta, const spb_fr* gamma,
+                                    const spb_fr* y, const spb_fr* extended_omega);
+/* the five lookup-argument terms of one lookup; d_table_value[idx] = (compressed input + beta)(compressed table + gamma) */
+int spb_lookup_constraints_dev(spb_ctx* ctx, spb_fr* d_values, uint64_t size, int32_t rot_scale, const spb_fr* d_product, const spb_fr* d_permuted_input,
+                               const spb_fr* d_permuted_table, const spb_fr* d_table_value, const spb_fr* d_l0, const spb_fr* d_l_last,
+                               const spb_fr* d_l_active, const spb_fr* beta, const spb_fr* gamma, const spb_fr* y);
+
 /* ---- test / bench utilities -------------------------------------------------------------------------------- */
 /* out[i] = scalars[i] * G1 (affine), computed on the device */
 int spb_g1_fixed_base_mul(spb_ctx* ctx, const spb_fr* scalars, size_t n, spb_g1_affine* out);

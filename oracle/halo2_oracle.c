@@ -739,3 +739,126 @@ void orc_commit_lagrange_known_tau(uint32_t k, const fe* evals, size_t n_used, g
   fb_table_build();
   g1j p = fb_mul(&acc); *out = g1j_to_affine(&p);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Quotient numerator: [UPSTREAM] halo2_proofs/src/plonk/evaluation.rs -- GraphEvaluator::evaluate,
+ * Evaluator::evaluate_h (custom gates, permutation argument, lookup argument), restated from the PSE fork
+ * (SURVEY.md 8a row a6). No reference-owned vector pins these (no Rust host, proofs are randomised), so
+ * parity for this row is GPU vs this restatement on synthetic constraint systems: "parity unpinned".
+ *
+ * Program encoding shared with the CUDA side (spectre_b200/csrc/quotient.cu): a calculation is
+ *   word0 = op | nparts << 8        op: 0 Add 1 Sub 2 Mul 3 Square 4 Double 5 Negate 6 Horner 7 Store
+ *   word1 = target intermediate
+ *   then sources, two words each: kind, idx | rot_idx << 16
+ *       kind: 0 Constant 1 Intermediate 2 Fixed 3 Advice 4 Instance 5 Challenge 6 Beta 7 Gamma 8 Theta 9 Y 10 PreviousValue
+ *   Add/Sub/Mul: a, b. Square/Double/Negate/Store: a. Horner: start, factor, then nparts parts.
+ * ---------------------------------------------------------------------------------------------- */
+static inline uint64_t rotation_idx(uint64_t idx, int32_t rot, int32_t rot_scale, int64_t isize) {
+  int64_t v = ((int64_t)idx + (int64_t)rot * rot_scale) % isize;
+  if (v < 0) v += isize;
+  return (uint64_t)v;
+}
+typedef struct {
+  const fe* constants; const fe* inter; const uint64_t* rot_idx;
+  const fe* const* fixed; const fe* const* advice; const fe* const* instance; const fe* challenges;
+  const fe* bgty; fe previous;
+} graph_env;
+static inline fe graph_src(const graph_env* e, const uint32_t* w) {
+  uint32_t kind = w[0], idx = w[1] & 0xffff, rot = w[1] >> 16;
+  switch (kind) {
+    case 0: return e->constants[idx];
+    case 1: return e->inter[idx];
+    case 2: return e->fixed[idx][e->rot_idx[rot]];
+    case 3: return e->advice[idx][e->rot_idx[rot]];
+    case 4: return e->instance[idx][e->rot_idx[rot]];
+    case 5: return e->challenges[idx];
+    case 6: return e->bgty[0];
+    case 7: return e->bgty[1];
+    case 8: return e->bgty[2];
+    case 9: return e->bgty[3];
+    default: return e->previous;
+  }
+}
+void orc_graph_evaluate(const uint32_t* prog, uint32_t ncalc, uint32_t n_inter, const fe* constants, const int32_t* rotations, uint32_t nrot,
+                        const fe* const* fixed, const fe* const* advice, const fe* const* instance, const fe* challenges, const fe* bgty,
+                        fe* values, uint64_t size, int32_t rot_scale) {
+  fe* inter = (fe*)malloc((n_inter ? n_inter : 1) * sizeof(fe));
+  uint64_t* ridx = (uint64_t*)malloc((nrot ? nrot : 1) * sizeof(uint64_t));
+  for (uint64_t idx = 0; idx < size; idx++) {
+    for (uint32_t r = 0; r < nrot; r++) ridx[r] = rotation_idx(idx, rotations[r], rot_scale, (int64_t)size);
+    graph_env e = {constants, inter, ridx, fixed, advice, instance, challenges, bgty, values[idx]};
+    const uint32_t* w = prog;
+    fe last; memset(&last, 0, sizeof last);
+    for (uint32_t c = 0; c < ncalc; c++) {
+      uint32_t op = w[0] & 0xff, nparts = w[0] >> 8, target = w[1];
+      fe r;
+      if (op <= 2) {
+        fe a = graph_src(&e, w + 2), b = graph_src(&e, w + 4);
+        r = op == 0 ? f_add(&FR, a, b) : op == 1 ? f_sub(&FR, a, b) : f_mul(&FR, a, b);
+        w += 6;
+      } else if (op == 6) {
+        fe acc = graph_src(&e, w + 2), factor = graph_src(&e, w + 4);
+        for (uint32_t p = 0; p < nparts; p++) acc = f_add(&FR, f_mul(&FR, acc, factor), graph_src(&e, w + 6 + 2 * p));
+        r = acc; w += 6 + 2 * nparts;
+      } else {
+        fe a = graph_src(&e, w + 2);
+        r = op == 3 ? f_sqr(&FR, a) : op == 4 ? f_dbl(&FR, a) : op == 5 ? f_neg(&FR, a) : a;
+        w += 4;
+      }
+      inter[target] = r; last = r;
+    }
+    values[idx] = ncalc ? last : (fe){{0, 0, 0, 0}};
+  }
+  free(inter); free(ridx);
+}
+
+/* Permutation argument part of evaluate_h. sets: n_sets product cosets z_i; columns: n_cols value cosets and sigma
+ * cosets in permutation order, chunk_len per set (last set may be short). */
+void orc_permutation_constraints(fe* values, uint64_t size, int32_t rot_scale, int32_t last_rotation, uint32_t n_sets, uint32_t chunk_len,
+                                 const fe* const* z, uint32_t n_cols, const fe* const* col_values, const fe* const* sigma,
+                                 const fe* l0, const fe* l_last, const fe* l_active, const fe* beta, const fe* gamma, const fe* y,
+                                 const fe* delta, const fe* extended_omega) {
+  if (!n_sets) return;
+  fe delta_start = f_mul(&FR, *beta, FR_ZETA);
+  fe beta_term = FR.r;  /* extended_omega^idx */
+  for (uint64_t idx = 0; idx < size; idx++) {
+    uint64_t r_next = rotation_idx(idx, 1, rot_scale, (int64_t)size), r_last = rotation_idx(idx, last_rotation, rot_scale, (int64_t)size);
+    fe v = values[idx];
+    v = f_add(&FR, f_mul(&FR, v, *y), f_mul(&FR, f_sub(&FR, FR.r, z[0][idx]), l0[idx]));
+    fe zl = z[n_sets - 1][idx];
+    v = f_add(&FR, f_mul(&FR, v, *y), f_mul(&FR, f_sub(&FR, f_sqr(&FR, zl), zl), l_last[idx]));
+    for (uint32_t s = 1; s < n_sets; s++)
+      v = f_add(&FR, f_mul(&FR, v, *y), f_mul(&FR, f_sub(&FR, z[s][idx], z[s - 1][r_last]), l0[idx]));
+    fe current_delta = f_mul(&FR, delta_start, beta_term);
+    for (uint32_t s = 0; s < n_sets; s++) {
+      uint32_t lo = s * chunk_len, hi = lo + chunk_len < n_cols ? lo + chunk_len : n_cols;
+      fe left = z[s][r_next], right = z[s][idx];
+      for (uint32_t c = lo; c < hi; c++) left = f_mul(&FR, left, f_add(&FR, f_add(&FR, col_values[c][idx], f_mul(&FR, *beta, sigma[c][idx])), *gamma));
+      for (uint32_t c = lo; c < hi; c++) { right = f_mul(&FR, right, f_add(&FR, f_add(&FR, col_values[c][idx], current_delta), *gamma)); current_delta = f_mul(&FR, current_delta, *delta); }
+      v = f_add(&FR, f_mul(&FR, v, *y), f_mul(&FR, f_sub(&FR, left, right), l_active[idx]));
+    }
+    values[idx] = v;
+    beta_term = f_mul(&FR, beta_term, *extended_omega);
+  }
+}
+
+/* Lookup argument part of evaluate_h for one lookup; table_value[idx] = (compressed input + beta)(compressed table + gamma)
+ * as produced by that lookup's GraphEvaluator. */
+void orc_lookup_constraints(fe* values, uint64_t size, int32_t rot_scale, const fe* product, const fe* permuted_input, const fe* permuted_table,
+                            const fe* table_value, const fe* l0, const fe* l_last, const fe* l_active, const fe* beta, const fe* gamma, const fe* y) {
+  for (uint64_t idx = 0; idx < size; idx++) {
+    uint64_t r_next = rotation_idx(idx, 1, rot_scale, (int64_t)size), r_prev = rotation_idx(idx, -1, rot_scale, (int64_t)size);
+    fe a_minus_s = f_sub(&FR, permuted_input[idx], permuted_table[idx]);
+    fe v = values[idx], zp = product[idx];
+    v = f_add(&FR, f_mul(&FR, v, *y), f_mul(&FR, f_sub(&FR, FR.r, zp), l0[idx]));
+    v = f_add(&FR, f_mul(&FR, v, *y), f_mul(&FR, f_sub(&FR, f_sqr(&FR, zp), zp), l_last[idx]));
+    fe lhs = f_mul(&FR, f_mul(&FR, product[r_next], f_add(&FR, permuted_input[idx], *beta)), f_add(&FR, permuted_table[idx], *gamma));
+    v = f_add(&FR, f_mul(&FR, v, *y), f_mul(&FR, f_sub(&FR, lhs, f_mul(&FR, zp, table_value[idx])), l_active[idx]));
+    v = f_add(&FR, f_mul(&FR, v, *y), f_mul(&FR, a_minus_s, l0[idx]));
+    v = f_add(&FR, f_mul(&FR, v, *y), f_mul(&FR, f_mul(&FR, a_minus_s, f_sub(&FR, permuted_input[idx], permuted_input[r_prev])), l_active[idx]));
+    values[idx] = v;
+  }
+}
+void orc_fr_delta(fe* out) {  /* Fr::DELTA = MULTIPLICATIVE_GENERATOR^(2^S) = 7^(2^28) */
+  *out = f_pow(&FR, f_from_u64(&FR, 7), (uint64_t[4]){1ull << 28, 0, 0, 0});
+}

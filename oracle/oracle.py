@@ -274,3 +274,43 @@ def fr_seq(n):
     out = np.zeros((n, 4), dtype=np.uint64)
     lib().orc_fr_seq(_p(out), ctypes.c_size_t(n))
     return out
+
+
+# ---- quotient numerator (evaluate_h pieces) ----------------------------------------------------------
+def _ptr_array(arrs):
+    arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in arrs]
+    return (ctypes.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs]), arrs
+
+
+def fr_delta():
+    out = np.empty(4, dtype=np.uint64)
+    lib().orc_fr_delta(_p(out))
+    return out
+
+
+def graph_evaluate(prog, ncalc, n_inter, constants, rotations, fixed, advice, instance, challenges, bgty, values, rot_scale):
+    prog = np.ascontiguousarray(prog, dtype=np.uint32); rotations = np.ascontiguousarray(rotations, dtype=np.int32)
+    constants = np.ascontiguousarray(constants, dtype=np.uint64).reshape(-1, 4)
+    challenges = np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4); bgty = np.ascontiguousarray(bgty, dtype=np.uint64).reshape(4, 4)
+    values = np.ascontiguousarray(values, dtype=np.uint64).copy()
+    pf, kf = _ptr_array(fixed); pa, ka = _ptr_array(advice); pi, ki = _ptr_array(instance)
+    lib().orc_graph_evaluate(_p(prog), ctypes.c_uint32(ncalc), ctypes.c_uint32(n_inter), _p(constants), _p(rotations), ctypes.c_uint32(len(rotations)),
+                             pf, pa, pi, _p(challenges), _p(bgty), _p(values), ctypes.c_uint64(values.shape[0]), ctypes.c_int32(rot_scale))
+    return values
+
+
+def permutation_constraints(values, rot_scale, last_rotation, chunk_len, z, col_values, sigma, l0, l_last, l_active, beta, gamma, y, extended_omega):
+    values = np.ascontiguousarray(values, dtype=np.uint64).copy()
+    pz, kz = _ptr_array(z); pc, kc = _ptr_array(col_values); ps, ks = _ptr_array(sigma)
+    d = fr_delta()
+    args = [np.ascontiguousarray(a, dtype=np.uint64) for a in (l0, l_last, l_active, beta, gamma, y, d, extended_omega)]
+    lib().orc_permutation_constraints(_p(values), ctypes.c_uint64(values.shape[0]), ctypes.c_int32(rot_scale), ctypes.c_int32(last_rotation), ctypes.c_uint32(len(z)),
+                                      ctypes.c_uint32(chunk_len), pz, ctypes.c_uint32(len(col_values)), pc, ps, *[_p(a) for a in args])
+    return values
+
+
+def lookup_constraints(values, rot_scale, product, permuted_input, permuted_table, table_value, l0, l_last, l_active, beta, gamma, y):
+    values = np.ascontiguousarray(values, dtype=np.uint64).copy()
+    args = [np.ascontiguousarray(a, dtype=np.uint64) for a in (product, permuted_input, permuted_table, table_value, l0, l_last, l_active, beta, gamma, y)]
+    lib().orc_lookup_constraints(_p(values), ctypes.c_uint64(values.shape[0]), ctypes.c_int32(rot_scale), *[_p(a) for a in args])
+    return values

@@ -217,6 +217,37 @@ class Backend:
     def vec_scale_dev(self, d_a, alpha, n):
         self.check(self.lib.spb_vec_scale_dev(self.ctx, _p(d_a), _p(_fr_array(alpha, 1)), ctypes.c_size_t(n)), "spb_vec_scale_dev")
 
+    # ---- quotient numerator (plonk::evaluation) ---------------------------------------------------------
+    def graph_evaluate_dev(self, prog, ncalc, n_inter, constants, rotations, d_fixed, d_advice, d_instance, challenges, beta, gamma, theta, y,
+                           d_values, size, rot_scale):
+        """GraphEvaluator::evaluate for every extended row; column lists hold device addresses (ints)."""
+        class _Graph(ctypes.Structure):
+            _fields_ = [("program", ctypes.c_void_p), ("program_words", ctypes.c_size_t), ("num_calculations", ctypes.c_uint32),
+                        ("num_intermediates", ctypes.c_uint32), ("constants", ctypes.c_void_p), ("num_constants", ctypes.c_uint32),
+                        ("rotations", ctypes.c_void_p), ("num_rotations", ctypes.c_uint32)]
+        prog = np.ascontiguousarray(prog, dtype=np.uint32); rotations = np.ascontiguousarray(rotations, dtype=np.int32)
+        constants = np.ascontiguousarray(constants, dtype=np.uint64).reshape(-1, 4)
+        challenges = np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4)
+        g = _Graph(prog.ctypes.data, prog.size, ncalc, n_inter, constants.ctypes.data, constants.shape[0], rotations.ctypes.data, rotations.size)
+        mk = lambda ps: (ctypes.c_void_p * max(1, len(ps)))(*ps)
+        self.check(self.lib.spb_graph_evaluate_dev(self.ctx, ctypes.byref(g), mk(d_fixed), len(d_fixed), mk(d_advice), len(d_advice), mk(d_instance), len(d_instance),
+                                                   _p(challenges), challenges.shape[0], _p(_fr_array(beta, 1)), _p(_fr_array(gamma, 1)), _p(_fr_array(theta, 1)),
+                                                   _p(_fr_array(y, 1)), _p(d_values), ctypes.c_uint64(size), ctypes.c_int32(rot_scale)), "spb_graph_evaluate_dev")
+
+    def permutation_constraints_dev(self, d_values, size, rot_scale, last_rotation, chunk_len, d_z, d_col_values, d_sigma, d_l0, d_l_last, d_l_active,
+                                    beta, gamma, y, extended_omega):
+        mk = lambda ps: (ctypes.c_void_p * max(1, len(ps)))(*ps)
+        self.check(self.lib.spb_permutation_constraints_dev(self.ctx, _p(d_values), ctypes.c_uint64(size), ctypes.c_int32(rot_scale), ctypes.c_int32(last_rotation),
+                                                            len(d_z), chunk_len, mk(d_z), len(d_col_values), mk(d_col_values), mk(d_sigma), _p(d_l0), _p(d_l_last),
+                                                            _p(d_l_active), _p(_fr_array(beta, 1)), _p(_fr_array(gamma, 1)), _p(_fr_array(y, 1)),
+                                                            _p(_fr_array(extended_omega, 1))), "spb_permutation_constraints_dev")
+
+    def lookup_constraints_dev(self, d_values, size, rot_scale, d_product, d_permuted_input, d_permuted_table, d_table_value, d_l0, d_l_last, d_l_active,
+                               beta, gamma, y):
+        self.check(self.lib.spb_lookup_constraints_dev(self.ctx, _p(d_values), ctypes.c_uint64(size), ctypes.c_int32(rot_scale), _p(d_product), _p(d_permuted_input),
+                                                       _p(d_permuted_table), _p(d_table_value), _p(d_l0), _p(d_l_last), _p(d_l_active), _p(_fr_array(beta, 1)),
+                                                       _p(_fr_array(gamma, 1)), _p(_fr_array(y, 1))), "spb_lookup_constraints_dev")
+
     # ---- utilities -------------------------------------------------------------------------------------
     def g1_fixed_base_mul(self, scalars):
         scalars = _fr_array(scalars)
