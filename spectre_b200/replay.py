@@ -5,9 +5,11 @@ C ABI on synthetic columns.
 This is NOT a proof: without a Rust host there is no circuit, witness or transcript here. It is the in-container proxy
 SURVEY.md 7 ("Hard parts") prescribes for BASELINE configs 3-5 -- every primitive call a proof of that shape makes,
 with the right sizes, counts and data residency -- so that "proof-generation seconds" can be reported for the GPU path
-and extrapolated for the CPU path from the same primitives' measured CPU times. evaluate_h's gate arithmetic is
-circuit specific; its stand-in is one fold-with-powers-of-y pass over every extended polynomial (the same HBM traffic:
-each extended polynomial read once, one written; fewer multiplications per row than the real gate graph).
+and extrapolated for the CPU path from the same primitives' measured CPU times. evaluate_h runs through the real
+kernels (graph evaluator + permutation + lookup constraints) on a synthetic constraint system of the right shape: one
+halo2-lib basic gate q*(a + b*c - d) per advice column, the permutation argument over all equality-enabled columns in
+chunks of (degree - 2), and per lookup a theta-compression graph plus the five lookup terms. The SHA gate sets of the
+real circuits are not modelled (their column counts are, through A).
 """
 import time
 
@@ -95,9 +97,44 @@ def replay(be, shape_name, tau, seed=1, tables=True, verbose=False):
         for c, e in zip(cols, ext):
             dom.coeff_to_extended_dev(ptr(c), ptr(e))
     timed("8a_coeff_to_extended", to_extended)
-    # evaluate_h stand-in: fold computed + proving-key-resident extended polynomials with powers of y
-    all_ext = [ptr(e) for e in ext] + [ptr(ext[i % n_polys]) for i in range(F)]
-    timed("8b_quotient_fold_standin", lambda: be.lincomb_dev(all_ext, y, ptr(scratch), E))
+    # evaluate_h on the extended coset: custom gates (graph), permutation argument, lookups
+    rot_scale = 1 << (dom.extended_k - k)
+    ADD, SUB, MUL, HORNER = 0, 1, 2, 6
+    K_INTER, K_FIXED, K_ADVICE, K_BETA, K_GAMMA, K_THETA, K_Y, K_PREV = 1, 2, 3, 6, 7, 8, 9, 10
+    rotations = np.array([0, 1, 2, 3], dtype=np.int32)
+    prog, t = [], 0
+    for a_i in range(A):                                   # q_a * (a + b*c - d) with b,c,d at rotations 1,2,3; fold with y
+        prog += [MUL, t, K_ADVICE, a_i | (1 << 16), K_ADVICE, a_i | (2 << 16)]
+        prog += [ADD, t + 1, K_ADVICE, a_i, K_INTER, t]
+        prog += [SUB, t + 2, K_INTER, t + 1, K_ADVICE, a_i | (3 << 16)]
+        prog += [MUL, t + 3, K_FIXED, a_i % max(1, F), K_INTER, t + 2]
+        prog += [HORNER | (1 << 8), t + 4, (K_PREV if a_i == 0 else K_INTER), (0 if a_i == 0 else t - 1), K_Y, 0, K_INTER, t + 3]
+        t += 5
+    gate_prog = np.array(prog, dtype=np.uint32)
+    fixed_ext = [ptr(ext[i % n_polys]) for i in range(max(1, F))]       # proving-key cosets (resident in a real prover)
+    advice_ext = [ptr(e) for e in ext[:A]]
+    zero = np.zeros((1, 4), dtype=np.uint64)
+    beta, gamma, theta = y, x, y
+    perm_cols = [ptr(e) for e in ext[:A + 1]] + fixed_ext[:1]            # advice + instance + one constant column
+    chunk = max(1, j - 2)
+    n_sets = (len(perm_cols) + chunk - 1) // chunk
+    z_sets = [ptr(ext[(A + 1 + i) % n_polys]) for i in range(n_sets)]
+    sigma = [fixed_ext[i % len(fixed_ext)] for i in range(len(perm_cols))]
+    l0, l_last, l_active = fixed_ext[0], fixed_ext[-1], fixed_ext[len(fixed_ext) // 2]
+    lk_prog = np.array([HORNER | (1 << 8), 0, K_ADVICE, 0, K_THETA, 0, K_ADVICE, 0 | (1 << 16),      # compressed input
+                        HORNER | (1 << 8), 1, K_FIXED, 0, K_THETA, 0, K_FIXED, 0 | (1 << 16),        # compressed table
+                        ADD, 2, K_INTER, 0, K_BETA, 0, ADD, 3, K_INTER, 1, K_GAMMA, 0, MUL, 4, K_INTER, 2, K_INTER, 3], dtype=np.uint32)
+    table_value = torch.empty((E, 4), dtype=torch.int64, device=dev)
+
+    def evaluate_h():
+        be.graph_evaluate_dev(gate_prog, 5 * A, 5 * A, zero, rotations, fixed_ext, advice_ext, [], zero, beta, gamma, theta, y, ptr(scratch), E, rot_scale)
+        be.permutation_constraints_dev(ptr(scratch), E, rot_scale, -(6 + 1), chunk, z_sets, perm_cols, sigma, l0, l_last, l_active, beta, gamma, y, dom.extended_omega)
+        for li in range(L):
+            be.graph_evaluate_dev(lk_prog, 5, 5, zero, rotations, fixed_ext, [advice_ext[li % A]], [], zero, beta, gamma, theta, y, ptr(table_value), E, rot_scale)
+            lp = (A + 1 + P + 3 * li) % n_polys
+            be.lookup_constraints_dev(ptr(scratch), E, rot_scale, ptr(ext[lp]), ptr(ext[(lp + 1) % n_polys]), ptr(ext[(lp + 2) % n_polys]), ptr(table_value),
+                                      l0, l_last, l_active, beta, gamma, y)
+    timed("8b_evaluate_h", evaluate_h)
 
     def vanishing():
         dom.divide_by_vanishing_poly_dev(ptr(scratch))
