@@ -250,11 +250,53 @@ inline G1Xyzz msm_tail_finish(const MsmGeom& g, const G1Xyzz* part) {
 // ---- kernels --------------------------------------------------------------------------------------------
 // The number of sorted entries M is read from device memory (the last element of the offset scan), so the
 // whole MSM is enqueued without a host round trip between the sort and the accumulation.
+// Warp-aggregated versions of msm_count_thread / msm_scatter_thread: lanes whose digit lands in the same bucket
+// (witness columns are full of repeated small values) are found with match.any and served by ONE atomic, so a column
+// of equal scalars costs one atomic per warp and window instead of 32 serialised ones on the same address. The loop
+// is kept convergent (inactive lanes carry a flag instead of leaving) so the warp-level primitives are well defined.
 __global__ void msm_count_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* counts) {
-  msm_count_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, n, scalars, g, counts);
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool live = tid < n;
+  Fr s = live ? fp_from_mont(scalars[tid]) : fp_zero<FrParams>();
+  live = live && !fp_is_zero(s);
+  DigitIter it; it.init(s, g.c);
+  for (uint32_t w = 0; w < g.W; w++) {
+    int32_t d = it.next();
+    const bool act = live && d != 0;
+    const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    const uint32_t key = (g.precomp ? 0u : w * g.B) + mag - 1;
+    const unsigned actmask = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      const unsigned peers = __match_any_sync(actmask, key);
+      if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
+    }
+  }
 }
 __global__ void msm_scatter_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* cursor, MsmEntry* ent) {
-  msm_scatter_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, n, scalars, g, cursor, ent);
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool live = tid < n;
+  Fr s = live ? fp_from_mont(scalars[tid]) : fp_zero<FrParams>();
+  live = live && !fp_is_zero(s);
+  DigitIter it; it.init(s, g.c);
+  for (uint32_t w = 0; w < g.W; w++) {
+    int32_t d = it.next();
+    const bool act = live && d != 0;
+    const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    const uint32_t key = (g.precomp ? 0u : w * g.B) + mag - 1;
+    const unsigned actmask = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      const unsigned peers = __match_any_sync(actmask, key);
+      const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      MsmEntry e; e.key = key; e.val = ((uint32_t)tid + (g.precomp ? w * g.tab_stride : 0u)) | (d < 0 ? 0x80000000u : 0u);
+      ent[pos] = e;
+    }
+  }
 }
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* total, MsmGeom g, const MsmEntry* ent,
                                                              const G1Affine* bases, G1Xyzz* buckets, uint32_t* head_key, G1Xyzz* head,
