@@ -254,14 +254,14 @@ def main():
                 omega = np.array([[(w >> (64 * j)) & (2**64 - 1) for j in range(4)]], dtype=np.uint64)
                 host = torch.from_numpy(rand_fr(1 << k, k).view(np.int64)).pin_memory()
                 arr = host.numpy().view(np.uint64)
-                dev_ms, wall = [], []
+                nd_ms, wall = [], []
                 for _ in range(4):
                     t0 = time.perf_counter()
                     rc = be_all.lib.spb_ntt(be_all.ctx, arr.ctypes.data_as(__import__("ctypes").c_void_p), k, omega.ctypes.data_as(__import__("ctypes").c_void_p))
                     wall.append((time.perf_counter() - t0) * 1e3)
                     be_all.check(rc, "spb_ntt (multi-device)")
-                    dev_ms.append(be_all.last_device_ms)
-                ntt_multi["2^%d" % k] = {"devices": world, "device_ms": float(np.median(dev_ms[1:])), "elems_per_s_device": (1 << k) / (float(np.median(dev_ms[1:])) * 1e-3),
+                    nd_ms.append(be_all.last_device_ms)
+                ntt_multi["2^%d" % k] = {"devices": world, "device_ms": float(np.median(nd_ms[1:])), "elems_per_s_device": (1 << k) / (float(np.median(nd_ms[1:])) * 1e-3),
                                          "e2e_ms_pinned_host": float(np.median(wall[1:])),
                                          "note": "device_ms = first pass + peer all-to-all + remaining passes (max over devices); e2e includes the strided H2D/D2H copies"}
             be_all.close()
