@@ -200,6 +200,13 @@ int ntt_multi_host(spb_ctx* ctx, const Fr* in, Fr* out, uint32_t k, const Fr& om
     SPB_TRY(set_smem_attr(ctx, d));
     // 1. column block q of the first rows_in rows
     if (rows_in) SPB_CUDA(ctx, cudaMemcpy2DAsync(A[q], lo_loc * sizeof(Fr), in + q * lo_loc, lo_count * sizeof(Fr), lo_loc * sizeof(Fr), rows_in, cudaMemcpyHostToDevice, d.stream));
+    SPB_CUDA(ctx, cudaEventRecord(d.stage_ev[2], d.stream));   // "input block resident on q"
+  }
+  for (size_t q = 0; q < G; q++) {
+    DeviceState& d = ctx->dev[q];
+    SPB_CUDA(ctx, cudaSetDevice(d.device));
+    // start the clock (and the compute) once every device has its block: the timed span is passes + all-to-all only
+    for (size_t o = 0; o < G; o++) SPB_CUDA(ctx, cudaStreamWaitEvent(d.stream, ctx->dev[o].stage_ev[2], 0));
     SPB_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
     // 2. first pass
     NttShare sh; sh.g_log = g; sh.q = (uint32_t)q; sh.mode = 1;
