@@ -126,12 +126,17 @@ spb_ctx* spb_init(const int* device_ids, int n_dev) {
     ctx->dev.push_back(d);
   }
   // several devices: direct NVLink peer copies for the NTT all-to-all and the sharded-MSM scalar scatter
+  ctx->peer_access = ctx->dev.size() > 1;
   for (size_t i = 0; i < ctx->dev.size(); i++)
     for (size_t j = 0; j < ctx->dev.size(); j++) {
       if (i == j) continue;
       int can = 0;
       cudaDeviceCanAccessPeer(&can, ctx->dev[i].device, ctx->dev[j].device);
-      if (can) { cudaSetDevice(ctx->dev[i].device); cudaError_t e = cudaDeviceEnablePeerAccess(ctx->dev[j].device, 0); if (e != cudaSuccess) cudaGetLastError(); }
+      if (!can) { ctx->peer_access = false; continue; }
+      cudaSetDevice(ctx->dev[i].device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(ctx->dev[j].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ctx->peer_access = false;
+      cudaGetLastError();
     }
   if (!ctx->dev.empty()) cudaSetDevice(ctx->dev[0].device);
   return ctx;

@@ -45,6 +45,7 @@ struct spb_ctx {
   std::vector<spb::DeviceState> dev;
   std::mutex mu;
   std::string last_error;
+  bool peer_access = false;  // every device of the context can load from every other one (NVLink P2P enabled)
   // counters (per-call instrumentation behind the C ABI)
   uint64_t n_kernel_launches = 0;
   float last_kernel_ms = 0.f;

@@ -213,15 +213,23 @@ int ntt_multi_host(spb_ctx* ctx, const Fr* in, Fr* out, uint32_t k, const Fr& om
     SPB_TRY(launch_pass(ctx, d, plan, 0, k, tbs[q], h, A[q], A[q], opts, sh));
     SPB_CUDA(ctx, cudaEventRecord(d.stage_ev[0], d.stream));   // "pass 1 done on q"
   }
-  // 3. all-to-all: block (rows of q', columns of q) goes from A[q] to B[q'] at column offset q
+  // 3. all-to-all: destination qd pulls block (rows of qd, columns of qs) from every A[qs] into B[qd] at column offset qs.
+  //    With peer access this is one kernel per destination reading peers' HBM over NVLink; without it, 2-D copies.
   for (size_t qd = 0; qd < G; qd++) {
     DeviceState& dd = ctx->dev[qd];
     SPB_CUDA(ctx, cudaSetDevice(dd.device));
-    for (size_t qs = 0; qs < G; qs++) {
-      DeviceState& ds = ctx->dev[qs];
-      SPB_CUDA(ctx, cudaStreamWaitEvent(dd.stream, ds.stage_ev[0], 0));
-      SPB_CUDA(ctx, cudaMemcpy2DAsync(B[qd] + qs * lo_loc, lo_count * sizeof(Fr), A[qs] + qd * rows_loc * lo_loc, lo_loc * sizeof(Fr),
-                                      lo_loc * sizeof(Fr), rows_loc, cudaMemcpyDefault, dd.stream));
+    for (size_t qs = 0; qs < G; qs++) SPB_CUDA(ctx, cudaStreamWaitEvent(dd.stream, ctx->dev[qs].stage_ev[0], 0));
+    if (ctx->peer_access && G <= 16) {
+      NttGatherArgs ga; memset(&ga, 0, sizeof ga);
+      for (size_t qs = 0; qs < G; qs++) ga.peers[qs] = A[qs];
+      ga.dst = B[qd]; ga.rows_loc = rows_loc; ga.lo_loc = lo_loc; ga.row_base = qd * rows_loc; ga.g_log = g;
+      ntt_gather_kernel<<<dd.sm_count * 8, 256, 0, dd.stream>>>(ga);
+      SPB_CUDA(ctx, cudaGetLastError());
+      ctx->n_kernel_launches++;
+    } else {
+      for (size_t qs = 0; qs < G; qs++)
+        SPB_CUDA(ctx, cudaMemcpy2DAsync(B[qd] + qs * lo_loc, lo_count * sizeof(Fr), A[qs] + qd * rows_loc * lo_loc, lo_loc * sizeof(Fr),
+                                        lo_loc * sizeof(Fr), rows_loc, cudaMemcpyDefault, dd.stream));
     }
     SPB_CUDA(ctx, cudaEventRecord(dd.stage_ev[1], dd.stream));  // "B[qd] complete": A[qs] blocks for qd have been read
   }

@@ -243,6 +243,22 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
   }
 }
 
+// All-to-all of the six-step NTT as ONE kernel per destination device: every thread pulls one 32-byte element
+// straight out of a peer's buffer over NVLink (peer access enabled at spb_init) and drops it at its transposed place.
+//   dst[row][qs * lo_loc + c] = peers[qs][(row_base + row) * lo_loc + c],   row < rows_loc, qs < G, c < lo_loc
+struct NttGatherArgs { const Fr* peers[16]; Fr* dst; uint64_t rows_loc, lo_loc, row_base; uint32_t g_log; };
+__global__ void __launch_bounds__(256) ntt_gather_kernel(NttGatherArgs a) {
+  const uint64_t total = a.rows_loc * (a.lo_loc << a.g_log);
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = i / (a.lo_loc << a.g_log), col = i % (a.lo_loc << a.g_log);
+    const uint64_t qs = col / a.lo_loc, c = col % a.lo_loc;
+    const uint4* src = reinterpret_cast<const uint4*>(a.peers[qs] + (a.row_base + row) * a.lo_loc + c);
+    uint4 lo = src[0], hi = src[1];
+    uint4* d = reinterpret_cast<uint4*>(a.dst + i);
+    d[0] = lo; d[1] = hi;
+  }
+}
+
 // out[i] = base^(i << shift), i < count  (power tables; also reused for coset / vanishing constants)
 __global__ void fr_pow_table_kernel(Fr* out, Fr base, uint64_t count, uint32_t shift) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
