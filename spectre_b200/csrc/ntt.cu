@@ -256,6 +256,15 @@ int ntt_multi_host(spb_ctx* ctx, const Fr* in, Fr* out, uint32_t k, const Fr& om
     float ms = 0.f; cudaEventElapsedTime(&ms, d.ev0, d.ev1);
     if (ms > worst) worst = ms;
   }
+  if (getenv("SPB_NTT_MD_DEBUG")) {
+    for (size_t q = 0; q < G; q++) {
+      DeviceState& d = ctx->dev[q];
+      cudaSetDevice(d.device);
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, d.ev0, d.stage_ev[0]); cudaEventElapsedTime(&b, d.stage_ev[0], d.stage_ev[1]); cudaEventElapsedTime(&c, d.stage_ev[1], d.ev1);
+      fprintf(stderr, "[spb ntt md] k=%u dev %zu: pass1 %.3f ms, all-to-all (incl. wait) %.3f ms, remaining passes %.3f ms, peer_access=%d\n", k, q, a, b, c, (int)ctx->peer_access);
+    }
+  }
   if (ev_ms) *ev_ms = worst;
   ctx->last_kernel_ms = worst;
   return 0;
