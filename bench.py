@@ -141,8 +141,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    cpu_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_pg = dist.new_group(backend="gloo")   # host-side barrier: idle ranks must not spin a kernel on their GPU
     dev = torch.device("cuda", local_rank)
     be = halo2.Backend([local_rank])
 
@@ -244,7 +246,10 @@ def main():
     # ---- multi-GPU NTT: one process drives all N devices (six-step across devices, one all-to-all over NVLink) ----
     ntt_multi = None
     if world > 1 and not args.no_ntt:
-        barrier()
+        # rank 0 drives all N devices from one process; the other ranks wait on the CPU (a NCCL barrier would keep a
+        # spinning kernel on their GPU, and kernels of two processes time-slice on one device)
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_pg)
         if rank == 0:
             ntt_multi = {}
             be_all = halo2.Backend(list(range(world)))
@@ -265,7 +270,7 @@ def main():
                                          "e2e_ms_pinned_host": float(np.median(wall[1:])),
                                          "note": "device_ms = first pass + peer all-to-all + remaining passes (max over devices); e2e includes the strided H2D/D2H copies"}
             be_all.close()
-        barrier()
+        dist.barrier(group=cpu_pg)
 
     if rank != 0:
         be.close()
