@@ -136,6 +136,7 @@ def main():
     import torch
     import torch.distributed as dist
     from spectre_b200 import halo2
+    from spectre_b200 import dist as spb_dist
 
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
@@ -160,23 +161,11 @@ def main():
     torch.cuda.synchronize()
 
     def fold_partials(partial):
-        """all-gather the 96-byte Jacobian partials and fold them (EC addition is not an NCCL reduction op)."""
-        if world == 1:
-            return partial
-        t = torch.from_numpy(partial.view(np.int64)).to(dev)
-        out = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        return halo2.g1_sum(torch.stack(out).cpu().numpy().view(np.uint64))
+        return spb_dist.fold_partials(partial, world, device=dev)[0]
 
     def fold_batch(partials):
         """one all_gather for the whole batch of (count, 12) partial sums, then `count` host folds"""
-        if world == 1:
-            return partials
-        t = torch.from_numpy(np.ascontiguousarray(partials).view(np.int64)).to(dev)
-        out = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        allp = torch.stack(out).cpu().numpy().view(np.uint64)          # (world, count, 12)
-        return np.stack([halo2.g1_sum(allp[:, i, :]) for i in range(allp.shape[1])])
+        return spb_dist.fold_partials(partials, world, device=dev)
 
     def step_dev(i):
         s = dev_sets[i % N_SCALAR_SETS]

@@ -105,3 +105,34 @@ def test_multi_device_six_step_ntt_if_available(orc):
     e = orc.fr_random_chacha(1 << d.extended_k, 98)
     assert np.array_equal(d.extended_to_coeff(e), od.extended_to_coeff(e))
     be2.close()
+
+
+@pytest.mark.parametrize("k", [24, 25])
+def test_full_size_roundtrip_and_linearity(be, orc, k):
+    """BASELINE extended-domain sizes (2^25 = K=23 extended): size-independent properties on device-resident data --
+    ifft(fft(a)) == n*a (sampled), fft(a + b) == fft(a) + fft(b) (sampled), and fft of a delta is the all-ones / omega row."""
+    import ctypes
+    import torch
+    n = 1 << k
+    w = pyref.omega(k)
+    omega = orc.fr([w])[0]; omega_inv = orc.fr([pow(w, -1, pyref.R_MOD)])[0]
+    a = orc.fr_random_chacha(n, 0x5eed0300 + k)
+    da = torch.from_numpy(a.view(np.int64)).cuda()
+    orig = da.clone()
+    be.best_fft_dev(da.data_ptr(), omega, k)
+    fa = da.clone()
+    be.best_fft_dev(da.data_ptr(), omega_inv, k)
+    idx = [0, 1, 2, 3, n // 2, n - 1, 123457 % n, (1 << (k - 1)) + 5]
+    back = orc.fr_ints(da[idx].cpu().numpy().view(np.uint64)); ai = orc.fr_ints(orig[idx].cpu().numpy().view(np.uint64))
+    assert back == [(x << k) % pyref.R_MOD for x in ai]
+    # X[0] = sum of inputs: check against a device-side reduction through eval_polynomial at x = 1
+    s = orc.fr_ints(be.eval_polynomial_dev(orig.data_ptr(), n, orc.fr([1])[0]))[0]
+    assert orc.fr_ints(fa[0:1].cpu().numpy().view(np.uint64))[0] == s
+    # X[1] = p(omega)
+    assert orc.fr_ints(fa[1:2].cpu().numpy().view(np.uint64))[0] == orc.fr_ints(be.eval_polynomial_dev(orig.data_ptr(), n, omega))[0]
+    # delta at position 1 -> row of powers of omega
+    d = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+    d[1] = torch.from_numpy(orc.fr([1])[0].view(np.int64)).cuda()
+    be.best_fft_dev(d.data_ptr(), omega, k)
+    got = orc.fr_ints(d[idx].cpu().numpy().view(np.uint64))
+    assert got == [pow(w, i, pyref.R_MOD) for i in idx]
