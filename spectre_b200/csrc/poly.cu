@@ -4,16 +4,18 @@
 // src/poly/kzg/multiopen/shplonk/prover.rs). All are HBM-streaming passes:
 // algorithmic bytes = 64 B/element (read + write), 32 B/element for the reductions.
 //
-// The three scans (grand product, Kate division, batch inversion) are chunked three-phase scans: per-chunk
-// partials on the device, a tiny serial carry pass over the chunk partials on the host (n / 256 elements), and a
-// device fix-up pass. Element order and results are exactly the serial CPU recurrences'.
+// The three scans (grand product, Kate division, batch inversion) are chunked three-phase scans, all on the device:
+// per-chunk partials, a carry pass over the chunk partials (one block: prefix product / suffix scan of affine maps;
+// batch inversion needs none -- every chunk inverts its own product), and a fix-up pass. Element order and results
+// are exactly the serial CPU recurrences'.
 #include "common.cuh"
 #include "ntt.cuh"
 #include <string.h>
 
 using namespace spb;
 
-static const uint32_t kChunk = 256;
+static const uint32_t kChunk = 256;       // batch inversion: one Fermat inversion per chunk
+static const uint32_t kScanChunk = 64;    // grand product / Kate division: short serial chains, carries scanned on the device
 
 __global__ void vec_mul_kernel(Fr* a, const Fr* b, uint64_t n) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -31,9 +33,9 @@ __global__ void vec_scale_kernel(Fr* a, Fr alpha, uint64_t n) {
 // ---- grand product -------------------------------------------------------------------------------------------
 __global__ void chunk_product_kernel(const Fr* a, uint64_t n, Fr* partial) {
   uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  uint64_t lo = c * kChunk;
+  uint64_t lo = c * kScanChunk;
   if (lo >= n) return;
-  uint64_t hi = lo + kChunk < n ? lo + kChunk : n;
+  uint64_t hi = lo + kScanChunk < n ? lo + kScanChunk : n;
   Fr p = fp_one<FrParams>();
   for (uint64_t i = lo; i < hi; i++) p = fp_mul(p, ntt_ldg(a + i));
   partial[c] = p;
@@ -41,9 +43,9 @@ __global__ void chunk_product_kernel(const Fr* a, uint64_t n, Fr* partial) {
 // z[i] = carry[c] * prod_{lo <= j < i} a[j]
 __global__ void chunk_product_fix_kernel(const Fr* a, uint64_t n, const Fr* carry, Fr* z) {
   uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  uint64_t lo = c * kChunk;
+  uint64_t lo = c * kScanChunk;
   if (lo >= n) return;
-  uint64_t hi = lo + kChunk < n ? lo + kChunk : n;
+  uint64_t hi = lo + kScanChunk < n ? lo + kScanChunk : n;
   Fr p = carry[c];
   for (uint64_t i = lo; i < hi; i++) { Fr v = ntt_ldg(a + i); ntt_stg(z + i, p); p = fp_mul(p, v); }
 }
@@ -52,15 +54,66 @@ __global__ void chunk_product_fix_kernel(const Fr* a, uint64_t n, const Fr* carr
 // with_store = 0: only the chunk head q[lo] (carry-in 0) is produced; 1: full chunk with the true carry-in.
 __global__ void kate_chunk_kernel(const Fr* a, uint64_t nq, Fr b, const Fr* carry_in, Fr* heads, Fr* q, int with_store) {
   uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  uint64_t lo = c * kChunk;
+  uint64_t lo = c * kScanChunk;
   if (lo >= nq) return;
-  uint64_t hi = lo + kChunk < nq ? lo + kChunk : nq;
+  uint64_t hi = lo + kScanChunk < nq ? lo + kScanChunk : nq;
   Fr t = with_store ? carry_in[c] : fp_zero<FrParams>();
   for (uint64_t i = hi; i-- > lo;) {
     t = fp_add(ntt_ldg(a + i + 1), fp_mul(b, t));
     if (with_store) ntt_stg(q + i, t);
   }
   if (!with_store) heads[c] = t;
+}
+
+// ---- carry passes of the two scans, one block of 1024 threads (the partial arrays are n / 64 long) ---------------
+// part[c] <- prod_{c' < c} part[c']   (exclusive prefix product, in place)
+__global__ void __launch_bounds__(1024) carry_product_kernel(Fr* part, uint64_t m) {
+  __shared__ Fr sh[1024];
+  const uint32_t tid = threadIdx.x;
+  const uint64_t per = (m + 1023) / 1024, lo = tid * per, hi = lo + per < m ? lo + per : m;
+  Fr local = fp_one<FrParams>();
+  for (uint64_t i = lo; i < hi; i++) local = fp_mul(local, part[i]);
+  sh[tid] = local;
+  __syncthreads();
+  for (uint32_t off = 1; off < 1024; off <<= 1) {           // inclusive Hillis-Steele scan
+    Fr v = sh[tid];
+    if (tid >= off) v = fp_mul(sh[tid - off], v);
+    __syncthreads();
+    sh[tid] = v;
+    __syncthreads();
+  }
+  Fr run = tid ? sh[tid - 1] : fp_one<FrParams>();
+  for (uint64_t i = lo; i < hi; i++) { Fr t = part[i]; part[i] = run; run = fp_mul(run, t); }
+}
+// Kate: chunk recurrence t_c = head_c + B_c * t_{c+1}, t_m = 0, B_c = b^64 except the last chunk (b_last).
+// carry[c] <- t_{c+1}. Affine maps (H, B): t_lo = H + B * t_hi compose associatively, scanned from the right.
+__global__ void __launch_bounds__(512) carry_kate_kernel(const Fr* heads, Fr* carry, uint64_t m, Fr b_chunk, Fr b_last) {
+  __shared__ Fr shH[512];
+  __shared__ Fr shB[512];
+  const uint32_t tid = threadIdx.x;
+  const uint64_t per = (m + 511) / 512, lo = tid * per, hi = lo + per < m ? lo + per : m;
+  Fr H = fp_zero<FrParams>(), B = fp_one<FrParams>();      // identity map
+  for (uint64_t c = hi; c-- > lo;) {                         // prepend chunk c: t_c = head_c + B_c * (H + B * t_hi)
+    Fr Bc = (c == m - 1) ? b_last : b_chunk;
+    H = fp_add(heads[c], fp_mul(Bc, H));
+    B = fp_mul(Bc, B);
+  }
+  shH[tid] = H; shB[tid] = B;
+  __syncthreads();
+  for (uint32_t off = 1; off < 512; off <<= 1) {            // inclusive suffix scan of map composition
+    Fr h = shH[tid], bb = shB[tid];
+    if (tid + off < 512) { h = fp_add(h, fp_mul(bb, shH[tid + off])); bb = fp_mul(bb, shB[tid + off]); }
+    __syncthreads();
+    shH[tid] = h; shB[tid] = bb;
+    __syncthreads();
+  }
+  // value entering this thread's range from the right: t_{hi} = H-component of the suffix starting at tid+1 (t_m = 0)
+  Fr t = (tid + 1 < 512) ? shH[tid + 1] : fp_zero<FrParams>();
+  for (uint64_t c = hi; c-- > lo;) {
+    carry[c] = t;
+    Fr Bc = (c == m - 1) ? b_last : b_chunk;
+    t = fp_add(heads[c], fp_mul(Bc, t));
+  }
 }
 
 // ---- batch inversion (zeros stay zero) ----------------------------------------------------------------------------
@@ -131,43 +184,27 @@ inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t
 
 // ---- device-resident cores (all pointers on device d, work enqueued on d.stream; no final synchronisation unless noted)
 int dev_grand_product(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, Fr* dz) {
-  size_t m = (n + kChunk - 1) / kChunk;
+  size_t m = (n + kScanChunk - 1) / kScanChunk;
   Fr* dp = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32);
   if (!dp) return SPB_ERR_OOM;
-  chunk_product_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, dp);
-  std::vector<Fr> part(m);
-  SPB_CUDA(ctx, cudaMemcpyAsync(part.data(), dp, m * 32, cudaMemcpyDeviceToHost, d.stream));
-  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
-  Fr run = fp_one<FrParams>();
-  for (size_t c = 0; c < m; c++) { Fr t = part[c]; part[c] = run; run = fp_mul(run, t); }  // exclusive carry
-  SPB_CUDA(ctx, cudaMemcpyAsync(dp, part.data(), m * 32, cudaMemcpyHostToDevice, d.stream));
-  chunk_product_fix_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, n, dp, dz);
-  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));  // `part` must outlive the H2D copy
-  ctx->n_kernel_launches += 2;
+  chunk_product_kernel<<<nblk(m, 128), 128, 0, d.stream>>>(da, n, dp);
+  carry_product_kernel<<<1, 1024, 0, d.stream>>>(dp, m);
+  chunk_product_fix_kernel<<<nblk(m, 128), 128, 0, d.stream>>>(da, n, dp, dz);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches += 3;
   return 0;
 }
 
 int dev_kate_division(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, const Fr& bb, Fr* dq) {
-  size_t nq = n - 1, m = (nq + kChunk - 1) / kChunk;
+  size_t nq = n - 1, m = (nq + kScanChunk - 1) / kScanChunk;
   Fr* dh = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32);
   if (!dh) return SPB_ERR_OOM;
-  kate_chunk_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, nq, bb, nullptr, dh, nullptr, 0);
-  std::vector<Fr> heads(m), carry(m);
-  SPB_CUDA(ctx, cudaMemcpyAsync(heads.data(), dh, m * 32, cudaMemcpyDeviceToHost, d.stream));
-  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
-  // carry into chunk c = q[hi_c] = true head of chunk c+1; true head_c = head0_c + b^(len_c) * carry_c
-  Fr bch = fp_pow_u64(bb, kChunk);
-  Fr next = fp_zero<FrParams>();
-  for (size_t c = m; c-- > 0;) {
-    carry[c] = next;
-    size_t len = (c == m - 1) ? nq - c * kChunk : kChunk;
-    Fr bl = (len == kChunk) ? bch : fp_pow_u64(bb, len);
-    next = fp_add(heads[c], fp_mul(bl, next));
-  }
-  SPB_CUDA(ctx, cudaMemcpyAsync(dh + m, carry.data(), m * 32, cudaMemcpyHostToDevice, d.stream));
-  kate_chunk_kernel<<<nblk(m, 64), 64, 0, d.stream>>>(da, nq, bb, dh + m, nullptr, dq, 1);
-  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
-  ctx->n_kernel_launches += 2;
+  kate_chunk_kernel<<<nblk(m, 128), 128, 0, d.stream>>>(da, nq, bb, nullptr, dh, nullptr, 0);
+  size_t last_len = nq - (m - 1) * kScanChunk;
+  carry_kate_kernel<<<1, 512, 0, d.stream>>>(dh, dh + m, m, fp_pow_u64(bb, kScanChunk), fp_pow_u64(bb, last_len));
+  kate_chunk_kernel<<<nblk(m, 128), 128, 0, d.stream>>>(da, nq, bb, dh + m, nullptr, dq, 1);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches += 3;
   return 0;
 }
 
@@ -296,7 +333,9 @@ int spb_grand_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* d_z
   if (!ctx || !d_a || !d_z) return SPB_ERR_ARG;
   if (!n) return 0;
   SPB_ENTER(ctx);
-  return dev_grand_product(ctx, d, (const Fr*)d_a, n, (Fr*)d_z);
+  SPB_TRY(dev_grand_product(ctx, d, (const Fr*)d_a, n, (Fr*)d_z));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
 }
 int spb_grand_product(spb_ctx* ctx, const spb_fr* a, size_t n, spb_fr* z) {
   if (!ctx || !a || !z) return SPB_ERR_ARG;
@@ -316,7 +355,9 @@ int spb_kate_division_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, const spb_f
   if (n == 1) return 0;
   SPB_ENTER(ctx);
   Fr bb; memcpy(&bb, b, 32);
-  return dev_kate_division(ctx, d, (const Fr*)d_a, n, bb, (Fr*)d_q);
+  SPB_TRY(dev_kate_division(ctx, d, (const Fr*)d_a, n, bb, (Fr*)d_q));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
 }
 int spb_kate_division(spb_ctx* ctx, const spb_fr* a, size_t n, const spb_fr* b, spb_fr* q) {
   if (!ctx || !a || !b || !q || n < 1) return SPB_ERR_ARG;

@@ -22,14 +22,14 @@ def test_eval_polynomial(be, orc, n):
     assert np.array_equal(be.eval_polynomial(poly, x), orc.eval_polynomial(poly, x))
 
 
-@pytest.mark.parametrize("n", [2, 3, 256, 257, 258, 5000, 65537])
+@pytest.mark.parametrize("n", [2, 3, 64, 65, 66, 129, 256, 257, 258, 5000, 65537, 32769, 32770, (1 << 20) + 3])
 def test_kate_division(be, orc, n):
     a = orc.fr_random_chacha(n, 40 + n)
     b = orc.fr_random_chacha(1, 41)[0]
     assert np.array_equal(be.kate_division(a, b), orc.kate_division(a, b))
 
 
-@pytest.mark.parametrize("n", [1, 2, 256, 257, 10000])
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 256, 257, 10000, 65536, 65537, 100003])
 def test_grand_product(be, orc, n):
     a = orc.fr_random_chacha(n, 50 + n)
     ai = orc.fr_ints(a)
