@@ -21,7 +21,6 @@ struct spb_srs {
   std::vector<SrsShard> shards;  // one per device of the context, contiguous point ranges
 };
 
-static uint64_t g_last_adds = 0;
 
 namespace spb {
 
@@ -34,10 +33,12 @@ struct Lane {
   void* pinned = nullptr;
   bool ready = false;
 };
-static std::map<std::pair<spb_ctx*, int>, std::vector<Lane>> g_lanes;
+static std::map<std::pair<spb_ctx*, int>, std::vector<Lane>> g_lanes;   // process-wide: guarded by g_lanes_mu
+static std::mutex g_lanes_mu;
 static const size_t kLanePinnedBytes = 256 * 1024;  // window partials of one MSM (<= 128 windows x a few points)
 
 static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
+  std::lock_guard<std::mutex> lk(g_lanes_mu);
   auto& v = g_lanes[std::make_pair(ctx, dev_index)];
   if (v.size() < 2) v.resize(2);
   Lane& l = v[lane_index];
@@ -52,6 +53,7 @@ static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
 }
 
 void msm_release_ctx(spb_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_lanes_mu);
   for (auto it = g_lanes.begin(); it != g_lanes.end();) {
     if (it->first.first != ctx) { ++it; continue; }
     cudaSetDevice(ctx->dev[it->first.second].device);
@@ -142,12 +144,12 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   return 0;
 }
 
-static G1Xyzz msm_finish(Lane& ln, MsmGeom g) {
+static G1Xyzz msm_finish(Lane& ln, MsmGeom g, uint64_t* adds) {
   const MsmTail tl = msm_tail_shape(g.c);
   const uint32_t per = 2 * tl.nbr + tl.nbc;
   const G1Xyzz* P = (const G1Xyzz*)ln.pinned;
   uint32_t M; memcpy(&M, (const char*)ln.pinned + (size_t)g.BW * per * sizeof(G1Xyzz), 4);
-  g_last_adds += (uint64_t)M + 2ull * g.BW * g.B;
+  if (adds) *adds += (uint64_t)M + 2ull * g.BW * g.B;
   std::vector<G1Xyzz> S(g.BW);
   for (uint32_t w = 0; w < g.BW; w++) S[w] = msm_tail_finish(g, P + (size_t)w * per);
   return msm_combine_windows(S.data(), g.BW, g.c);
@@ -204,7 +206,7 @@ static int job_collect(spb_ctx* ctx, int lane, const std::vector<MsmPart>& parts
     SPB_CUDA(ctx, cudaEventElapsedTime(&ms, ln->ev[8], ln->ev[7]));
     if (ms > worst) worst = ms;
     if (p.dev_index == 0) for (int e = 0; e < 7; e++) cudaEventElapsedTime(&ctx->msm_stage_ms[e], ln->ev[e], ln->ev[e + 1]);
-    G1Xyzz r = msm_finish(*ln, p.g);
+    G1Xyzz r = msm_finish(*ln, p.g, &ctx->last_msm_adds);
     xyzz_add(acc, r);
   }
   ctx->last_kernel_ms = worst;
@@ -216,7 +218,7 @@ static int job_collect(spb_ctx* ctx, int lane, const std::vector<MsmPart>& parts
 
 extern "C" {
 
-uint64_t spb_last_msm_adds(spb_ctx* ctx) { (void)ctx; return g_last_adds; }
+uint64_t spb_last_msm_adds(spb_ctx* ctx) { return ctx ? ctx->last_msm_adds : 0; }
 void spb_last_msm_stage_ms(spb_ctx* ctx, float out[7]) { for (int i = 0; i < 7; i++) out[i] = ctx ? ctx->msm_stage_ms[i] : 0.f; }
 void spb_msm_geometry(size_t n, int tables, uint32_t* c, uint32_t* windows) { MsmGeom g = msm_make_geometry(msm_choose_c(n ? n : 1, tables != 0), tables != 0, 0); *c = g.c; *windows = g.W; }
 
@@ -332,7 +334,7 @@ int spb_srs_download(spb_ctx* ctx, const spb_srs* srs, int basis, size_t start, 
 int spb_msm_raw(spb_ctx* ctx, const spb_fr* scalars, const spb_g1_affine* bases, size_t n, spb_g1* out) {
   if (!ctx || !out || (n && (!scalars || !bases))) return SPB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  g_last_adds = 0;
+  ctx->last_msm_adds = 0;
   std::vector<MsmPart> parts;
   size_t D = ctx->dev.size();
   for (size_t i = 0; i < D; i++) {
@@ -372,7 +374,7 @@ static int srs_parts(spb_ctx* ctx, const spb_srs* srs, int basis, const Fr* scal
 static int msm_batch_common(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* const* scalars, bool on_device, size_t n, size_t count, spb_g1* out) {
   if (!ctx || !srs || !out || (count && !scalars)) return SPB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  g_last_adds = 0;
+  ctx->last_msm_adds = 0;
   std::vector<MsmPart> jobs[2];
   for (size_t i = 0; i < count; i++) {
     int lane = (int)(i & 1);

@@ -7,7 +7,8 @@
 // sum_i scalars[i] * bases[i]; integers are exact, so any correct schedule is bit-identical to the CPU
 // result after affine normalisation.
 //
-// Pipeline (one MSM of n pairs, window width c, W = ceil(255/c) windows, B = 2^(c-1) buckets per window):
+// Pipeline (one MSM of n pairs, window width c, W = ceil(255/c) windows, B = 2^(c-1) buckets per bucket set; a basis
+// with precomputed 2^(c*w) multiples folds all windows into ONE bucket set, otherwise there are W sets):
 //   1. digits   : Montgomery -> canonical scalar (one product), signed c-bit digits d_w in (-B, B], histogram
 //                 of (w, |d_w|) with global atomics; zero digits are dropped here.
 //   2. scan     : exclusive prefix sum of the W*B counters (bucket offsets).
@@ -20,12 +21,12 @@
 //                 a chunk ("tail") and the run that enters one ("head") are stored as chunk pieces.
 //   5. stitch   : one thread per tail piece walks the following head pieces of the same key and stores the
 //                 bucket; chains longer than a cap (giant buckets) go to a block-wide tree reduction.
-//   6. reduce   : per window S_w = sum_b b * bucket[b]: running sums over segments of 16 buckets, a small
-//                 scalar multiplication by the segment offset, and a block tree sum per window.
-//   7. host     : sum_w 2^(c w) S_w by Horner (W*c doublings on the CPU 64-bit path) and one inversion.
+//   6. reduce   : per bucket set S = sum_b (b+1) * bucket[b] with the buckets viewed as an R x C matrix:
+//                 S = C * sum_r r*Row_r + sum_r Row_r + sum_c c*Col_c -- tree sums and scalar multiples < 2^10 only.
+//   7. host     : fold the few partial sums per bucket set, Horner over the sets (none with tables), one inversion.
 //
 // Roofline: algorithmic bytes = 96 B per pair. The kernel that dominates (step 4) executes
-// W mixed additions of 8M+2S (~1390 IMAD.WIDE) per pair: it is bound by the INT32 multiply pipe by two
+// W mixed additions of 8M+2S (~1390 IMAD-class instructions each) per pair: it is bound by the INT32 multiply pipe by two
 // orders of magnitude, not by HBM. DESIGN.md states both fractions.
 //
 // Every function below is written per thread (`tid`) so that tests/hostemu can run the identical code
