@@ -102,6 +102,9 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   G1Xyzz* head = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_head", (Tmax + 1) * sizeof(G1Xyzz));
   G1Xyzz* tail = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_tail", (Tmax + 1) * sizeof(G1Xyzz));
   uint32_t* giant = (uint32_t*)lane_slot(ctx, d, lane, "msm_giant", (Tmax + 2) * 4);  // [0] = count, [1..] = queue
+  const uint64_t max_huge = Tmax / kHugeChain + 1;
+  uint32_t* huge = (uint32_t*)lane_slot(ctx, d, lane, "msm_huge", (2 * max_huge + 2) * 4);  // [0] = count, [2..] = (t0, end) pairs
+  G1Xyzz* huge_part = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_huge_part", max_huge * kHugeBlocks * sizeof(G1Xyzz));
   const MsmTail tl = msm_tail_shape(g.c);
   const uint32_t R = 1u << tl.r_log, C = 1u << tl.c_log, per = 2 * tl.nbr + tl.nbc;
   G1Xyzz* seg_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_rowcol", (uint64_t)g.BW * (R + C) * sizeof(G1Xyzz));
@@ -109,7 +112,7 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   size_t scan_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, offsets, (int)(nb + 1), ln.stream);
   void* scan_tmp = lane_slot(ctx, d, lane, "msm_scan_tmp", scan_bytes ? scan_bytes : 16);
-  if (!counts || !offsets || !ent || !buckets || !head_key || !tail_key || !head || !tail || !giant || !seg_out || !win_out || !scan_tmp)
+  if (!counts || !offsets || !ent || !buckets || !head_key || !tail_key || !head || !tail || !giant || !huge || !huge_part || !seg_out || !win_out || !scan_tmp)
     return SPB_ERR_OOM;
   if ((size_t)g.BW * per * sizeof(G1Xyzz) + 16 > kLanePinnedBytes) return set_error(ctx, SPB_ERR_STATE, "msm: %u window partials exceed the pinned staging area", g.BW * per);
 
@@ -117,6 +120,7 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   SPB_CUDA(ctx, cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
   SPB_CUDA(ctx, cudaMemsetAsync(buckets, 0, nb * sizeof(G1Xyzz), st));
   SPB_CUDA(ctx, cudaMemsetAsync(giant, 0, 4, st));
+  SPB_CUDA(ctx, cudaMemsetAsync(huge, 0, 4, st));
   const unsigned tb = 256;
   cudaEventRecord(ln.ev[0], st);
   msm_count_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(n, d_scalars, g, counts);
@@ -131,14 +135,16 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   msm_accumulate_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g, ent, d_bases, buckets, head_key, head, tail_key, tail);
   cudaEventRecord(ln.ev[4], st);
   msm_stitch_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g.L, 24, head_key, head, tail_key, tail, buckets, giant, giant + 1);
-  msm_giant_kernel<<<256, 128, 0, st>>>(total, g.L, giant, giant + 1, head_key, head, tail_key, tail, buckets);
+  msm_giant_kernel<<<256, 128, 0, st>>>(total, g.L, giant, giant + 1, head_key, head, tail_key, tail, buckets, huge, huge + 2);
+  msm_huge_kernel<<<kHugeBlocks, 128, 0, st>>>(huge, huge + 2, head, huge_part);
+  msm_huge_finish_kernel<<<8, 128, 0, st>>>(huge, huge + 2, kHugeBlocks, huge_part, tail_key, tail, buckets);
   cudaEventRecord(ln.ev[5], st);
   msm_rowcol_kernel<<<g.BW * (R + C), 64, 0, st>>>(g, tl, buckets, seg_out, seg_out + (uint64_t)g.BW * R);
   cudaEventRecord(ln.ev[6], st);
   msm_weighted_kernel<<<g.BW * (tl.nbr + tl.nbc), 128, 0, st>>>(g, tl, seg_out, seg_out + (uint64_t)g.BW * R, win_out);
   cudaEventRecord(ln.ev[7], st);
   SPB_CUDA(ctx, cudaGetLastError());
-  ctx->n_kernel_launches += 7;
+  ctx->n_kernel_launches += 9;
   SPB_CUDA(ctx, cudaMemcpyAsync(ln.pinned, win_out, (size_t)g.BW * per * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
   SPB_CUDA(ctx, cudaMemcpyAsync((char*)ln.pinned + (size_t)g.BW * per * sizeof(G1Xyzz), total, 4, cudaMemcpyDeviceToHost, st));
   return 0;

@@ -334,20 +334,65 @@ __device__ void block_sum2_xyzz(G1Xyzz& a, G1Xyzz& b, G1Xyzz* sh /* NT entries *
   }
 }
 
-// giant chains (queued by the stitch kernel): one block per chain, grid-stride over the queue
+// giant chains (queued by the stitch kernel): one block per chain, grid-stride over the queue. Chains with more than
+// kHugeChain links (a column of equal scalars puts n/32 pieces into one bucket) are handed on to the huge-chain
+// kernels, which spread ONE chain over the whole grid.
+static const uint32_t kHugeChain = 4096;
+static const uint32_t kHugeBlocks = 256;
 __global__ void __launch_bounds__(128) msm_giant_kernel(const uint32_t* total, uint32_t L, const uint32_t* giant_count, const uint32_t* giant_list,
                                                         const uint32_t* head_key, const G1Xyzz* head, const uint32_t* tail_key, const G1Xyzz* tail,
-                                                        G1Xyzz* buckets) {
+                                                        G1Xyzz* buckets, uint32_t* huge_count, uint32_t* huge_list /* pairs: t0, end */) {
   __shared__ G1Xyzz sh[64];
+  __shared__ uint64_t s_end;
   const uint64_t T = ((uint64_t)*total + L - 1) / L;
   const uint32_t count = *giant_count;
   for (uint32_t gi = blockIdx.x; gi < count; gi += gridDim.x) {
     uint64_t t0 = giant_list[gi];
     uint32_t key = tail_key[t0];
+    if (threadIdx.x == 0) {
+      // links are head[t0+1 .. end): keys are sorted, so "head_key[j] == key" is true on that range and never again
+      uint64_t lo = t0 + 1, hi = T;
+      while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (head_key[mid] == key) lo = mid + 1; else hi = mid; }
+      s_end = lo;
+    }
+    __syncthreads();
+    const uint64_t end = s_end;
+    if (end - (t0 + 1) > kHugeChain) {
+      if (threadIdx.x == 0) { uint32_t slot = atomicAdd(huge_count, 1u); huge_list[2 * slot] = (uint32_t)t0; huge_list[2 * slot + 1] = (uint32_t)end; }
+      __syncthreads();
+      continue;
+    }
     G1Xyzz acc = xyzz_identity();
-    for (uint64_t j = t0 + 1 + threadIdx.x; j < T && head_key[j] == key; j += 128) xyzz_add(acc, head[j]);
+    for (uint64_t j = t0 + 1 + threadIdx.x; j < end; j += 128) xyzz_add(acc, head[j]);
     block_sum_xyzz<128>(acc, sh);
     if (threadIdx.x == 0) { xyzz_add(acc, tail[t0]); buckets[key] = acc; }
+    __syncthreads();
+  }
+}
+// every block sums a strided share of each huge chain -> partial[chain][block]
+__global__ void __launch_bounds__(128) msm_huge_kernel(const uint32_t* huge_count, const uint32_t* huge_list, const G1Xyzz* head, G1Xyzz* partial) {
+  __shared__ G1Xyzz sh[64];
+  const uint32_t count = *huge_count;
+  for (uint32_t hi = 0; hi < count; hi++) {
+    const uint64_t t0 = huge_list[2 * hi], end = huge_list[2 * hi + 1];
+    G1Xyzz acc = xyzz_identity();
+    for (uint64_t j = t0 + 1 + (uint64_t)blockIdx.x * 128 + threadIdx.x; j < end; j += (uint64_t)gridDim.x * 128) xyzz_add(acc, head[j]);
+    block_sum_xyzz<128>(acc, sh);
+    if (threadIdx.x == 0) partial[(uint64_t)hi * gridDim.x + blockIdx.x] = acc;
+    __syncthreads();
+  }
+}
+// one block per huge chain: fold the per-block partials and the chain's tail piece into the bucket
+__global__ void __launch_bounds__(128) msm_huge_finish_kernel(const uint32_t* huge_count, const uint32_t* huge_list, uint32_t nparts, const G1Xyzz* partial,
+                                                              const uint32_t* tail_key, const G1Xyzz* tail, G1Xyzz* buckets) {
+  __shared__ G1Xyzz sh[64];
+  const uint32_t count = *huge_count;
+  for (uint32_t hi = blockIdx.x; hi < count; hi += gridDim.x) {
+    G1Xyzz acc = xyzz_identity();
+    for (uint32_t j = threadIdx.x; j < nparts; j += 128) xyzz_add(acc, partial[(uint64_t)hi * nparts + j]);
+    block_sum_xyzz<128>(acc, sh);
+    const uint64_t t0 = huge_list[2 * hi];
+    if (threadIdx.x == 0) { xyzz_add(acc, tail[t0]); buckets[tail_key[t0]] = acc; }
     __syncthreads();
   }
 }

@@ -93,6 +93,32 @@ def test_giant_bucket_block_path(be, orc, points):
     assert np.array_equal(got, want)
 
 
+def test_huge_chain_grid_path(be, orc):
+    """2^18 equal scalars: one bucket chain of 8192 chunk pieces (> 4096) -> the grid-wide huge-chain kernels; also a
+    0/1 column. Expected values by group arithmetic on the oracle: sum of all points / of the selected points."""
+    k = 18
+    n = 1 << k
+    pts = be.g1_fixed_base_mul(orc.fr_random_chacha(n, 0x5eed0042))
+    assert np.array_equal(pts[:64], orc.g1_fixed_base_mul(orc.fr_random_chacha(n, 0x5eed0042)[:64]))
+    ones = np.repeat(orc.fr([1]), n, axis=0)
+    total = be.best_multiexp(ones, pts)
+    # the same sum through a different schedule: random scalars r and 1 - r
+    r = orc.fr_random_chacha(n, 7)
+    one_minus_r = be.vec_axpy(ones, orc.fr([pyref.R_MOD - 1])[0], r)
+    alt = orc.g1_add(be.best_multiexp(r, pts), be.best_multiexp(one_minus_r, pts))
+    assert np.array_equal(affine_of(orc, total), orc.g1_to_affine(alt))
+    bits = np.zeros((n, 4), dtype=np.uint64)
+    sel = np.random.default_rng(1).random(n) < 0.5
+    bits[sel] = orc.fr([1])[0]
+    masked = r.copy(); masked[~sel] = 0
+    compl = be.vec_axpy(bits, orc.fr([pyref.R_MOD - 1])[0], masked)       # bits - masked r
+    alt = orc.g1_add(be.best_multiexp(masked, pts), be.best_multiexp(compl, pts))
+    assert np.array_equal(affine_of(orc, be.best_multiexp(bits, pts)), orc.g1_to_affine(alt))
+    # and directly against the CPU port on a prefix large enough to take the huge path with a small window choice
+    m = 1 << 17
+    assert np.array_equal(affine_of(orc, be.best_multiexp(ones[:m], pts[:m])), affine_of(orc, orc.best_multiexp(ones[:m], pts[:m])))
+
+
 def test_params_kzg_setup_and_commit_seed0(be, orc):
     """ParamsKZG::setup on the device with the seed-0 secret reproduces the oracle's (KAT-pinned) SRS, and
     commit / commit_lagrange agree with both best_multiexp and the O(n) known-tau shortcut."""
