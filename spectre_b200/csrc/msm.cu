@@ -106,7 +106,7 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   uint32_t* huge = (uint32_t*)lane_slot(ctx, d, lane, "msm_huge", (2 * max_huge + 2) * 4);  // [0] = count, [2..] = (t0, end) pairs
   G1Xyzz* huge_part = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_huge_part", max_huge * kHugeBlocks * sizeof(G1Xyzz));
   const MsmTail tl = msm_tail_shape(g.c);
-  const uint32_t R = 1u << tl.r_log, C = 1u << tl.c_log, per = 2 * tl.nbr + tl.nbc;
+  const uint32_t R = 1u << tl.r_log, C = 1u << tl.c_log, per = msm_tail_partials(tl);
   G1Xyzz* seg_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_rowcol", (uint64_t)g.BW * (R + C) * sizeof(G1Xyzz));
   G1Xyzz* win_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_partials", (uint64_t)g.BW * per * sizeof(G1Xyzz));
   size_t scan_bytes = 0;
@@ -152,7 +152,7 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
 
 static G1Xyzz msm_finish(Lane& ln, MsmGeom g, uint64_t* adds) {
   const MsmTail tl = msm_tail_shape(g.c);
-  const uint32_t per = 2 * tl.nbr + tl.nbc;
+  const uint32_t per = msm_tail_partials(tl);
   const G1Xyzz* P = (const G1Xyzz*)ln.pinned;
   uint32_t M; memcpy(&M, (const char*)ln.pinned + (size_t)g.BW * per * sizeof(G1Xyzz), 4);
   if (adds) *adds += (uint64_t)M + 2ull * g.BW * g.B;

@@ -213,10 +213,14 @@ inline MsmTail msm_tail_shape(uint32_t c) {
   t.nbr = ((1u << t.r_log) + 127) / 128; t.nbc = ((1u << t.c_log) + 127) / 128;
   return t;
 }
-// host-side reference of the two kernels below (tests/hostemu): partial layout per window = [A.., S.., D..]
+// Partial layout per bucket set: [A(nbr) | S(nbr) | D(nbc) | T(nbc)], each over a block of 128 rows / columns with
+// LOCAL weights: A[j] = sum_i i * Row_{128j+i}, S[j] = sum_i Row_{128j+i}, D[j] = sum_i i * Col_{128j+i}, T[j] = sum_i
+// Col_{128j+i}. The host adds the 128*j offsets (msm_tail_finish).
+SPB_HD uint32_t msm_tail_partials(const MsmTail& t) { return 2 * t.nbr + 2 * t.nbc; }
+// host-side reference of the two kernels below (tests/hostemu)
 inline void msm_tail_host(const MsmGeom& g, const G1Xyzz* buckets, G1Xyzz* partials) {
   MsmTail t = msm_tail_shape(g.c);
-  uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = 2 * t.nbr + t.nbc;
+  uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = msm_tail_partials(t);
   for (uint32_t w = 0; w < g.BW; w++) {
     const G1Xyzz* X = buckets + (uint64_t)w * g.B;
     G1Xyzz* out = partials + (uint64_t)w * per;
@@ -224,24 +228,37 @@ inline void msm_tail_host(const MsmGeom& g, const G1Xyzz* buckets, G1Xyzz* parti
     for (uint32_t r = 0; r < R; r++) {
       G1Xyzz row = xyzz_identity();
       for (uint32_t c = 0; c < C; c++) xyzz_add(row, X[(uint64_t)r * C + c]);
-      G1Xyzz wr = xyzz_mul_u32(row, r);
+      G1Xyzz wr = xyzz_mul_u32(row, r % 128);
       xyzz_add(out[r / 128], wr);
       xyzz_add(out[t.nbr + r / 128], row);
     }
     for (uint32_t c = 0; c < C; c++) {
       G1Xyzz col = xyzz_identity();
       for (uint32_t r = 0; r < R; r++) xyzz_add(col, X[(uint64_t)r * C + c]);
-      G1Xyzz wc = xyzz_mul_u32(col, c);
+      G1Xyzz wc = xyzz_mul_u32(col, c % 128);
       xyzz_add(out[2 * t.nbr + c / 128], wc);
+      xyzz_add(out[2 * t.nbr + t.nbc + c / 128], col);
     }
   }
 }
 // host: window sum from its partials
 inline G1Xyzz msm_tail_finish(const MsmGeom& g, const G1Xyzz* part) {
   MsmTail t = msm_tail_shape(g.c);
-  G1Xyzz A = xyzz_identity(), S = xyzz_identity(), D = xyzz_identity();
-  for (uint32_t i = 0; i < t.nbr; i++) { xyzz_add(A, part[i]); xyzz_add(S, part[t.nbr + i]); }
-  for (uint32_t i = 0; i < t.nbc; i++) xyzz_add(D, part[2 * t.nbr + i]);
+  // sum_j (X[j] + 128 j Y[j]) = sum_j X[j] + 128 * sum_j j Y[j]; the second sum by running sums from the top block down
+  auto fold = [](const G1Xyzz* X, const G1Xyzz* Y, uint32_t nb, G1Xyzz* plain) {
+    G1Xyzz sx = xyzz_identity(), run = xyzz_identity(), wsum = xyzz_identity();
+    for (int j = (int)nb - 1; j >= 0; j--) {
+      xyzz_add(sx, X[j]);
+      if (j >= 1) { xyzz_add(run, Y[j]); xyzz_add(wsum, run); }   // after the loop: wsum = sum_j j * Y[j]
+    }
+    if (plain) { *plain = run; xyzz_add(*plain, Y[0]); }
+    for (int i = 0; i < 7; i++) wsum = xyzz_dbl(wsum);
+    xyzz_add(sx, wsum);
+    return sx;
+  };
+  G1Xyzz S;
+  G1Xyzz A = fold(part, part + t.nbr, t.nbr, &S);
+  G1Xyzz D = fold(part + 2 * t.nbr, part + 2 * t.nbr + t.nbc, t.nbc, nullptr);
   for (uint32_t i = 0; i < t.c_log; i++) A = xyzz_dbl(A);
   xyzz_add(A, S); xyzz_add(A, D);
   return A;
@@ -410,24 +427,30 @@ __global__ void __launch_bounds__(64) msm_rowcol_kernel(MsmGeom g, MsmTail t, co
   block_sum_xyzz<64>(acc, sh);
   if (threadIdx.x == 0) { if (idx < R) row_out[(uint64_t)w * R + idx] = acc; else col_out[(uint64_t)w * C + (idx - R)] = acc; }
 }
-// block (w, j): j < nbr -> rows [128 j, 128 j + 128): A partial (weights r) and S partial (plain); else columns: D partial
+// block (w, j): j < nbr -> rows [128 j, 128 j + 128), else columns. Local weighted sum without any scalar multiple:
+// sum_i i * X_i = sum_{i >= 1} (suffix sum S_i), so one suffix scan (7 steps) and one tree sum (7 steps).
 __global__ void __launch_bounds__(128) msm_weighted_kernel(MsmGeom g, MsmTail t, const G1Xyzz* row_out, const G1Xyzz* col_out, G1Xyzz* partials) {
   __shared__ G1Xyzz sh[128];
-  const uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = 2 * t.nbr + t.nbc;
+  const uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = msm_tail_partials(t);
   const uint32_t w = blockIdx.x / (t.nbr + t.nbc), j = blockIdx.x % (t.nbr + t.nbc);
+  const bool rows = j < t.nbr;
+  const uint32_t jb = rows ? j : j - t.nbr, idx = jb * 128 + threadIdx.x, tid = threadIdx.x;
   G1Xyzz* out = partials + (uint64_t)w * per;
-  if (j < t.nbr) {
-    uint32_t r = j * 128 + threadIdx.x;
-    G1Xyzz x = r < R ? row_out[(uint64_t)w * R + r] : xyzz_identity();
-    G1Xyzz wx = xyzz_mul_u32(x, r);
-    block_sum2_xyzz<128>(wx, x, sh);
-    if (threadIdx.x == 0) { out[j] = wx; out[t.nbr + j] = x; }
-  } else {
-    uint32_t c = (j - t.nbr) * 128 + threadIdx.x;
-    G1Xyzz x = c < C ? col_out[(uint64_t)w * C + c] : xyzz_identity();
-    G1Xyzz wx = xyzz_mul_u32(x, c);
-    block_sum_xyzz<128>(wx, sh);
-    if (threadIdx.x == 0) out[2 * t.nbr + (j - t.nbr)] = wx;
+  G1Xyzz x = rows ? (idx < R ? row_out[(uint64_t)w * R + idx] : xyzz_identity()) : (idx < C ? col_out[(uint64_t)w * C + idx] : xyzz_identity());
+  // inclusive suffix scan: x <- sum_{t >= tid} X_t
+  for (uint32_t off = 1; off < 128; off <<= 1) {
+    sh[tid] = x;
+    __syncthreads();
+    if (tid + off < 128) xyzz_add(x, sh[tid + off]);
+    __syncthreads();
+  }
+  G1Xyzz total = x;                       // thread 0 holds the plain block sum
+  if (tid == 0) x = xyzz_identity();      // weights start at 0: drop S_0 from the weighted sum
+  __shared__ G1Xyzz sh2[64];
+  block_sum_xyzz<128>(x, sh2);
+  if (tid == 0) {
+    if (rows) { out[jb] = x; out[t.nbr + jb] = total; }
+    else { out[2 * t.nbr + jb] = x; out[2 * t.nbr + t.nbc + jb] = total; }
   }
 }
 

@@ -77,7 +77,7 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
   }
   if (giants) *giants = gcount;
   MsmTail tl = msm_tail_shape(g.c);
-  uint32_t per = 2 * tl.nbr + tl.nbc;
+  uint32_t per = msm_tail_partials(tl);
   std::vector<G1Xyzz> partials((uint64_t)g.BW * per), win(g.BW);
   msm_tail_host(g, buckets.data(), partials.data());
   for (uint32_t w = 0; w < g.BW; w++) win[w] = msm_tail_finish(g, partials.data() + (uint64_t)w * per);
