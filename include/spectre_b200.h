@@ -77,6 +77,14 @@ int spb_srs_setup(spb_ctx* ctx, uint32_t k, const spb_fr* s, spb_srs** out);
 /* copy a range of a resident basis back to the host (ParamsKZG::get_g / write) */
 int spb_srs_download(spb_ctx* ctx, const spb_srs* srs, int basis, size_t start, size_t count, spb_g1_affine* out);
 void spb_srs_free(spb_ctx* ctx, spb_srs* srs);
+/* ParamsKZG::read / ::write, SerdeFormat::RawBytes: k (u32 LE) | g[2^k] | g_lagrange[2^k] | g2 | s_g2 with every
+ * coordinate as its in-memory Montgomery limbs -- the `params/kzg_bn254_{k}.srs` file halo2-base's gen_srs caches
+ * (reference: prover/src/cli.rs:48, .gitignore:36). Read streams the points straight into device memory. */
+int spb_srs_read_file(spb_ctx* ctx, const char* path, spb_srs** out);
+int spb_srs_write_file(spb_ctx* ctx, const spb_srs* srs, const char* path);
+int spb_srs_set_g2(spb_ctx* ctx, spb_srs* srs, const unsigned char g2[128], const unsigned char s_g2[128]);
+int spb_srs_get_g2(spb_ctx* ctx, const spb_srs* srs, unsigned char g2[128], unsigned char s_g2[128]);
+uint32_t spb_srs_k(const spb_srs* srs);
 
 /* ---- MSM -------------------------------------------------------------------------------------------------- */
 /* best_multiexp(coeffs, bases) -> G1 ([UPSTREAM] halo2_proofs/src/arithmetic.rs): sum_i scalars[i] * bases[i].

@@ -862,3 +862,9 @@ void orc_lookup_constraints(fe* values, uint64_t size, int32_t rot_scale, const 
 void orc_fr_delta(fe* out) {  /* Fr::DELTA = MULTIPLICATIVE_GENERATOR^(2^S) = 7^(2^28) */
   *out = f_pow(&FR, f_from_u64(&FR, 7), (uint64_t[4]){1ull << 28, 0, 0, 0});
 }
+
+/* G2 generator and s_g2 in the RawBytes layout of ParamsKZG::write (x.c0, x.c1, y.c0, y.c1; Montgomery limbs). */
+void orc_srs_g2_raw(fe g2[4], fe s_g2[4]) {
+  g2[0] = G2_GEN.x.c0; g2[1] = G2_GEN.x.c1; g2[2] = G2_GEN.y.c0; g2[3] = G2_GEN.y.c1;
+  orc_srs_s_g2(s_g2);
+}

@@ -314,3 +314,17 @@ def lookup_constraints(values, rot_scale, product, permuted_input, permuted_tabl
     args = [np.ascontiguousarray(a, dtype=np.uint64) for a in (product, permuted_input, permuted_table, table_value, l0, l_last, l_active, beta, gamma, y)]
     lib().orc_lookup_constraints(_p(values), ctypes.c_uint64(values.shape[0]), ctypes.c_int32(rot_scale), *[_p(a) for a in args])
     return values
+
+
+def write_params_file(path, k, threads=None):
+    """The file `ParamsKZG::<Bn256>::setup(k, ChaCha20Rng::from_seed([0;32])).write(..)` produces (SerdeFormat::RawBytes):
+    k u32 LE | g | g_lagrange | g2 | s_g2, Montgomery limbs -- i.e. halo2-base gen_srs's params/kzg_bn254_{k}.srs."""
+    n = 1 << k
+    g2 = np.empty((4, 4), dtype=np.uint64); s_g2 = np.empty((4, 4), dtype=np.uint64)
+    lib().orc_srs_g2_raw(_p(g2), _p(s_g2))
+    with open(path, "wb") as f:
+        f.write(np.uint32(k).tobytes())
+        f.write(srs_g(k, 0, n, threads).tobytes())
+        f.write(srs_g_lagrange(k, 0, n, threads).tobytes())
+        f.write(g2.tobytes()); f.write(s_g2.tobytes())
+    return g2, s_g2

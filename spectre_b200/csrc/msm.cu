@@ -17,6 +17,7 @@ struct SrsShard {
 struct spb_srs {
   uint32_t k = 0;
   size_t n = 0;
+  unsigned char g2[128] = {0}, s_g2[128] = {0};  // carried through read/write only (the prover never touches G2)
   uint32_t table_c = 0;  // 0: no precomputed tables
   std::vector<SrsShard> shards;  // one per device of the context, contiguous point ranges
 };
@@ -319,6 +320,89 @@ fail:
   spb_srs_free(ctx, s);
   return SPB_ERR_CUDA;
 }
+
+// ParamsKZG::read / write in SerdeFormat::RawBytes: k (u32 LE) | g[n] | g_lagrange[n] | g2 | s_g2, every coordinate as
+// its in-memory Montgomery limbs -- the file halo2-base's gen_srs caches as params/kzg_bn254_{k}.srs
+// ([UPSTREAM] halo2_proofs/src/poly/kzg/commitment.rs; reference .gitignore:36 `params/`). Streamed through a pinned
+// staging buffer straight into device memory (K = 24: 4 GiB).
+int spb_srs_read_file(spb_ctx* ctx, const char* path, spb_srs** out) {
+  if (!ctx || !path || !out) return SPB_ERR_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) return set_error(ctx, SPB_ERR_ARG, "spb_srs_read_file: cannot open %s", path);
+  uint32_t k = 0;
+  if (fread(&k, 4, 1, f) != 1 || k > 28) { fclose(f); return set_error(ctx, SPB_ERR_ARG, "spb_srs_read_file: bad header in %s", path); }
+  spb_srs* s;
+  int rc = 0;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    s = srs_alloc(ctx, k);
+    const size_t chunk_pts = (size_t)1 << 18;  // 16 MiB staging
+    G1Affine* stage = nullptr;
+    if (cudaMallocHost(&stage, chunk_pts * sizeof(G1Affine)) != cudaSuccess) { fclose(f); delete s; return set_error(ctx, SPB_ERR_OOM, "spb_srs_read_file: pinned staging"); }
+    for (int which = 0; which < 2 && rc == 0; which++) {
+      for (auto& sh : s->shards) {
+        DeviceState& d = ctx->dev[sh.dev_index];
+        cudaSetDevice(d.device);
+        G1Affine** dst = which == 0 ? &sh.g : &sh.g_lagrange;
+        if (sh.count && cudaMalloc(dst, sh.count * sizeof(G1Affine)) != cudaSuccess) { rc = set_error(ctx, SPB_ERR_OOM, "spb_srs_read_file: cudaMalloc"); break; }
+        for (size_t off = 0; off < sh.count && rc == 0; off += chunk_pts) {
+          size_t cnt = sh.count - off < chunk_pts ? sh.count - off : chunk_pts;
+          if (fread(stage, sizeof(G1Affine), cnt, f) != cnt) { rc = set_error(ctx, SPB_ERR_ARG, "spb_srs_read_file: %s is truncated", path); break; }
+          if (cudaMemcpy(*dst + off, stage, cnt * sizeof(G1Affine), cudaMemcpyHostToDevice) != cudaSuccess) rc = set_error(ctx, SPB_ERR_CUDA, "spb_srs_read_file: H2D copy");
+        }
+        if (rc) break;
+      }
+    }
+    if (rc == 0 && (fread(s->g2, 128, 1, f) != 1 || fread(s->s_g2, 128, 1, f) != 1)) rc = set_error(ctx, SPB_ERR_ARG, "spb_srs_read_file: %s has no G2 trailer", path);
+    cudaFreeHost(stage);
+  }
+  fclose(f);
+  if (rc) { spb_srs_free(ctx, s); return rc; }
+  *out = s;
+  return 0;
+}
+
+int spb_srs_write_file(spb_ctx* ctx, const spb_srs* srs, const char* path) {
+  if (!ctx || !srs || !path) return SPB_ERR_ARG;
+  if (srs->table_c) return set_error(ctx, SPB_ERR_STATE, "spb_srs_write_file: call before spb_srs_precompute (rows 1.. are derived data)");
+  FILE* f = fopen(path, "wb");
+  if (!f) return set_error(ctx, SPB_ERR_ARG, "spb_srs_write_file: cannot create %s", path);
+  int rc = 0;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    fwrite(&srs->k, 4, 1, f);
+    const size_t chunk_pts = (size_t)1 << 18;
+    std::vector<G1Affine> stage(chunk_pts);
+    for (int which = 0; which < 2 && rc == 0; which++)
+      for (auto& sh : srs->shards) {
+        const G1Affine* src = which == 0 ? sh.g : sh.g_lagrange;
+        if (!src && sh.count) { rc = set_error(ctx, SPB_ERR_STATE, "spb_srs_write_file: basis %d not resident", which); break; }
+        cudaSetDevice(ctx->dev[sh.dev_index].device);
+        for (size_t off = 0; off < sh.count && rc == 0; off += chunk_pts) {
+          size_t cnt = sh.count - off < chunk_pts ? sh.count - off : chunk_pts;
+          if (cudaMemcpy(stage.data(), src + off, cnt * sizeof(G1Affine), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = set_error(ctx, SPB_ERR_CUDA, "spb_srs_write_file: D2H copy"); break; }
+          if (fwrite(stage.data(), sizeof(G1Affine), cnt, f) != cnt) rc = set_error(ctx, SPB_ERR_ARG, "spb_srs_write_file: short write");
+        }
+      }
+    if (rc == 0) { fwrite(srs->g2, 128, 1, f); fwrite(srs->s_g2, 128, 1, f); }
+  }
+  fclose(f);
+  return rc;
+}
+
+// G2 trailer of the params file (x.c0, x.c1, y.c0, y.c1 Montgomery limbs each): g2 and s_g2; set by the caller after
+// spb_srs_setup / spb_srs_upload when the handle will be written out.
+int spb_srs_set_g2(spb_ctx* ctx, spb_srs* srs, const unsigned char g2[128], const unsigned char s_g2[128]) {
+  if (!ctx || !srs || !g2 || !s_g2) return SPB_ERR_ARG;
+  memcpy(srs->g2, g2, 128); memcpy(srs->s_g2, s_g2, 128);
+  return 0;
+}
+int spb_srs_get_g2(spb_ctx* ctx, const spb_srs* srs, unsigned char g2[128], unsigned char s_g2[128]) {
+  if (!ctx || !srs || !g2 || !s_g2) return SPB_ERR_ARG;
+  memcpy(g2, srs->g2, 128); memcpy(s_g2, srs->s_g2, 128);
+  return 0;
+}
+uint32_t spb_srs_k(const spb_srs* srs) { return srs ? srs->k : 0; }
 
 int spb_srs_download(spb_ctx* ctx, const spb_srs* srs, int basis, size_t start, size_t count, spb_g1_affine* out) {
   if (!ctx || !srs || !out || start + count > srs->n) return SPB_ERR_ARG;

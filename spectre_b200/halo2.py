@@ -377,6 +377,27 @@ class ParamsKZG:
         backend.check(backend.lib.spb_srs_upload(backend.ctx, ctypes.c_uint32(k), _p(g), _p(g_lagrange), ctypes.byref(h)), "spb_srs_upload")
         return cls(backend, k, h)
 
+    @classmethod
+    def read(cls, backend, path):
+        """ParamsKZG::read(reader) for SerdeFormat::RawBytes (the params/kzg_bn254_{k}.srs cache of gen_srs)."""
+        h = ctypes.c_void_p()
+        backend.check(backend.lib.spb_srs_read_file(backend.ctx, path.encode(), ctypes.byref(h)), "spb_srs_read_file")
+        backend.lib.spb_srs_k.restype = ctypes.c_uint32
+        backend.lib.spb_srs_k.argtypes = [ctypes.c_void_p]
+        return cls(backend, int(backend.lib.spb_srs_k(h)), h)
+
+    def write(self, path):
+        self.be.check(self.be.lib.spb_srs_write_file(self.be.ctx, self.h, path.encode()), "spb_srs_write_file")
+
+    def set_g2(self, g2, s_g2):
+        g2 = np.ascontiguousarray(g2, dtype=np.uint64).reshape(16); s_g2 = np.ascontiguousarray(s_g2, dtype=np.uint64).reshape(16)
+        self.be.check(self.be.lib.spb_srs_set_g2(self.be.ctx, self.h, _p(g2), _p(s_g2)), "spb_srs_set_g2")
+
+    def get_g2(self):
+        g2 = np.empty(16, dtype=np.uint64); s_g2 = np.empty(16, dtype=np.uint64)
+        self.be.check(self.be.lib.spb_srs_get_g2(self.be.ctx, self.h, _p(g2), _p(s_g2)), "spb_srs_get_g2")
+        return g2, s_g2
+
     def __del__(self):
         try:
             if self.be.ctx:

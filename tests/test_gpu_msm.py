@@ -251,3 +251,25 @@ def test_full_size_k23_known_tau_and_linearity(be, orc):
     table[: 1 << kat["lookup_bits"]] = orc.fr_seq(1 << kat["lookup_bits"])
     got = orc.affine_ints(affine_of(orc, params.commit_lagrange(table)))[0]
     assert list(got) == [int(v, 16) for v in kat["xy"]]
+
+
+def test_params_file_read_write_roundtrip(be, orc, tmp_path):
+    """ParamsKZG::read of a gen_srs-style params file (written by the oracle in SerdeFormat::RawBytes), commit through
+    it, write it back byte-identically."""
+    from spectre_b200.halo2 import ParamsKZG, BASIS_G, BASIS_G_LAGRANGE
+    k = 9
+    src = str(tmp_path / ("kzg_bn254_%d.srs" % k))
+    g2, s_g2 = orc.write_params_file(src, k)
+    params = ParamsKZG.read(be, src)
+    assert params.k == k
+    assert np.array_equal(params.get_g(basis=BASIS_G), orc.srs_g(k, 0, 1 << k))
+    assert np.array_equal(params.get_g(basis=BASIS_G_LAGRANGE), orc.srs_g_lagrange(k, 0, 1 << k))
+    got_g2, got_s = params.get_g2()
+    assert np.array_equal(got_g2.reshape(4, 4), g2) and np.array_equal(got_s.reshape(4, 4), s_g2)
+    poly = orc.fr_random_chacha(1 << k, 5)
+    assert np.array_equal(affine_of(orc, params.commit_lagrange(poly)), orc.commit_lagrange_known_tau(k, poly))
+    dst = str(tmp_path / "copy.srs")
+    params.write(dst)
+    assert open(src, "rb").read() == open(dst, "rb").read()
+    with pytest.raises(Exception):
+        ParamsKZG.read(be, str(tmp_path / "missing.srs"))
