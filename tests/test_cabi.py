@@ -60,3 +60,57 @@ def test_product_never_imports_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     text = f.read()
                 assert "halo2_oracle" not in text and "from oracle" not in text and "import oracle" not in text, fn
+
+
+def _build_cpp_mirror(libpath):
+    exe = os.path.join(ROOT, "tests", "cpp", "host_mirror")
+    src = exe + ".cpp"
+    libdir = os.path.dirname(libpath)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, src, "-L" + libdir, "-lspectre_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_host_mirror_compiles_and_links(libpath):
+    """include/spectre_b200.hpp (the compiled-language host side) builds against the C ABI."""
+    exe = _build_cpp_mirror(libpath)
+    assert subprocess.check_output([exe], text=True).strip() == "linked"
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_runs(libpath):
+    exe = _build_cpp_mirror(libpath)
+    out = subprocess.run([exe, "run"], capture_output=True, text=True)
+    assert out.returncode == 0 and "host mirror ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_error_paths_and_threads(libpath):
+    """Errors come back as status codes with text; two Python threads can share one context."""
+    import threading
+    import numpy as np
+    from spectre_b200 import halo2
+    from oracle import oracle as orc
+    orc.build(); orc.lib()
+    be = halo2.Backend([0])
+    k = 8
+    params = halo2.ParamsKZG.setup(be, k, orc.srs_tau())
+    too_long = orc.fr_random_chacha((1 << k) + 1, 1)
+    with pytest.raises(AssertionError):
+        params.commit(too_long)
+    out = np.empty(12, dtype=np.uint64)
+    rc = be.lib.spb_msm(be.ctx, params.h, 0, too_long.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(too_long.shape[0]), out.ctypes.data_as(ctypes.c_void_p))
+    assert rc != 0 and b"SRS has" in be.lib.spb_last_error(be.ctx)
+    rc = be.lib.spb_ntt(be.ctx, too_long.ctypes.data_as(ctypes.c_void_p), 29, too_long.ctypes.data_as(ctypes.c_void_p))
+    assert rc != 0
+    empty = params.commit(np.zeros((0, 4), dtype=np.uint64))
+    assert not empty[8:].any()
+    polys = [orc.fr_random_chacha(1 << k, 10 + i) for i in range(6)]
+    want = [orc.commit_known_tau(p) for p in polys]
+    results = [None] * len(polys)
+
+    def work(i):
+        results[i] = orc.g1_to_affine(params.commit(polys[i]))
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(polys))]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert all(np.array_equal(r, w) for r, w in zip(results, want))
+    be.close()
