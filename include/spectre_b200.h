@@ -44,6 +44,7 @@ typedef struct spb_domain spb_domain; /* EvaluationDomain<Fr> constants */
 #define SPB_ERR_ARG (-2)
 #define SPB_ERR_OOM (-3)
 #define SPB_ERR_STATE (-4)
+#define SPB_ERR_CONSTRAINT (-5) /* halo2's Error::ConstraintSystemFailure (lookup input not in table) */
 
 #define SPB_BASIS_G 0          /* monomial basis  (Params::commit)          */
 #define SPB_BASIS_G_LAGRANGE 1 /* Lagrange basis  (Params::commit_lagrange) */
@@ -202,6 +203,13 @@ int spb_permutation_constraints_dev(spb_ctx* ctx, spb_fr* d_values, uint64_t siz
 int spb_lookup_constraints_dev(spb_ctx* ctx, spb_fr* d_values, uint64_t size, int32_t rot_scale, const spb_fr* d_product, const spb_fr* d_permuted_input,
                                const spb_fr* d_permuted_table, const spb_fr* d_table_value, const spb_fr* d_l0, const spb_fr* d_l_last,
                                const spb_fr* d_l_active, const spb_fr* beta, const spb_fr* gamma, const spb_fr* y);
+
+/* ---- lookup argument ([UPSTREAM] halo2_proofs/src/plonk/lookup/prover.rs) ------------------------------------------ */
+/* permute_expression_pair over the `usable` rows (blinding rows are appended by the caller from its RNG):
+ * d_permuted_input = input values sorted by canonical integer; d_permuted_table = the table values rearranged so that
+ * every row satisfies a' == s' or a' == a'[row-1], exactly as the CPU algorithm arranges them.
+ * Returns SPB_ERR_CONSTRAINT when an input value does not occur in the table. */
+int spb_permute_expression_pair_dev(spb_ctx* ctx, const spb_fr* d_input, const spb_fr* d_table, size_t usable, spb_fr* d_permuted_input, spb_fr* d_permuted_table);
 
 /* ---- test / bench utilities -------------------------------------------------------------------------------- */
 /* out[i] = scalars[i] * G1 (affine), computed on the device */

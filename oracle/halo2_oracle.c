@@ -868,3 +868,47 @@ void orc_srs_g2_raw(fe g2[4], fe s_g2[4]) {
   g2[0] = G2_GEN.x.c0; g2[1] = G2_GEN.x.c1; g2[2] = G2_GEN.y.c0; g2[3] = G2_GEN.y.c1;
   orc_srs_s_g2(s_g2);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * permute_expression_pair: [UPSTREAM] halo2_proofs/src/plonk/lookup/prover.rs (stage 4 of create_proof,
+ * SURVEY.md 8a row a8). Values are compared as halo2curves' `Ord for Fr` does: by canonical integer.
+ * Returns 0, or -1 when an input value does not occur in the table (upstream: Error::ConstraintSystemFailure).
+ * Only the first `usable` rows take part; blinding rows are appended by the caller from its RNG.
+ * ---------------------------------------------------------------------------------------------- */
+static int canon_cmp(const void* pa, const void* pb) {
+  const uint64_t* a = (const uint64_t*)pa; const uint64_t* b = (const uint64_t*)pb;
+  for (int i = 3; i >= 0; i--) { if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1; }
+  return 0;
+}
+int orc_permute_expression_pair(const fe* input, const fe* table, size_t usable, fe* permuted_input, fe* permuted_table) {
+  fe* in = (fe*)malloc((usable ? usable : 1) * sizeof(fe));
+  fe* tb = (fe*)malloc((usable ? usable : 1) * sizeof(fe));
+  uint8_t* used = (uint8_t*)calloc(usable ? usable : 1, 1);
+  size_t* repeated = (size_t*)malloc((usable ? usable : 1) * sizeof(size_t));
+  for (size_t i = 0; i < usable; i++) { in[i] = f_to_canonical(&FR, input[i]); tb[i] = f_to_canonical(&FR, table[i]); }
+  qsort(in, usable, sizeof(fe), canon_cmp);      /* permuted_input_expression.sort() */
+  qsort(tb, usable, sizeof(fe), canon_cmp);      /* the BTreeMap of table values, as a sorted multiset */
+  size_t nrep = 0; int rc = 0;
+  for (size_t row = 0; row < usable; row++) {
+    permuted_input[row] = f_mul(&FR, in[row], FR.r2);
+    if (row == 0 || canon_cmp(&in[row], &in[row - 1]) != 0) {
+      permuted_table[row] = permuted_input[row];
+      /* remove one instance of the value from the leftover multiset: first unused occurrence */
+      size_t lo = 0, hi = usable;
+      while (lo < hi) { size_t mid = (lo + hi) / 2; if (canon_cmp(&tb[mid], &in[row]) < 0) lo = mid + 1; else hi = mid; }
+      if (lo >= usable || canon_cmp(&tb[lo], &in[row]) != 0) { rc = -1; break; }
+      used[lo] = 1;   /* distinct input values hit distinct first occurrences */
+    } else repeated[nrep++] = row;
+  }
+  if (rc == 0) {
+    /* leftover table elements ascending, each popped onto the LAST remaining repeated row */
+    for (size_t i = 0; i < usable; i++) {
+      if (used[i]) continue;
+      if (!nrep) { rc = -2; break; }
+      permuted_table[repeated[--nrep]] = f_mul(&FR, tb[i], FR.r2);
+    }
+    if (rc == 0 && nrep) rc = -2;
+  }
+  free(in); free(tb); free(used); free(repeated);
+  return rc;
+}

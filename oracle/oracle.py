@@ -328,3 +328,15 @@ def write_params_file(path, k, threads=None):
         f.write(srs_g_lagrange(k, 0, n, threads).tobytes())
         f.write(g2.tobytes()); f.write(s_g2.tobytes())
     return g2, s_g2
+
+
+def permute_expression_pair(input_expr, table_expr):
+    """-> (permuted_input, permuted_table) over the usable rows given; raises ValueError like upstream's
+    Error::ConstraintSystemFailure when an input value is missing from the table."""
+    a = np.ascontiguousarray(input_expr, dtype=np.uint64); t = np.ascontiguousarray(table_expr, dtype=np.uint64)
+    assert a.shape == t.shape
+    pi = np.empty_like(a); pt = np.empty_like(a)
+    rc = lib().orc_permute_expression_pair(_p(a), _p(t), ctypes.c_size_t(a.shape[0]), _p(pi), _p(pt))
+    if rc != 0:
+        raise ValueError("permute_expression_pair: ConstraintSystemFailure (%d)" % rc)
+    return pi, pt

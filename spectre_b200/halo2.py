@@ -248,6 +248,11 @@ class Backend:
                                                        _p(d_permuted_table), _p(d_table_value), _p(d_l0), _p(d_l_last), _p(d_l_active), _p(_fr_array(beta, 1)),
                                                        _p(_fr_array(gamma, 1)), _p(_fr_array(y, 1))), "spb_lookup_constraints_dev")
 
+    def permute_expression_pair_dev(self, d_input, d_table, usable, d_permuted_input, d_permuted_table):
+        """lookup::prover::permute_expression_pair on device buffers; raises like Error::ConstraintSystemFailure."""
+        self.check(self.lib.spb_permute_expression_pair_dev(self.ctx, _p(d_input), _p(d_table), ctypes.c_size_t(usable), _p(d_permuted_input),
+                                                            _p(d_permuted_table)), "spb_permute_expression_pair_dev")
+
     # ---- utilities -------------------------------------------------------------------------------------
     def g1_fixed_base_mul(self, scalars):
         scalars = _fr_array(scalars)
