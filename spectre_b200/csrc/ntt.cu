@@ -124,7 +124,11 @@ static int launch_pass(spb_ctx* ctx, DeviceState& d, const NttPlan& plan, uint32
   uint32_t threads = quads < max_threads ? quads : max_threads;
   size_t smem = (size_t)8 * 4 * ((size_t)ntt_col_stride(S, C) * C + ntt_tw_words(S));
   if (smem > 227 * 1024) return set_error(ctx, SPB_ERR_STATE, "ntt: tile needs %zu B of shared memory", smem);
-  ntt_pass_kernel<<<(unsigned)tiles, threads, smem, d.stream>>>(p);
+  // persistent CTAs: as many as fit the SMs (shared memory bound), striding over the tiles
+  uint64_t per_sm = (227 * 1024) / (smem + 1024); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+  uint64_t grid = (uint64_t)d.sm_count * per_sm; if (grid > tiles) grid = tiles;
+  p.ntiles = tiles;
+  ntt_pass_kernel<<<(unsigned)grid, threads, smem, d.stream>>>(p);
   SPB_CUDA(ctx, cudaGetLastError());
   ctx->n_kernel_launches++;
   return 0;

@@ -45,7 +45,8 @@ struct NttPassParams {
   uint32_t b_next;   // bits below the NEXT digit (passes before the last)
   uint32_t first, last;
   // ---- multi-device (six-step across devices); all zero / equal to the global values on one device ----------
-  uint64_t tile_base;   // added to blockIdx.x: this device's first tile (passes sharded by the first digit)
+  uint64_t ntiles;      // tiles this launch covers; CTAs are persistent and stride over them
+  uint64_t tile_base;   // added to the tile index: this device's first tile (passes sharded by the first digit)
   uint64_t lo_base;     // global index of this device's first column (first pass, sharded by columns)
   uint32_t b_addr;      // bits below the digit in THIS device's buffer (== b unless sharded by columns)
   uint32_t out_local;   // last pass: store at (o >> s1) * 2^out_cols_log + (i_1 - i1_base) instead of o
@@ -138,11 +139,21 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
   sm.data = smem_raw;
   sm.tw = smem_raw + 8 * sm.plane_words;
 
+  // ---- stage sub-NTT twiddles omega_{2^s}^j = omega^(j << (k-s)) into shared memory -----------------
+  for (uint32_t j = tid; j < (S >> 1); j += T) {
+    Fr w = ntt_omega_pow(p, (uint64_t)j << (p.k - p.s));
+    uint32_t o = ntt_pad(j);
+#pragma unroll
+    for (int l = 0; l < 8; l++) sm.tw[l * sm.tw_words + o] = w.l[l];
+  }
+
+  // persistent CTA: the sub-NTT twiddles are staged once, then the CTA strides over its tiles
+  for (uint64_t tile_it = blockIdx.x; tile_it < p.ntiles; tile_it += gridDim.x) {
+  const uint64_t tile = tile_it + p.tile_base;
+  uint64_t hi = 0, lo0 = 0, i1_0 = 0, hi_rest = 0;
   // ---- tile coordinates ---------------------------------------------------------------------------
   // not last: tile = (hi, lo chunk);           element (r, c) at ((hi << s) + r) << b  +  lo0 + c
   // last    : tile = (hi-with-i_1-chunk, all);  column c is the row whose first digit is i1_0 + c
-  const uint64_t tile = blockIdx.x + p.tile_base;
-  uint64_t hi = 0, lo0 = 0, i1_0 = 0, hi_rest = 0;
   const uint32_t rest_bits = p.a > p.s1 ? p.a - p.s1 : 0;  // bits of hi that are not the first digit (last pass, P = 3)
   if (!p.last) {
     const uint32_t chunks_log = p.b_addr - p.logc;
@@ -152,14 +163,6 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
     // chunk along the first digit; remaining hi bits (second digit when P = 3) are fixed per tile
     hi_rest = tile & ((1ull << rest_bits) - 1);
     i1_0 = (tile >> rest_bits) << p.logc;
-  }
-
-  // ---- stage sub-NTT twiddles omega_{2^s}^j = omega^(j << (k-s)) into shared memory -----------------
-  for (uint32_t j = tid; j < (S >> 1); j += T) {
-    Fr w = ntt_omega_pow(p, (uint64_t)j << (p.k - p.s));
-    uint32_t o = ntt_pad(j);
-#pragma unroll
-    for (int l = 0; l < 8; l++) sm.tw[l * sm.tw_words + o] = w.l[l];
   }
 
   // ---- load tile (natural order), fusing zero padding and the zeta-coset pre-scale -----------------
@@ -240,6 +243,8 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassParams p) {
         ntt_stg(p.dst + addr, v);
       }
     }
+  }
+  __syncthreads();   // the next tile overwrites the shared-memory planes
   }
 }
 
