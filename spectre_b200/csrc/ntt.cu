@@ -127,6 +127,10 @@ static int launch_pass(spb_ctx* ctx, DeviceState& d, const NttPlan& plan, uint32
   // persistent CTAs: as many as fit the SMs (shared memory bound), striding over the tiles
   uint64_t per_sm = (227 * 1024) / (smem + 1024); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
   uint64_t grid = (uint64_t)d.sm_count * per_sm; if (grid > tiles) grid = tiles;
+  // Measured (profiles/r01_bench_progress.md): persistence pays up to 2^20 (launch + twiddle staging amortised); beyond
+  // that co-resident persistent CTAs run their load/compute phases in lockstep and lose the overlap that
+  // hardware-scheduled one-tile CTAs get for free, so large transforms launch one CTA per tile.
+  if (k > 20) grid = tiles;
   p.ntiles = tiles;
   ntt_pass_kernel<<<(unsigned)grid, threads, smem, d.stream>>>(p);
   SPB_CUDA(ctx, cudaGetLastError());
