@@ -74,7 +74,19 @@ def replay(be, shape_name, tau, seed=1, tables=True, verbose=False):
 
     t_all = time.perf_counter()
     timed("3_advice_commit", lambda: params.commit_batch_dev(GL, [ptr(c) for c in cols[:A]], n))
-    timed("4_lookup_permuted_commit", lambda: params.commit_batch_dev(GL, [ptr(cols[(A + i) % n_polys]) for i in range(2 * L)], n))
+    # lookups: permute_expression_pair (sort + multiset walk) on a range table, then the two permuted commitments
+    usable = n - 6
+    table = torch.zeros((n, 4), dtype=torch.int64, device=dev); table[:, 0] = torch.arange(n, device=dev) % (1 << min(k - 1, 19))
+    gsel = torch.Generator(device=dev); gsel.manual_seed(seed + 999)
+    lk_in = table[torch.randint(0, usable, (n,), device=dev, generator=gsel)].contiguous()
+    perm_in = torch.empty((n, 4), dtype=torch.int64, device=dev); perm_tb = torch.empty((n, 4), dtype=torch.int64, device=dev)
+
+    def lookups():
+        for _ in range(L):
+            be.permute_expression_pair_dev(ptr(lk_in), ptr(table), usable, ptr(perm_in), ptr(perm_tb))
+            perm_in[usable:] = 0; perm_tb[usable:] = 0     # blinding rows come from the caller's RNG
+            params.commit_batch_dev(GL, [ptr(perm_in), ptr(perm_tb)], n)
+    timed("4_lookup_permute_and_commit", lookups)
 
     def grand_products():
         for i in range(P + L):

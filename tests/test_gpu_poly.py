@@ -79,4 +79,4 @@ def test_proof_replay_tiny_runs(be, orc):
     from spectre_b200 import replay
     out = replay.replay(be, "tiny_k10", orc.srs_tau())
     assert out["msm_count"] == 3 + 2 + 3 + 1 + 3 + 2 and out["total_s"] > 0
-    assert set(out["stages_s"]) >= {"3_advice_commit", "7_lagrange_to_coeff", "8a_coeff_to_extended", "8b_evaluate_h", "9_vanishing_construct_commit", "11_shplonk"}
+    assert set(out["stages_s"]) >= {"3_advice_commit", "4_lookup_permute_and_commit", "7_lagrange_to_coeff", "8a_coeff_to_extended", "8b_evaluate_h", "9_vanishing_construct_commit", "11_shplonk"}
