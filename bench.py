@@ -297,7 +297,8 @@ def main():
         "config": {"workload": "BN254 G1 MSM 2^20 random points / uniform scalars per GPU (BASELINE configs[1]); N ranks = one N*2^20 MSM sharded by point range",
                    "log_n": LOG_N, "window_bits": c, "windows": W, "precomputed_window_tables": not args.no_tables,
                    "pipelining": "steps submitted through spb_msm_batch(_dev): two stream lanes overlap one MSM's tail with the next one's sort/accumulate", "l2": "scalars rotate over 8 resident sets (256 MiB > 126 MB L2); the 64 MiB basis is reused as in the prover",
-                   "collective": "all_gather of 96-byte partial sums (NCCL)" if world > 1 else "none"},
+                   "collective": "one all_gather of the batch's 96-byte partial sums (NCCL) + host fold" if world > 1 else "none",
+                   "timing": "wall clock between barrier + cuda synchronize pairs around exactly K steps, max over ranks; per-kernel times are CUDA events on the library's streams"},
         "single_msm_device_ms": dev_ms / args.steps, "g1_adds_per_s": adds * world / (ms_per_step * 1e-3),
         "stages_ms": stages_pipelined, "stages_ms_unpipelined": stages, "srs_setup_s": setup_s,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": N_PAIRS * 32, "d2h_bytes_per_step": 96, "ms_per_step": e2e_wall_ms / e2e_steps},
