@@ -72,104 +72,113 @@ def replay(be, shape_name, tau, seed=1, tables=True, verbose=False):
     params.commit_batch_dev(GL, [ptr(cols[0])], n); dom.lagrange_to_coeff_dev(ptr(scratch[:n])); dom.coeff_to_extended_dev(ptr(cols[0]), ptr(scratch)); dom.extended_to_coeff_dev(ptr(scratch), ptr(hq))
     torch.cuda.synchronize()
 
-    t_all = time.perf_counter()
-    timed("3_advice_commit", lambda: params.commit_batch_dev(GL, [ptr(c) for c in cols[:A]], n))
-    # lookups: permute_expression_pair (sort + multiset walk) on a range table, then the two permuted commitments
-    usable = n - 6
-    table = torch.zeros((n, 4), dtype=torch.int64, device=dev); table[:, 0] = torch.arange(n, device=dev) % (1 << min(k - 1, 19))
-    gsel = torch.Generator(device=dev); gsel.manual_seed(seed + 999)
-    lk_in = table[torch.randint(0, usable, (n,), device=dev, generator=gsel)].contiguous()
-    perm_in = torch.empty((n, 4), dtype=torch.int64, device=dev); perm_tb = torch.empty((n, 4), dtype=torch.int64, device=dev)
+    # The schedule runs twice and the second pass is reported: the first one pays the one-time costs a long-lived prover
+    # (Spectre's RPC server keeps ProverState for its lifetime, prover/src/prover.rs:44-116) pays once -- lazy kernel
+    # loading, workspace allocation, twiddle tables.
+    first_pass_s = None
+    for rep in range(2):
+        stages.clear()
+        t_all = time.perf_counter()
+        timed("3_advice_commit", lambda: params.commit_batch_dev(GL, [ptr(c) for c in cols[:A]], n))
+        # lookups: permute_expression_pair (sort + multiset walk) on a range table, then the two permuted commitments
+        usable = n - 6
+        table = torch.zeros((n, 4), dtype=torch.int64, device=dev); table[:, 0] = torch.arange(n, device=dev) % (1 << min(k - 1, 19))
+        gsel = torch.Generator(device=dev); gsel.manual_seed(seed + 999)
+        lk_in = table[torch.randint(0, usable, (n,), device=dev, generator=gsel)].contiguous()
+        perm_in = torch.empty((n, 4), dtype=torch.int64, device=dev); perm_tb = torch.empty((n, 4), dtype=torch.int64, device=dev)
 
-    def lookups():
-        for _ in range(L):
-            be.permute_expression_pair_dev(ptr(lk_in), ptr(table), usable, ptr(perm_in), ptr(perm_tb))
-            perm_in[usable:] = 0; perm_tb[usable:] = 0     # blinding rows come from the caller's RNG
-            params.commit_batch_dev(GL, [ptr(perm_in), ptr(perm_tb)], n)
-    timed("4_lookup_permute_and_commit", lookups)
+        def lookups():
+            for _ in range(L):
+                be.permute_expression_pair_dev(ptr(lk_in), ptr(table), usable, ptr(perm_in), ptr(perm_tb))
+                perm_in[usable:] = 0; perm_tb[usable:] = 0     # blinding rows come from the caller's RNG
+                torch.cuda.current_stream().synchronize()
+                params.commit_batch_dev(GL, [ptr(perm_in), ptr(perm_tb)], n)
+        timed("4_lookup_permute_and_commit", lookups)
 
-    def grand_products():
-        for i in range(P + L):
-            c = cols[(A + 1 + i) % n_polys]
-            tmp = scratch[:n]
-            tmp.copy_(c)
-            be.batch_invert_dev(ptr(tmp), n)          # denominators
-            be.vec_mul_dev(ptr(tmp), ptr(c), n)       # numerator / denominator
-            be.grand_product_dev(ptr(tmp), n, ptr(scratch[n:2 * n]))
-        params.commit_batch_dev(GL, [ptr(cols[(A + 1 + i) % n_polys]) for i in range(P + L)], n)
-    timed("5_grand_products_commit", grand_products)
-    timed("6_vanishing_random_commit", lambda: params.commit_batch_dev(G, [ptr(cols[0])], n))
+        def grand_products():
+            for i in range(P + L):
+                c = cols[(A + 1 + i) % n_polys]
+                tmp = scratch[:n]
+                tmp.copy_(c); torch.cuda.current_stream().synchronize()   # torch's stream is not the library's
+                be.batch_invert_dev(ptr(tmp), n)          # denominators
+                be.vec_mul_dev(ptr(tmp), ptr(c), n)       # numerator / denominator
+                be.grand_product_dev(ptr(tmp), n, ptr(scratch[n:2 * n]))
+            params.commit_batch_dev(GL, [ptr(cols[(A + 1 + i) % n_polys]) for i in range(P + L)], n)
+        timed("5_grand_products_commit", grand_products)
+        timed("6_vanishing_random_commit", lambda: params.commit_batch_dev(G, [ptr(cols[0])], n))
 
-    def to_coeff():
-        for c in cols:
-            dom.lagrange_to_coeff_dev(ptr(c))
-    timed("7_lagrange_to_coeff", to_coeff)
+        def to_coeff():
+            for c in cols:
+                dom.lagrange_to_coeff_dev(ptr(c))
+        timed("7_lagrange_to_coeff", to_coeff)
 
-    def to_extended():
-        for c, e in zip(cols, ext):
-            dom.coeff_to_extended_dev(ptr(c), ptr(e))
-    timed("8a_coeff_to_extended", to_extended)
-    # evaluate_h on the extended coset: custom gates (graph), permutation argument, lookups
-    rot_scale = 1 << (dom.extended_k - k)
-    ADD, SUB, MUL, HORNER = 0, 1, 2, 6
-    K_INTER, K_FIXED, K_ADVICE, K_BETA, K_GAMMA, K_THETA, K_Y, K_PREV = 1, 2, 3, 6, 7, 8, 9, 10
-    rotations = np.array([0, 1, 2, 3], dtype=np.int32)
-    prog, t = [], 0
-    for a_i in range(A):                                   # q_a * (a + b*c - d) with b,c,d at rotations 1,2,3; fold with y
-        prog += [MUL, t, K_ADVICE, a_i | (1 << 16), K_ADVICE, a_i | (2 << 16)]
-        prog += [ADD, t + 1, K_ADVICE, a_i, K_INTER, t]
-        prog += [SUB, t + 2, K_INTER, t + 1, K_ADVICE, a_i | (3 << 16)]
-        prog += [MUL, t + 3, K_FIXED, a_i % max(1, F), K_INTER, t + 2]
-        prog += [HORNER | (1 << 8), t + 4, (K_PREV if a_i == 0 else K_INTER), (0 if a_i == 0 else t - 1), K_Y, 0, K_INTER, t + 3]
-        t += 5
-    gate_prog = np.array(prog, dtype=np.uint32)
-    fixed_ext = [ptr(ext[i % n_polys]) for i in range(max(1, F))]       # proving-key cosets (resident in a real prover)
-    advice_ext = [ptr(e) for e in ext[:A]]
-    zero = np.zeros((1, 4), dtype=np.uint64)
-    beta, gamma, theta = y, x, y
-    perm_cols = [ptr(e) for e in ext[:A + 1]] + fixed_ext[:1]            # advice + instance + one constant column
-    chunk = max(1, j - 2)
-    n_sets = (len(perm_cols) + chunk - 1) // chunk
-    z_sets = [ptr(ext[(A + 1 + i) % n_polys]) for i in range(n_sets)]
-    sigma = [fixed_ext[i % len(fixed_ext)] for i in range(len(perm_cols))]
-    l0, l_last, l_active = fixed_ext[0], fixed_ext[-1], fixed_ext[len(fixed_ext) // 2]
-    lk_prog = np.array([HORNER | (1 << 8), 0, K_ADVICE, 0, K_THETA, 0, K_ADVICE, 0 | (1 << 16),      # compressed input
-                        HORNER | (1 << 8), 1, K_FIXED, 0, K_THETA, 0, K_FIXED, 0 | (1 << 16),        # compressed table
-                        ADD, 2, K_INTER, 0, K_BETA, 0, ADD, 3, K_INTER, 1, K_GAMMA, 0, MUL, 4, K_INTER, 2, K_INTER, 3], dtype=np.uint32)
-    table_value = torch.empty((E, 4), dtype=torch.int64, device=dev)
+        def to_extended():
+            for c, e in zip(cols, ext):
+                dom.coeff_to_extended_dev(ptr(c), ptr(e))
+        timed("8a_coeff_to_extended", to_extended)
+        # evaluate_h on the extended coset: custom gates (graph), permutation argument, lookups
+        rot_scale = 1 << (dom.extended_k - k)
+        ADD, SUB, MUL, HORNER = 0, 1, 2, 6
+        K_INTER, K_FIXED, K_ADVICE, K_BETA, K_GAMMA, K_THETA, K_Y, K_PREV = 1, 2, 3, 6, 7, 8, 9, 10
+        rotations = np.array([0, 1, 2, 3], dtype=np.int32)
+        prog, t = [], 0
+        for a_i in range(A):                                   # q_a * (a + b*c - d) with b,c,d at rotations 1,2,3; fold with y
+            prog += [MUL, t, K_ADVICE, a_i | (1 << 16), K_ADVICE, a_i | (2 << 16)]
+            prog += [ADD, t + 1, K_ADVICE, a_i, K_INTER, t]
+            prog += [SUB, t + 2, K_INTER, t + 1, K_ADVICE, a_i | (3 << 16)]
+            prog += [MUL, t + 3, K_FIXED, a_i % max(1, F), K_INTER, t + 2]
+            prog += [HORNER | (1 << 8), t + 4, (K_PREV if a_i == 0 else K_INTER), (0 if a_i == 0 else t - 1), K_Y, 0, K_INTER, t + 3]
+            t += 5
+        gate_prog = np.array(prog, dtype=np.uint32)
+        fixed_ext = [ptr(ext[i % n_polys]) for i in range(max(1, F))]       # proving-key cosets (resident in a real prover)
+        advice_ext = [ptr(e) for e in ext[:A]]
+        zero = np.zeros((1, 4), dtype=np.uint64)
+        beta, gamma, theta = y, x, y
+        perm_cols = [ptr(e) for e in ext[:A + 1]] + fixed_ext[:1]            # advice + instance + one constant column
+        chunk = max(1, j - 2)
+        n_sets = (len(perm_cols) + chunk - 1) // chunk
+        z_sets = [ptr(ext[(A + 1 + i) % n_polys]) for i in range(n_sets)]
+        sigma = [fixed_ext[i % len(fixed_ext)] for i in range(len(perm_cols))]
+        l0, l_last, l_active = fixed_ext[0], fixed_ext[-1], fixed_ext[len(fixed_ext) // 2]
+        lk_prog = np.array([HORNER | (1 << 8), 0, K_ADVICE, 0, K_THETA, 0, K_ADVICE, 0 | (1 << 16),      # compressed input
+                            HORNER | (1 << 8), 1, K_FIXED, 0, K_THETA, 0, K_FIXED, 0 | (1 << 16),        # compressed table
+                            ADD, 2, K_INTER, 0, K_BETA, 0, ADD, 3, K_INTER, 1, K_GAMMA, 0, MUL, 4, K_INTER, 2, K_INTER, 3], dtype=np.uint32)
+        table_value = torch.empty((E, 4), dtype=torch.int64, device=dev)
 
-    def evaluate_h():
-        be.graph_evaluate_dev(gate_prog, 5 * A, 5 * A, zero, rotations, fixed_ext, advice_ext, [], zero, beta, gamma, theta, y, ptr(scratch), E, rot_scale)
-        be.permutation_constraints_dev(ptr(scratch), E, rot_scale, -(6 + 1), chunk, z_sets, perm_cols, sigma, l0, l_last, l_active, beta, gamma, y, dom.extended_omega)
-        for li in range(L):
-            be.graph_evaluate_dev(lk_prog, 5, 5, zero, rotations, fixed_ext, [advice_ext[li % A]], [], zero, beta, gamma, theta, y, ptr(table_value), E, rot_scale)
-            lp = (A + 1 + P + 3 * li) % n_polys
-            be.lookup_constraints_dev(ptr(scratch), E, rot_scale, ptr(ext[lp]), ptr(ext[(lp + 1) % n_polys]), ptr(ext[(lp + 2) % n_polys]), ptr(table_value),
-                                      l0, l_last, l_active, beta, gamma, y)
-    timed("8b_evaluate_h", evaluate_h)
+        def evaluate_h():
+            be.graph_evaluate_dev(gate_prog, 5 * A, 5 * A, zero, rotations, fixed_ext, advice_ext, [], zero, beta, gamma, theta, y, ptr(scratch), E, rot_scale)
+            be.permutation_constraints_dev(ptr(scratch), E, rot_scale, -(6 + 1), chunk, z_sets, perm_cols, sigma, l0, l_last, l_active, beta, gamma, y, dom.extended_omega)
+            for li in range(L):
+                be.graph_evaluate_dev(lk_prog, 5, 5, zero, rotations, fixed_ext, [advice_ext[li % A]], [], zero, beta, gamma, theta, y, ptr(table_value), E, rot_scale)
+                lp = (A + 1 + P + 3 * li) % n_polys
+                be.lookup_constraints_dev(ptr(scratch), E, rot_scale, ptr(ext[lp]), ptr(ext[(lp + 1) % n_polys]), ptr(ext[(lp + 2) % n_polys]), ptr(table_value),
+                                          l0, l_last, l_active, beta, gamma, y)
+        timed("8b_evaluate_h", evaluate_h)
 
-    def vanishing():
-        dom.divide_by_vanishing_poly_dev(ptr(scratch))
-        dom.extended_to_coeff_dev(ptr(scratch), ptr(hq))
-        params.commit_batch_dev(G, [ptr(hq[i * n:(i + 1) * n]) for i in range(Q)], n)
-    timed("9_vanishing_construct_commit", vanishing)
+        def vanishing():
+            dom.divide_by_vanishing_poly_dev(ptr(scratch))
+            dom.extended_to_coeff_dev(ptr(scratch), ptr(hq))
+            params.commit_batch_dev(G, [ptr(hq[i * n:(i + 1) * n]) for i in range(Q)], n)
+        timed("9_vanishing_construct_commit", vanishing)
 
-    def evaluations():
-        for i in range(evals):
-            be.eval_polynomial_dev(ptr(cols[i % n_polys]), n, x)
-    timed("10_evaluations", evaluations)
+        def evaluations():
+            for i in range(evals):
+                be.eval_polynomial_dev(ptr(cols[i % n_polys]), n, x)
+        timed("10_evaluations", evaluations)
 
-    def shplonk():
-        opened = [ptr(c) for c in cols] + [ptr(cols[i % n_polys]) for i in range(F)]
-        for s in range(4):                                    # rotation sets
-            be.lincomb_dev(opened[s::4], y, ptr(scratch[:n]), n)
-            be.kate_division_dev(ptr(scratch[:n]), n, x, ptr(scratch[n:2 * n]))
-        params.commit_batch_dev(G, [ptr(scratch[:n]), ptr(scratch[n:2 * n])], n)
-    timed("11_shplonk", shplonk)
-    total = time.perf_counter() - t_all
+        def shplonk():
+            opened = [ptr(c) for c in cols] + [ptr(cols[i % n_polys]) for i in range(F)]
+            for s in range(4):                                    # rotation sets
+                be.lincomb_dev(opened[s::4], y, ptr(scratch[:n]), n)
+                be.kate_division_dev(ptr(scratch[:n]), n, x, ptr(scratch[n:2 * n]))
+            params.commit_batch_dev(G, [ptr(scratch[:n]), ptr(scratch[n:2 * n])], n)
+        timed("11_shplonk", shplonk)
+        total = time.perf_counter() - t_all
+        if rep == 0:
+            first_pass_s = total
     msm_count = A + 2 * L + (P + L) + 1 + Q + 2
     out = {"shape": shape_name, "k": k, "extended_k": dom.extended_k, "msm_count": msm_count, "ntt_n": n_polys, "ntt_ext": n_polys, "intt_ext": 1,
-           "total_s": total, "setup_s": setup_s, "stages_s": {k_: round(v, 5) for k_, v in stages.items()},
+           "total_s": total, "first_pass_s": first_pass_s, "setup_s": setup_s, "stages_s": {k_: round(v, 5) for k_, v in stages.items()},
            "note": "proof-shaped replay of the primitive schedule (uniform synthetic columns), not a proof"}
     if verbose:
         print(out)
