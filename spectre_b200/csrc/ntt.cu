@@ -139,7 +139,9 @@ static int launch_pass(spb_ctx* ctx, DeviceState& d, const NttPlan& plan, uint32
 }
 
 static int set_smem_attr(spb_ctx* ctx, DeviceState& d) {
-  static std::map<int, bool> done;
+  static std::map<int, bool> done;      // process-wide (several contexts may share a device)
+  static std::mutex done_mu;
+  std::lock_guard<std::mutex> lk(done_mu);
   if (!done[d.device]) {
     SPB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     done[d.device] = true;
