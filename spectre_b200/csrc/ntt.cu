@@ -30,24 +30,7 @@ static size_t full_table_budget() {
   return v;
 }
 
-struct NttPlan {
-  uint32_t npass;
-  uint32_t s[3];
-};
-
-static NttPlan make_plan(uint32_t k) {
-  NttPlan p; memset(&p, 0, sizeof p);
-  const uint32_t kMaxDigitBits = max_digit_bits();
-  if (k <= kMaxDigitBits) { p.npass = 1; p.s[0] = k; return p; }
-  p.npass = (k + kMaxDigitBits - 1) / kMaxDigitBits;
-  uint32_t rem = k;
-  for (uint32_t i = 0; i < p.npass; i++) {
-    uint32_t left = p.npass - i;
-    p.s[i] = (rem + left - 1) / left;  // larger digits first
-    rem -= p.s[i];
-  }
-  return p;
-}
+static NttPlan make_plan(uint32_t k) { return ntt_make_plan(k, max_digit_bits()); }
 
 static int get_tables(spb_ctx* ctx, DeviceState& d, uint32_t k, const Fr& omega, uint32_t h, NttTables** out) {
   for (auto& t : d.ntt_tables)
@@ -83,56 +66,28 @@ static int get_tables(spb_ctx* ctx, DeviceState& d, uint32_t k, const Fr& omega,
   return 0;
 }
 
-// Fill the geometry of pass `pi` of `plan` (global view) and launch it. `sh` describes the device's share:
-// g_log = log2(#devices) (0 on one device), q = this device's index, mode: 0 = whole problem on this device,
-// 1 = first pass sharded by columns, 2 = later pass sharded by the first digit.
-struct NttShare { uint32_t g_log = 0, q = 0, mode = 0; };
+static uint32_t max_threads_per_cta() {
+  static uint32_t v = 0;
+  if (!v) { const char* e = getenv("SPB_NTT_THREADS"); v = e ? (uint32_t)atoi(e) : 256; if (v < 32 || v > 512) v = 512; }
+  return v;
+}
 
+// Geometry of pass `pi` (ntt_fill_pass, shared with the host emulation) and its launch.
 static int launch_pass(spb_ctx* ctx, DeviceState& d, const NttPlan& plan, uint32_t pi, uint32_t k, const NttTables* tb, uint32_t h,
                        const Fr* src, Fr* dst, const NttOpts& opts, const NttShare& sh) {
-  const uint64_t n = 1ull << k;
-  NttPassParams p; memset(&p, 0, sizeof p);
-  uint32_t a = 0; for (uint32_t i = 0; i < pi; i++) a += plan.s[i];
-  p.k = k; p.h = h; p.tw_lo = tb->tw_lo; p.tw_hi = tb->tw_hi; p.tw_full = tb->tw_full;
-  p.s = plan.s[pi]; p.a = a; p.b = k - a - p.s; p.s1 = plan.s[0];
-  p.first = (pi == 0); p.last = (pi == plan.npass - 1);
-  p.b_next = p.last ? 0 : p.b - plan.s[pi + 1];
-  p.n_in = opts.n_in ? opts.n_in : n;
-  p.n_out = opts.n_out ? opts.n_out : n;
-  if (p.first && opts.pre3) { p.use_pre = 1; for (int i = 0; i < 3; i++) p.pre[i] = opts.pre3[i]; }
-  if (p.last && opts.post3) { p.use_post = 1; for (int i = 0; i < 3; i++) p.post[i] = opts.post3[i]; }
-  p.b_addr = p.b;
-  // columns per tile: as many as fit, bounded by what the direction offers on this device
-  uint32_t avail = p.last ? (p.a ? p.s1 : 0) : p.b;
-  if (sh.mode == 1) { avail = p.b - sh.g_log; p.b_addr = p.b - sh.g_log; p.lo_base = (uint64_t)sh.q << p.b_addr; }
-  if (sh.mode == 2 && p.last) avail = p.s1 - sh.g_log;
-  const uint32_t tile_log = tile_elems_log(k);
-  uint32_t logc = tile_log > p.s ? tile_log - p.s : 0;
-  if (logc > avail) logc = avail;
-  if (logc > 5) logc = 5;
-  p.logc = logc;
-  uint64_t tiles = (n >> (p.s + logc)) >> sh.g_log;   // this device's tiles
-  if (sh.mode == 2) {
-    p.tile_base = tiles * sh.q;
-    if (p.last) { p.out_local = 1; p.out_cols_log = p.s1 - sh.g_log; p.i1_base = sh.q << (p.s1 - sh.g_log); }
-  }
-  p.src = src; p.dst = dst;
-  uint32_t S = 1u << p.s, C = 1u << logc;
-  uint32_t quads = (S * C) / 4; if (quads < 32) quads = 32;
-  static uint32_t max_threads = 0;
-  if (!max_threads) { const char* e = getenv("SPB_NTT_THREADS"); max_threads = e ? (uint32_t)atoi(e) : 256; if (max_threads < 32 || max_threads > 512) max_threads = 512; }
-  uint32_t threads = quads < max_threads ? quads : max_threads;
-  size_t smem = (size_t)8 * 4 * ((size_t)ntt_col_stride(S, C) * C + ntt_tw_words(S));
-  if (smem > 227 * 1024) return set_error(ctx, SPB_ERR_STATE, "ntt: tile needs %zu B of shared memory", smem);
+  NttPassParams p;
+  p.src = src; p.dst = dst; p.tw_lo = tb->tw_lo; p.tw_hi = tb->tw_hi; p.tw_full = tb->tw_full;
+  NttOptsHost oh; oh.n_in = opts.n_in; oh.n_out = opts.n_out; oh.pre3 = opts.pre3; oh.post3 = opts.post3;
+  NttLaunch L = ntt_fill_pass(p, plan, pi, k, h, oh, sh, tile_elems_log(k), max_threads_per_cta());
+  if (L.smem > 227 * 1024) return set_error(ctx, SPB_ERR_STATE, "ntt: tile needs %zu B of shared memory", L.smem);
   // persistent CTAs: as many as fit the SMs (shared memory bound), striding over the tiles
-  uint64_t per_sm = (227 * 1024) / (smem + 1024); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
-  uint64_t grid = (uint64_t)d.sm_count * per_sm; if (grid > tiles) grid = tiles;
+  uint64_t per_sm = (227 * 1024) / (L.smem + 1024); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+  uint64_t grid = (uint64_t)d.sm_count * per_sm; if (grid > L.tiles) grid = L.tiles;
   // Measured (profiles/r01_bench_progress.md): persistence pays up to 2^20 (launch + twiddle staging amortised); beyond
   // that co-resident persistent CTAs run their load/compute phases in lockstep and lose the overlap that
   // hardware-scheduled one-tile CTAs get for free, so large transforms launch one CTA per tile.
-  if (k > 20) grid = tiles;
-  p.ntiles = tiles;
-  ntt_pass_kernel<<<(unsigned)grid, threads, smem, d.stream>>>(p);
+  if (k > 20) grid = L.tiles;
+  ntt_pass_kernel<<<(unsigned)grid, L.threads, L.smem, d.stream>>>(p);
   SPB_CUDA(ctx, cudaGetLastError());
   ctx->n_kernel_launches++;
   return 0;

@@ -86,3 +86,78 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
 }
 void he_geometry(uint64_t n, int precomp, uint32_t* c, uint32_t* W) { MsmGeom g = msm_make_geometry(msm_choose_c(n, precomp != 0), precomp != 0, 0); *c = g.c; *W = g.W; }
 }
+
+// ---- NTT: the kernel's phases run serially (every phase for all tid), single- and multi-device plans -----------------
+#include "../../spectre_b200/csrc/ntt.cuh"
+namespace {
+void run_pass(const NttPassParams& p, const NttLaunch& L) {
+  const uint32_t S = 1u << p.s, C = 1u << p.logc, T = L.threads;
+  std::vector<uint32_t> smem(L.smem / 4 + 64, 0xdeadbeefu);
+  NttSmem sm; sm.bind(smem.data(), S, C);
+  for (uint32_t tid = 0; tid < T; tid++) ntt_phase_twiddles(p, sm, tid, T);
+  for (uint64_t tile_it = 0; tile_it < p.ntiles; tile_it++) {
+    NttTile t = ntt_tile_coords(p, tile_it + p.tile_base);
+    for (uint32_t tid = 0; tid < T; tid++) ntt_phase_load(p, sm, t, tid, T);
+    uint32_t m = S >> 1;
+    if (p.s & 1) { for (uint32_t tid = 0; tid < T; tid++) ntt_phase_radix2(p, sm, m, tid, T); m >>= 1; }
+    for (; m >= 2; m >>= 2) for (uint32_t tid = 0; tid < T; tid++) ntt_phase_radix4(p, sm, m, tid, T);
+    for (uint32_t tid = 0; tid < T; tid++) ntt_phase_store(p, sm, t, tid, T);
+  }
+}
+}  // namespace
+extern "C" {
+// in: n_in_copy elements (rest of the 2^k input is zero padding when n_in < n); out: n_out elements.
+// g_log = 0: the single-device plan; > 0: the six-step plan across 2^g_log emulated devices. use_full: full twiddle table.
+int he_ntt(const Fr* in, Fr* out, uint32_t k, const Fr* omega, uint32_t max_digit, uint32_t tile_log, uint32_t threads, uint32_t g_log,
+           uint64_t n_in, uint64_t n_out, const Fr* pre3, const Fr* post3, int use_full) {
+  const uint64_t n = 1ull << k;
+  NttPlan plan = ntt_make_plan(k, max_digit);
+  const uint32_t h = k - plan.s[0];
+  std::vector<Fr> tw_lo((size_t)1 << h), tw_hi((size_t)1 << (k - h)), tw_full;
+  for (size_t i = 0; i < tw_lo.size(); i++) tw_lo[i] = fp_pow_u64(*omega, i);
+  for (size_t i = 0; i < tw_hi.size(); i++) tw_hi[i] = fp_pow_u64(*omega, (uint64_t)i << h);
+  if (use_full) { tw_full.resize(n); for (uint64_t i = 0; i < n; i++) tw_full[i] = fp_pow_u64(*omega, i); }
+  NttOptsHost oh; oh.n_in = n_in; oh.n_out = n_out; oh.pre3 = pre3; oh.post3 = post3;
+  if (!n_in) n_in = n;
+  if (!n_out) n_out = n;
+  auto bind = [&](NttPassParams& p, const Fr* src, Fr* dst) { p.src = src; p.dst = dst; p.tw_lo = tw_lo.data(); p.tw_hi = tw_hi.data(); p.tw_full = use_full ? tw_full.data() : nullptr; };
+  if (g_log == 0) {
+    std::vector<Fr> buf(n), tmp(n);
+    for (uint64_t i = 0; i < n_in; i++) buf[i] = in[i];   // elements >= n_in are never read
+    for (uint32_t pi = 0; pi < plan.npass; pi++) {
+      NttPassParams p; bind(p, pi == 0 ? buf.data() : tmp.data(), pi == plan.npass - 1 ? buf.data() : tmp.data());
+      NttLaunch L = ntt_fill_pass(p, plan, pi, k, h, oh, NttShare(), tile_log, threads);
+      run_pass(p, L);
+    }
+    for (uint64_t i = 0; i < n_out; i++) out[i] = buf[i];
+    return (int)plan.npass;
+  }
+  if (plan.npass < 2 || plan.s[0] <= g_log || (k - plan.s[0]) <= g_log + 1) return -1;
+  const uint32_t G = 1u << g_log, s1 = plan.s[0], rest = k - s1;
+  const uint64_t n1 = 1ull << s1, lo_count = 1ull << rest, lo_loc = lo_count >> g_log, rows_loc = n1 >> g_log, per = n >> g_log;
+  const uint64_t rows_in = (n_in + lo_count - 1) / lo_count, rows_out = (n_out + n1 - 1) / n1;
+  std::vector<std::vector<Fr>> A(G, std::vector<Fr>(per));
+  std::vector<Fr> Bfull(n);   // device q's slice B[q] sits at its global position q*per
+  for (uint32_t q = 0; q < G; q++) {
+    for (uint64_t r = 0; r < rows_in; r++) for (uint64_t c = 0; c < lo_loc; c++) { uint64_t gi = r * lo_count + q * lo_loc + c; if (gi < n_in) A[q][r * lo_loc + c] = in[gi]; }
+    NttPassParams p; bind(p, A[q].data(), A[q].data());
+    NttShare sh; sh.g_log = g_log; sh.q = q; sh.mode = 1;
+    NttLaunch L = ntt_fill_pass(p, plan, 0, k, h, oh, sh, tile_log, threads);
+    run_pass(p, L);
+  }
+  for (uint32_t qd = 0; qd < G; qd++)   // what ntt_gather_kernel does
+    for (uint64_t row = 0; row < rows_loc; row++) for (uint32_t qs = 0; qs < G; qs++) for (uint64_t c = 0; c < lo_loc; c++)
+      Bfull[qd * per + row * lo_count + qs * lo_loc + c] = A[qs][(qd * rows_loc + row) * lo_loc + c];
+  for (uint32_t q = 0; q < G; q++) {
+    NttShare sh; sh.g_log = g_log; sh.q = q; sh.mode = 2;
+    for (uint32_t pi = 1; pi < plan.npass; pi++) {
+      bool last = pi == plan.npass - 1;
+      NttPassParams p; bind(p, Bfull.data(), last ? A[q].data() : Bfull.data());
+      NttLaunch L = ntt_fill_pass(p, plan, pi, k, h, oh, sh, tile_log, threads);
+      run_pass(p, L);
+    }
+    for (uint64_t r = 0; r < rows_out; r++) for (uint64_t c = 0; c < rows_loc; c++) { uint64_t o = r * n1 + q * rows_loc + c; if (o < n_out) out[o] = A[q][r * rows_loc + c]; }
+  }
+  return (int)plan.npass;
+}
+}
