@@ -211,6 +211,43 @@ int spb_lookup_constraints_dev(spb_ctx* ctx, spb_fr* d_values, uint64_t size, in
  * Returns SPB_ERR_CONSTRAINT when an input value does not occur in the table. */
 int spb_permute_expression_pair_dev(spb_ctx* ctx, const spb_fr* d_input, const spb_fr* d_table, size_t usable, spb_fr* d_permuted_input, spb_fr* d_permuted_table);
 
+/* ---- argument provers, device resident ([UPSTREAM] halo2_proofs/src/plonk/{permutation,lookup}/prover.rs) ----------- */
+/* permutation::Argument::commit for ONE set (a chunk of <= degree-2 columns, first_col = its index of first column in
+ * the permutation): over all n = 2^k rows
+ *   d_z[0] = *last_z,  d_z[i+1] = d_z[i] * prod_c (v_c[i] + beta*delta^(first_col+c)*omega^i + gamma) / prod_c (v_c[i] + beta*sigma_c[i] + gamma)
+ * then the last n_blinds entries are overwritten with `blinds` (the caller's RNG draws, in order) and
+ * *last_z <- d_z[n - n_blinds - 1]. d_values / d_sigma: HOST arrays of n_cols device pointers (Lagrange basis). */
+int spb_permutation_product_dev(spb_ctx* ctx, uint32_t k, const spb_fr* const* d_values, const spb_fr* const* d_sigma, uint32_t n_cols, uint32_t first_col,
+                                const spb_fr* beta, const spb_fr* gamma, const spb_fr* blinds, uint32_t n_blinds, spb_fr* last_z, spb_fr* d_z);
+/* lookup Permuted::commit_product: d_z[0] = 1, d_z[i+1] = d_z[i] * (a[i]+beta)(s[i]+gamma) / ((a'[i]+beta)(s'[i]+gamma)),
+ * last n_blinds entries <- blinds. a, s = compressed input / table; a', s' = their permuted forms (all n rows). */
+int spb_lookup_product_dev(spb_ctx* ctx, size_t n, const spb_fr* d_compressed_input, const spb_fr* d_compressed_table, const spb_fr* d_permuted_input,
+                           const spb_fr* d_permuted_table, const spb_fr* beta, const spb_fr* gamma, const spb_fr* blinds, uint32_t n_blinds, spb_fr* d_z);
+/* d_out[i] = sum_p weights[p] * d_polys[p][i] (weights: host array). */
+int spb_weighted_sum_dev(spb_ctx* ctx, const spb_fr* const* d_polys, const spb_fr* weights, size_t count, spb_fr* d_out, size_t n);
+
+/* ---- SHPLONK multi-open prover ([UPSTREAM] halo2_proofs/src/poly/kzg/multiopen/shplonk/prover.rs) ------------------- */
+/* One rotation set as construct_intermediate_sets (shplonk.rs) yields it: the polynomials opened at exactly `points`,
+ * in first-queried order, with evals[j * n_points + p] = poly_j(points[p]). Polynomials are device pointers in
+ * coefficient form, n coefficients each. */
+typedef struct {
+  const spb_fr* points;
+  uint32_t n_points;             /* 1..8 */
+  const spb_fr* const* d_polys;  /* host array of n_polys device pointers */
+  uint32_t n_polys;
+  const spb_fr* evals;
+} spb_rotation_set;
+typedef struct spb_shplonk spb_shplonk;
+/* After squeezing y and v: h(X) = sum_i v^(s-1-i) * [sum_j y^(m_i-1-j) (P_ij(X) - R_ij(X))] / Z_{S_i}(X), committed with
+ * `g`; the handle keeps h(X) on the device until the second call. The caller's polynomials must stay alive and
+ * unchanged until then. */
+int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_rotation_set* sets, uint32_t n_sets, const spb_fr* y, const spb_fr* v,
+                          spb_g1* h_commitment, spb_shplonk** out);
+/* After squeezing u: L(X) = sum_i v^(s-1-i) Z_{T\S_i}(u) sum_j y^(m_i-1-j) (P_ij(X) - R_ij(u)) - Z_T(u) h(X); commits
+ * L(X) / (X - u) / Z_{T\S_0}(u). Consumes the handle (also on error). */
+int spb_shplonk_finish_dev(spb_ctx* ctx, spb_shplonk* s, const spb_fr* u, spb_g1* commitment);
+void spb_shplonk_abort(spb_ctx* ctx, spb_shplonk* s);
+
 /* ---- test / bench utilities -------------------------------------------------------------------------------- */
 /* out[i] = scalars[i] * G1 (affine), computed on the device */
 int spb_g1_fixed_base_mul(spb_ctx* ctx, const spb_fr* scalars, size_t n, spb_g1_affine* out);

@@ -912,3 +912,171 @@ int orc_permute_expression_pair(const fe* input, const fe* table, size_t usable,
   free(in); free(tb); free(used); free(repeated);
   return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Argument provers: [UPSTREAM] halo2_proofs/src/plonk/permutation/prover.rs (Argument::commit),
+ * src/plonk/lookup/prover.rs (Permuted::commit_product) -- SURVEY.md 8a row a8. Restated in the
+ * upstream order: denominators over all rows, batch inversion, numerators, running product, blinding
+ * tail. "parity unpinned" (no reference-owned vector; GPU vs this restatement).
+ * ---------------------------------------------------------------------------------------------- */
+static fe fr_omega_k(uint32_t k) { fe w = FR_ROOT_OF_UNITY; for (uint32_t i = k; i < 28; i++) w = f_sqr(&FR, w); return w; }
+
+/* One permutation set: columns values[c], permuted columns sigma[c] (Lagrange basis, n = 2^k rows). deltaomega starts at
+ * delta^first_col; z[0] = *last_z; the last n_blinds rows are overwritten with blinds; *last_z <- z[n - n_blinds - 1]. */
+void orc_permutation_product(uint32_t k, const fe* const* values, const fe* const* sigma, uint32_t n_cols, uint32_t first_col,
+                             const fe* beta, const fe* gamma, const fe* blinds, uint32_t n_blinds, fe* last_z, fe* z) {
+  size_t n = (size_t)1 << k;
+  fe* modified = (fe*)malloc(n * sizeof(fe));
+  for (size_t i = 0; i < n; i++) modified[i] = FR.r;
+  for (uint32_t c = 0; c < n_cols; c++)
+    for (size_t i = 0; i < n; i++) modified[i] = f_mul(&FR, modified[i], f_add(&FR, f_add(&FR, f_mul(&FR, *beta, sigma[c][i]), *gamma), values[c][i]));
+  orc_batch_invert(modified, n);
+  fe delta; orc_fr_delta(&delta);
+  fe omega = fr_omega_k(k);
+  fe deltaomega = FR.r;
+  for (uint32_t c = 0; c < first_col; c++) deltaomega = f_mul(&FR, deltaomega, delta);
+  for (uint32_t c = 0; c < n_cols; c++) {
+    fe beta_term = deltaomega;   /* delta^j * omega^i */
+    for (size_t i = 0; i < n; i++) {
+      modified[i] = f_mul(&FR, modified[i], f_add(&FR, f_add(&FR, f_mul(&FR, beta_term, *beta), *gamma), values[c][i]));
+      beta_term = f_mul(&FR, beta_term, omega);
+    }
+    deltaomega = f_mul(&FR, deltaomega, delta);
+  }
+  z[0] = *last_z;
+  for (size_t row = 1; row < n; row++) z[row] = f_mul(&FR, z[row - 1], modified[row - 1]);
+  for (uint32_t b = 0; b < n_blinds; b++) z[n - n_blinds + b] = blinds[b];
+  *last_z = z[n - n_blinds - 1];
+  free(modified);
+}
+
+void orc_lookup_product(size_t n, const fe* compressed_input, const fe* compressed_table, const fe* permuted_input, const fe* permuted_table,
+                        const fe* beta, const fe* gamma, const fe* blinds, uint32_t n_blinds, fe* z) {
+  fe* prod = (fe*)malloc(n * sizeof(fe));
+  for (size_t i = 0; i < n; i++) prod[i] = f_mul(&FR, f_add(&FR, permuted_input[i], *beta), f_add(&FR, permuted_table[i], *gamma));
+  orc_batch_invert(prod, n);
+  for (size_t i = 0; i < n; i++)
+    prod[i] = f_mul(&FR, prod[i], f_mul(&FR, f_add(&FR, compressed_input[i], *beta), f_add(&FR, compressed_table[i], *gamma)));
+  /* z = once(1).chain(prod).scan(1, *).take(n - blinding_factors).chain(blinds) */
+  fe state = FR.r;
+  z[0] = state;
+  for (size_t i = 1; i < n - n_blinds; i++) { state = f_mul(&FR, state, prod[i - 1]); z[i] = state; }
+  for (uint32_t b = 0; b < n_blinds; b++) z[n - n_blinds + b] = blinds[b];
+  free(prod);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * SHPLONK prover: [UPSTREAM] halo2_proofs/src/poly/kzg/multiopen/shplonk/prover.rs
+ * (ProverSHPLONK::create_proof, quotient_contribution, linearisation_contribution)
+ * and arithmetic.rs lagrange_interpolate / evaluate_vanishing_polynomial. Polynomials are whole
+ * coefficient vectors handled one after the other, as upstream does. "parity unpinned".
+ * The rotation sets come from construct_intermediate_sets (restated in Python next to the transcript).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { const fe* points; uint32_t n_points; const fe* const* polys; uint32_t n_polys; const fe* evals; } orc_rotation_set;
+
+static void lagrange_interpolate(const fe* points, const fe* evals, uint32_t m, fe* out /* m */) {
+  if (m == 1) { out[0] = evals[0]; return; }
+  fe denoms[8][8];
+  for (uint32_t j = 0; j < m; j++) { uint32_t t = 0; for (uint32_t k2 = 0; k2 < m; k2++) if (k2 != j) denoms[j][t++] = f_inv(&FR, f_sub(&FR, points[j], points[k2])); }
+  for (uint32_t i = 0; i < m; i++) memset(&out[i], 0, sizeof(fe));
+  for (uint32_t j = 0; j < m; j++) {
+    fe tmp[9], product[9]; uint32_t tlen = 1; tmp[0] = FR.r;
+    uint32_t t = 0;
+    for (uint32_t k2 = 0; k2 < m; k2++) {
+      if (k2 == j) continue;
+      fe denom = denoms[j][t++];
+      /* product = tmp * (X - x_k) * denom */
+      for (uint32_t a = 0; a <= tlen; a++) memset(&product[a], 0, sizeof(fe));
+      fe c0 = f_mul(&FR, f_neg(&FR, denom), points[k2]);
+      for (uint32_t a = 0; a < tlen; a++) {
+        product[a] = f_add(&FR, product[a], f_mul(&FR, tmp[a], c0));
+        product[a + 1] = f_add(&FR, product[a + 1], f_mul(&FR, tmp[a], denom));
+      }
+      tlen++;
+      for (uint32_t a = 0; a < tlen; a++) tmp[a] = product[a];
+    }
+    for (uint32_t a = 0; a < m; a++) out[a] = f_add(&FR, out[a], f_mul(&FR, tmp[a], evals[j]));
+  }
+}
+static fe evaluate_vanishing_polynomial(const fe* roots, uint32_t m, fe z) {
+  fe acc = FR.r;
+  for (uint32_t i = 0; i < m; i++) acc = f_mul(&FR, acc, f_sub(&FR, z, roots[i]));
+  return acc;
+}
+/* poly <- poly / prod (X - root): successive kate divisions; returns the new length */
+static size_t div_by_vanishing(fe* poly, size_t len, const fe* roots, uint32_t m, fe* scratch) {
+  for (uint32_t i = 0; i < m; i++) { orc_kate_division(scratch, poly, len, &roots[i]); len--; memcpy(poly, scratch, len * sizeof(fe)); }
+  return len;
+}
+static int fe_same(const fe* a, const fe* b) { return memcmp(a, b, sizeof(fe)) == 0; }
+
+/* h_x (n coefficients) = fold over sets with v of [ fold over commitments with y of (P - R) ] / Z_set */
+void orc_shplonk_quotient(size_t n, const orc_rotation_set* sets, uint32_t n_sets, const fe* y, const fe* v, fe* h_x) {
+  fe* n_x = (fe*)malloc(n * sizeof(fe)); fe* scratch = (fe*)malloc(n * sizeof(fe));
+  memset(h_x, 0, n * sizeof(fe));
+  for (uint32_t s = 0; s < n_sets; s++) {
+    const orc_rotation_set* rs = &sets[s];
+    memset(n_x, 0, n * sizeof(fe));
+    for (uint32_t j = 0; j < rs->n_polys; j++) {
+      fe r[8]; lagrange_interpolate(rs->points, rs->evals + (size_t)j * rs->n_points, rs->n_points, r);
+      for (size_t i = 0; i < n; i++) {          /* acc * y + (poly - low_degree_equivalent) */
+        fe q = rs->polys[j][i];
+        if (i < rs->n_points) q = f_sub(&FR, q, r[i]);
+        n_x[i] = f_add(&FR, f_mul(&FR, n_x[i], *y), q);
+      }
+    }
+    size_t len = div_by_vanishing(n_x, n, rs->points, rs->n_points, scratch);
+    for (size_t i = len; i < n; i++) memset(&n_x[i], 0, sizeof(fe));   /* poly.resize(n, 0) */
+    for (size_t i = 0; i < n; i++) h_x[i] = f_add(&FR, f_mul(&FR, h_x[i], *v), n_x[i]);
+  }
+  free(n_x); free(scratch);
+}
+/* final (n - 1 coefficients): ((fold_v [ z_i * fold_y (P - R(u)) ]) - zt_eval * h_x) / (X - u) / z_0 */
+int orc_shplonk_linearisation(size_t n, const orc_rotation_set* sets, uint32_t n_sets, const fe* y, const fe* v, const fe* u, const fe* h_x, fe* out) {
+  fe super[64]; uint32_t n_super = 0;
+  for (uint32_t s = 0; s < n_sets; s++) for (uint32_t p = 0; p < sets[s].n_points; p++) {
+    int seen = 0;
+    for (uint32_t t = 0; t < n_super; t++) if (fe_same(&super[t], &sets[s].points[p])) seen = 1;
+    if (!seen) { if (n_super == 64) return -1; super[n_super++] = sets[s].points[p]; }
+  }
+  fe* l_x = (fe*)calloc(n, sizeof(fe)); fe* inner = (fe*)malloc(n * sizeof(fe));
+  fe z_0_diff; memset(&z_0_diff, 0, sizeof z_0_diff);
+  for (uint32_t s = 0; s < n_sets; s++) {
+    const orc_rotation_set* rs = &sets[s];
+    fe diffs[64]; uint32_t nd = 0;
+    for (uint32_t t = 0; t < n_super; t++) { int in_set = 0; for (uint32_t p = 0; p < rs->n_points; p++) if (fe_same(&super[t], &rs->points[p])) in_set = 1; if (!in_set) diffs[nd++] = super[t]; }
+    fe z_i = evaluate_vanishing_polynomial(diffs, nd, *u);
+    if (s == 0) z_0_diff = z_i;
+    memset(inner, 0, n * sizeof(fe));
+    for (uint32_t j = 0; j < rs->n_polys; j++) {
+      fe r[8]; lagrange_interpolate(rs->points, rs->evals + (size_t)j * rs->n_points, rs->n_points, r);
+      fe r_eval; orc_eval_polynomial(&r_eval, r, rs->n_points, u);
+      for (size_t i = 0; i < n; i++) {
+        fe q = rs->polys[j][i];
+        if (i == 0) q = f_sub(&FR, q, r_eval);
+        inner[i] = f_add(&FR, f_mul(&FR, inner[i], *y), q);
+      }
+    }
+    for (size_t i = 0; i < n; i++) l_x[i] = f_add(&FR, f_mul(&FR, l_x[i], *v), f_mul(&FR, inner[i], z_i));
+  }
+  fe zt_eval = evaluate_vanishing_polynomial(super, n_super, *u);
+  for (size_t i = 0; i < n; i++) l_x[i] = f_sub(&FR, l_x[i], f_mul(&FR, h_x[i], zt_eval));
+  fe must_be_zero; orc_eval_polynomial(&must_be_zero, l_x, n, u);
+  int rc = f_is_zero(must_be_zero) ? 0 : -2;      /* upstream debug_assert */
+  orc_kate_division(out, l_x, n, u);
+  fe z_0_diff_inv = f_inv(&FR, z_0_diff);
+  for (size_t i = 0; i + 1 < n; i++) out[i] = f_mul(&FR, out[i], z_0_diff_inv);
+  free(l_x); free(inner);
+  return rc;
+}
+
+/* plain vector helpers for the proof driver's CPU binding (tests/plonk_oracle_engine.py) */
+void orc_vec_scale(fe* a, const fe* alpha, size_t n) { for (size_t i = 0; i < n; i++) a[i] = f_mul(&FR, a[i], *alpha); }
+/* out[i] = sum_p y^p polys[p][i]: vanishing::evaluate's fold of the h pieces with x^n (rev().fold(acc * xn + piece)) */
+void orc_vec_fold(const fe* const* polys, size_t count, const fe* y, fe* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    fe acc; memset(&acc, 0, sizeof acc);
+    for (size_t p = count; p-- > 0;) acc = f_add(&FR, f_mul(&FR, acc, *y), polys[p][i]);
+    out[i] = acc;
+  }
+}

@@ -340,3 +340,71 @@ def permute_expression_pair(input_expr, table_expr):
     if rc != 0:
         raise ValueError("permute_expression_pair: ConstraintSystemFailure (%d)" % rc)
     return pi, pt
+
+
+# ---- argument provers (permutation / lookup grand products, SHPLONK) -----------------------------------------
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def permutation_product(k, values, sigma, first_col, beta, gamma, blinds, last_z):
+    """One permutation set -> (z over all 2^k rows, new last_z)."""
+    n = 1 << k
+    pv, kv = _ptr_array(values); ps, ks = _ptr_array(sigma)
+    blinds = _c(blinds).reshape(-1, 4); z = np.empty((n, 4), dtype=np.uint64); lz = _c(last_z).copy()
+    lib().orc_permutation_product(ctypes.c_uint32(k), pv, ps, ctypes.c_uint32(len(values)), ctypes.c_uint32(first_col), _p(_c(beta)), _p(_c(gamma)),
+                                  _p(blinds), ctypes.c_uint32(blinds.shape[0]), _p(lz), _p(z))
+    return z, lz
+
+
+def lookup_product(compressed_input, compressed_table, permuted_input, permuted_table, beta, gamma, blinds):
+    a = [_c(x) for x in (compressed_input, compressed_table, permuted_input, permuted_table)]
+    n = a[0].shape[0]
+    blinds = _c(blinds).reshape(-1, 4); z = np.empty((n, 4), dtype=np.uint64)
+    lib().orc_lookup_product(ctypes.c_size_t(n), *[_p(x) for x in a], _p(_c(beta)), _p(_c(gamma)), _p(blinds), ctypes.c_uint32(blinds.shape[0]), _p(z))
+    return z
+
+
+class _RotationSet(ctypes.Structure):
+    _fields_ = [("points", ctypes.c_void_p), ("n_points", ctypes.c_uint32), ("polys", ctypes.c_void_p), ("n_polys", ctypes.c_uint32), ("evals", ctypes.c_void_p)]
+
+
+def _rotation_sets(sets):
+    """sets: list of (points (m,4), [poly arrays], evals (n_polys, m, 4)) -> ctypes array + keep-alive list"""
+    keep = []
+    arr = (_RotationSet * len(sets))()
+    for i, (points, polys, evals) in enumerate(sets):
+        points = _c(points).reshape(-1, 4); evals = _c(evals).reshape(len(polys), points.shape[0], 4)
+        pp, kp = _ptr_array(polys)
+        keep += [points, evals, pp, kp]
+        arr[i] = _RotationSet(points.ctypes.data, points.shape[0], ctypes.cast(pp, ctypes.c_void_p).value, len(polys), evals.ctypes.data)
+    return arr, keep
+
+
+def shplonk_quotient(n, sets, y, v):
+    arr, keep = _rotation_sets(sets)
+    h = np.empty((n, 4), dtype=np.uint64)
+    lib().orc_shplonk_quotient(ctypes.c_size_t(n), arr, ctypes.c_uint32(len(sets)), _p(_c(y)), _p(_c(v)), _p(h))
+    return h
+
+
+def shplonk_linearisation(n, sets, y, v, u, h_x):
+    arr, keep = _rotation_sets(sets)
+    out = np.empty((n - 1, 4), dtype=np.uint64)
+    rc = lib().orc_shplonk_linearisation(ctypes.c_size_t(n), arr, ctypes.c_uint32(len(sets)), _p(_c(y)), _p(_c(v)), _p(_c(u)), _p(_c(h_x)), _p(out))
+    if rc != 0:
+        raise ValueError("shplonk: linearisation polynomial does not vanish at u (%d): evaluations inconsistent with the polynomials" % rc)
+    return out
+
+
+def vec_scale(a, alpha):
+    a = _c(a).copy()
+    lib().orc_vec_scale(_p(a), _p(_c(alpha)), ctypes.c_size_t(a.shape[0]))
+    return a
+
+
+def vec_fold(polys, y):
+    pp, keep = _ptr_array(polys)
+    out = np.empty_like(keep[0])
+    lib().orc_vec_fold(pp, ctypes.c_size_t(len(polys)), _p(_c(y)), _p(out), ctypes.c_size_t(out.shape[0]))
+    return out

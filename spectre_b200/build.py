@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libspectre_b200.so")
 OBJDIR = os.path.join(HERE, "_obj")
-SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "poly.cu", "quotient.cu", "lookup.cu"]
+SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "poly.cu", "quotient.cu", "lookup.cu", "plonk.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-cudart", "static"]

@@ -85,6 +85,12 @@ int ntt_device(spb_ctx* ctx, DeviceState& d, const Fr* d_src, Fr* d_dst, uint32_
 bool ntt_multi_applicable(spb_ctx* ctx, uint32_t log_n);
 int ntt_multi_host(spb_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, const Fr& omega, const NttOpts& opts, float* ev_ms);
 
+// ---- poly.cu: device-resident cores (pointers on device d, work enqueued on d.stream, no synchronisation unless noted) ----
+int dev_grand_product(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, Fr* dz, const Fr& init);  // z[i] = init * prod_{j<i} a[j]
+int dev_kate_division(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, const Fr& b, Fr* dq);
+int dev_batch_invert(spb_ctx* ctx, DeviceState& d, Fr* da, size_t n);
+int dev_eval_polynomial(spb_ctx* ctx, DeviceState& d, const Fr* dp, size_t n, const Fr& x, Fr* out_host);  // synchronises
+
 // ---- host field helpers (64-bit path) ----
 inline Fr fr_from_u64(uint64_t v) {
   Fr a = fp_zero<FrParams>(); a.l[0] = (uint32_t)v; a.l[1] = (uint32_t)(v >> 32);

@@ -40,13 +40,13 @@ __global__ void chunk_product_kernel(const Fr* a, uint64_t n, Fr* partial) {
   for (uint64_t i = lo; i < hi; i++) p = fp_mul(p, ntt_ldg(a + i));
   partial[c] = p;
 }
-// z[i] = carry[c] * prod_{lo <= j < i} a[j]
-__global__ void chunk_product_fix_kernel(const Fr* a, uint64_t n, const Fr* carry, Fr* z) {
+// z[i] = init * carry[c] * prod_{lo <= j < i} a[j]
+__global__ void chunk_product_fix_kernel(const Fr* a, uint64_t n, const Fr* carry, Fr init, Fr* z) {
   uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   uint64_t lo = c * kScanChunk;
   if (lo >= n) return;
   uint64_t hi = lo + kScanChunk < n ? lo + kScanChunk : n;
-  Fr p = carry[c];
+  Fr p = fp_mul(carry[c], init);
   for (uint64_t i = lo; i < hi; i++) { Fr v = ntt_ldg(a + i); ntt_stg(z + i, p); p = fp_mul(p, v); }
 }
 
@@ -178,18 +178,18 @@ __global__ void lincomb_kernel(const Fr* const* polys, uint32_t count, Fr y, Fr*
   ntt_stg(out + i, acc);
 }
 
-namespace {
+namespace spb {
 
-inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 // ---- device-resident cores (all pointers on device d, work enqueued on d.stream; no final synchronisation unless noted)
-int dev_grand_product(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, Fr* dz) {
+int dev_grand_product(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, Fr* dz, const Fr& init) {
   size_t m = (n + kScanChunk - 1) / kScanChunk;
   Fr* dp = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32);
   if (!dp) return SPB_ERR_OOM;
   chunk_product_kernel<<<nblk(m, 128), 128, 0, d.stream>>>(da, n, dp);
   carry_product_kernel<<<1, 1024, 0, d.stream>>>(dp, m);
-  chunk_product_fix_kernel<<<nblk(m, 128), 128, 0, d.stream>>>(da, n, dp, dz);
+  chunk_product_fix_kernel<<<nblk(m, 128), 128, 0, d.stream>>>(da, n, dp, init, dz);
   SPB_CUDA(ctx, cudaGetLastError());
   ctx->n_kernel_launches += 3;
   return 0;
@@ -238,7 +238,7 @@ int dev_eval_polynomial(spb_ctx* ctx, DeviceState& d, const Fr* dp, size_t n, co
   return 0;
 }
 
-}  // namespace
+}  // namespace spb
 
 extern "C" {
 
@@ -333,7 +333,7 @@ int spb_grand_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* d_z
   if (!ctx || !d_a || !d_z) return SPB_ERR_ARG;
   if (!n) return 0;
   SPB_ENTER(ctx);
-  SPB_TRY(dev_grand_product(ctx, d, (const Fr*)d_a, n, (Fr*)d_z));
+  SPB_TRY(dev_grand_product(ctx, d, (const Fr*)d_a, n, (Fr*)d_z, fp_one<FrParams>()));
   SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
   return 0;
 }
@@ -344,7 +344,7 @@ int spb_grand_product(spb_ctx* ctx, const spb_fr* a, size_t n, spb_fr* z) {
   Fr* da = (Fr*)slot(ctx, d, "poly_a", n * 32); Fr* dz = (Fr*)slot(ctx, d, "poly_b", n * 32);
   if (!da || !dz) return SPB_ERR_OOM;
   SPB_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, d.stream));
-  SPB_TRY(dev_grand_product(ctx, d, da, n, dz));
+  SPB_TRY(dev_grand_product(ctx, d, da, n, dz, fp_one<FrParams>()));
   SPB_CUDA(ctx, cudaMemcpyAsync(z, dz, n * 32, cudaMemcpyDeviceToHost, d.stream));
   SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
   return 0;

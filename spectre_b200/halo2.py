@@ -248,6 +248,50 @@ class Backend:
                                                        _p(d_permuted_table), _p(d_table_value), _p(d_l0), _p(d_l_last), _p(d_l_active), _p(_fr_array(beta, 1)),
                                                        _p(_fr_array(gamma, 1)), _p(_fr_array(y, 1))), "spb_lookup_constraints_dev")
 
+    # ---- argument provers (plonk::{permutation,lookup}::prover, multiopen::shplonk) -----------------------
+    def permutation_product_dev(self, k, d_values, d_sigma, first_col, beta, gamma, blinds, last_z, d_z):
+        """permutation::Argument::commit for one set; returns the new last_z. blinds: (blinding_factors, 4) RNG draws."""
+        mk = lambda ps: (ctypes.c_void_p * max(1, len(ps)))(*ps)
+        blinds = np.ascontiguousarray(blinds, dtype=np.uint64).reshape(-1, 4)
+        lz = _fr_array(last_z, 1).copy()
+        self.check(self.lib.spb_permutation_product_dev(self.ctx, ctypes.c_uint32(k), mk(d_values), mk(d_sigma), ctypes.c_uint32(len(d_values)), ctypes.c_uint32(first_col),
+                                                        _p(_fr_array(beta, 1)), _p(_fr_array(gamma, 1)), _p(blinds), ctypes.c_uint32(blinds.shape[0]), _p(lz), _p(d_z)),
+                   "spb_permutation_product_dev")
+        return lz.reshape(4)
+
+    def lookup_product_dev(self, n, d_compressed_input, d_compressed_table, d_permuted_input, d_permuted_table, beta, gamma, blinds, d_z):
+        blinds = np.ascontiguousarray(blinds, dtype=np.uint64).reshape(-1, 4)
+        self.check(self.lib.spb_lookup_product_dev(self.ctx, ctypes.c_size_t(n), _p(d_compressed_input), _p(d_compressed_table), _p(d_permuted_input), _p(d_permuted_table),
+                                                   _p(_fr_array(beta, 1)), _p(_fr_array(gamma, 1)), _p(blinds), ctypes.c_uint32(blinds.shape[0]), _p(d_z)), "spb_lookup_product_dev")
+
+    def weighted_sum_dev(self, d_ptrs, weights, d_out, n):
+        ptrs = (ctypes.c_void_p * len(d_ptrs))(*d_ptrs)
+        w = np.ascontiguousarray(weights, dtype=np.uint64).reshape(len(d_ptrs), 4)
+        self.check(self.lib.spb_weighted_sum_dev(self.ctx, ptrs, _p(w), ctypes.c_size_t(len(d_ptrs)), _p(d_out), ctypes.c_size_t(n)), "spb_weighted_sum_dev")
+
+    def shplonk_begin_dev(self, params, n, sets, y, v):
+        """ProverSHPLONK::create_proof up to the first commitment. sets: list of (points (m,4), [device addresses], evals (n_polys, m, 4)).
+        Returns (h commitment, handle for shplonk_finish_dev)."""
+        class _Set(ctypes.Structure):
+            _fields_ = [("points", ctypes.c_void_p), ("n_points", ctypes.c_uint32), ("d_polys", ctypes.c_void_p), ("n_polys", ctypes.c_uint32), ("evals", ctypes.c_void_p)]
+        keep = []
+        arr = (_Set * len(sets))()
+        for i, (points, d_polys, evals) in enumerate(sets):
+            points = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 4)
+            evals = np.ascontiguousarray(evals, dtype=np.uint64).reshape(len(d_polys), points.shape[0], 4)
+            ptrs = (ctypes.c_void_p * len(d_polys))(*d_polys)
+            keep += [points, evals, ptrs]
+            arr[i] = _Set(points.ctypes.data, points.shape[0], ctypes.cast(ptrs, ctypes.c_void_p).value, len(d_polys), evals.ctypes.data)
+        out = np.empty(12, dtype=np.uint64); h = ctypes.c_void_p()
+        self.check(self.lib.spb_shplonk_begin_dev(self.ctx, params.h, ctypes.c_size_t(n), arr, ctypes.c_uint32(len(sets)), _p(_fr_array(y, 1)), _p(_fr_array(v, 1)),
+                                                  _p(out), ctypes.byref(h)), "spb_shplonk_begin_dev")
+        return out, h
+
+    def shplonk_finish_dev(self, handle, u):
+        out = np.empty(12, dtype=np.uint64)
+        self.check(self.lib.spb_shplonk_finish_dev(self.ctx, handle, _p(_fr_array(u, 1)), _p(out)), "spb_shplonk_finish_dev")
+        return out
+
     def permute_expression_pair_dev(self, d_input, d_table, usable, d_permuted_input, d_permuted_table):
         """lookup::prover::permute_expression_pair on device buffers; raises like Error::ConstraintSystemFailure."""
         self.check(self.lib.spb_permute_expression_pair_dev(self.ctx, _p(d_input), _p(d_table), ctypes.c_size_t(usable), _p(d_permuted_input),

@@ -1,0 +1,149 @@
+"""GPU parity of the argument provers (permutation / lookup grand products, weighted sums, the SHPLONK opener) through
+the C ABI against the oracle's restatement of the upstream prover code. Parity unpinned vs the Rust reference (no
+reference-owned vector for these rows); the SHPLONK outputs are additionally checked to be valid openings."""
+import numpy as np
+import pytest
+
+from tests import pyref
+from tests.gpu_common import be  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(torch, arr):
+    return torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).cuda()
+
+
+def _host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("k,n_cols,chunk,n_blinds", [(4, 1, 1, 0), (8, 5, 3, 5), (12, 7, 2, 6), (14, 3, 3, 1)])
+def test_permutation_product_sets_chain(be, orc, k, n_cols, chunk, n_blinds):
+    import torch
+    n = 1 << k
+    values = [orc.fr_random_chacha(n, 100 + c) for c in range(n_cols)]
+    sigma = [orc.fr_random_chacha(n, 200 + c) for c in range(n_cols)]
+    values[0][3] = 0; sigma[0][5] = 0
+    beta, gamma = orc.fr_random_chacha(2, 300 + k)
+    dv, ds = [_dev(torch, a) for a in values], [_dev(torch, a) for a in sigma]
+    dz = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    last_o = last_g = orc.fr([1])[0]
+    for s, lo in enumerate(range(0, n_cols, chunk)):
+        hi = min(lo + chunk, n_cols)
+        blinds = orc.fr_random_chacha(n_blinds, 400 + s).reshape(-1, 4)
+        z_want, last_o = orc.permutation_product(k, values[lo:hi], sigma[lo:hi], lo, beta, gamma, blinds, last_o)
+        last_g = be.permutation_product_dev(k, [t.data_ptr() for t in dv[lo:hi]], [t.data_ptr() for t in ds[lo:hi]], lo, beta, gamma, blinds, last_g, dz.data_ptr())
+        assert np.array_equal(_host(dz), z_want)
+        assert np.array_equal(last_g, last_o.reshape(4))
+
+
+def test_permutation_product_of_a_real_permutation_closes(be, orc):
+    """with sigma encoding an actual permutation of equal cells the product over the usable rows returns to 1"""
+    import torch
+    k, n_cols = 8, 3
+    n = 1 << k
+    R = pyref.R_MOD
+    delta = orc.fr_ints(orc.fr_delta().reshape(1, 4))[0]
+    omega = pyref.omega(k)
+    ident = [[pow(delta, c, R) * pow(omega, i, R) % R for i in range(n)] for c in range(n_cols)]
+    vals = [[(7 * i + c) % 50 for i in range(n)] for c in range(n_cols)]           # many equal cells
+    cells = {}
+    for c in range(n_cols):
+        for i in range(n):
+            cells.setdefault(vals[c][i], []).append((c, i))
+    sig = [[0] * n for _ in range(n_cols)]
+    for group in cells.values():                                                    # one cycle per value class
+        for a, b in zip(group, group[1:] + group[:1]):
+            sig[a[0]][a[1]] = ident[b[0]][b[1]]
+    values = [orc.fr(v) for v in vals]; sigma = [orc.fr(s) for s in sig]
+    beta, gamma = orc.fr_random_chacha(2, 77)
+    dv, ds = [_dev(torch, a) for a in values], [_dev(torch, a) for a in sigma]
+    dz = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    one = orc.fr([1])[0]
+    # n_blinds = 0 and a permutation over ALL rows: z[n-1] * last factor = 1, so check z[n-1] * modified[n-1] via a second set of length 0 ... simply:
+    last = be.permutation_product_dev(k, [t.data_ptr() for t in dv], [t.data_ptr() for t in ds], 0, beta, gamma, np.zeros((0, 4), np.uint64), one, dz.data_ptr())
+    z = _host(dz)
+    z_want, _ = orc.permutation_product(k, values, sigma, 0, beta, gamma, np.zeros((0, 4), np.uint64), one)
+    assert np.array_equal(z, z_want)
+    # the full product over all n rows is 1: z[n-1] * num[n-1] / den[n-1] == 1
+    b, g = orc.fr_ints(np.stack([beta, gamma]))
+    num = den = 1
+    for c in range(n_cols):
+        num = num * (vals[c][n - 1] + b * ident[c][n - 1] + g) % R
+        den = den * (vals[c][n - 1] + b * sig[c][n - 1] + g) % R
+    assert orc.fr_ints(z[n - 1:n])[0] * num % R == den
+    assert np.array_equal(last, z[n - 1])
+
+
+@pytest.mark.parametrize("n,n_blinds", [(16, 0), (1 << 10, 5), (3000, 6), (1 << 15, 6)])
+def test_lookup_product(be, orc, n, n_blinds):
+    import torch
+    arrs = [orc.fr_random_chacha(n, 500 + i) for i in range(4)]
+    beta, gamma = orc.fr_random_chacha(2, 601)
+    arrs[3][9] = orc.fr([-orc.fr_ints(gamma.reshape(1, 4))[0]])[0]                   # a zero denominator: batch_invert leaves 0
+    blinds = orc.fr_random_chacha(n_blinds, 602).reshape(-1, 4)
+    want = orc.lookup_product(*arrs, beta, gamma, blinds)
+    d = [_dev(torch, a) for a in arrs]
+    dz = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    be.lookup_product_dev(n, *[t.data_ptr() for t in d], beta, gamma, blinds, dz.data_ptr())
+    assert np.array_equal(_host(dz), want)
+
+
+def test_weighted_sum(be, orc):
+    import torch
+    n, count = 5000, 9
+    polys = [orc.fr_random_chacha(n, 700 + i) for i in range(count)]
+    w = orc.fr_random_chacha(count, 800)
+    wi = orc.fr_ints(w); pi = [orc.fr_ints(p) for p in polys]
+    want = orc.fr([sum(wi[j] * pi[j][i] for j in range(count)) for i in range(n)])
+    d = [_dev(torch, a) for a in polys]
+    out = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    be.weighted_sum_dev([t.data_ptr() for t in d], w, out.data_ptr(), n)
+    assert np.array_equal(_host(out), want)
+
+
+def _open_sets(orc, n, layout, seed):
+    """layout: list of (point indices, number of polys) -> (sets with host polys, point array)"""
+    pts = orc.fr_random_chacha(8, seed)
+    sets = []
+    for si, (pidx, m) in enumerate(layout):
+        polys = [orc.fr_random_chacha(n, seed * 100 + si * 10 + j) for j in range(m)]
+        evals = np.stack([np.stack([orc.eval_polynomial(p, pts[i]) for i in pidx]) for p in polys])
+        sets.append((pts[list(pidx)], polys, evals))
+    return sets
+
+
+@pytest.mark.parametrize("k,layout", [(6, [((0,), 1)]), (10, [((0,), 3), ((0, 1), 2), ((0, 1, 2), 1), ((3,), 2)]), (13, [((0, 1, 2, 3, 4), 2), ((1, 5), 4)])])
+def test_shplonk_prover_matches_oracle_and_opens(be, orc, k, layout):
+    import torch
+    from spectre_b200.halo2 import ParamsKZG
+    n = 1 << k
+    params = ParamsKZG.setup(be, k, orc.srs_tau())
+    sets = _open_sets(orc, n, layout, 40 + k)
+    y, v, u = orc.fr_random_chacha(3, 900 + k)
+    h_x = orc.shplonk_quotient(n, sets, y, v)
+    final = orc.shplonk_linearisation(n, sets, y, v, u, h_x)      # raises unless L(u) == 0
+    keep = [[_dev(torch, p) for p in polys] for _, polys, _ in sets]
+    dsets = [(pts, [t.data_ptr() for t in dp], ev) for (pts, _, ev), dp in zip(sets, keep)]
+    h_commit, handle = be.shplonk_begin_dev(params, n, dsets, y, v)
+    assert np.array_equal(orc.g1_to_affine(h_commit), orc.commit_known_tau(h_x))
+    got = be.shplonk_finish_dev(handle, u)
+    assert np.array_equal(orc.g1_to_affine(got), orc.commit_known_tau(final))
+
+
+def test_shplonk_argument_errors(be, orc):
+    import torch
+    from spectre_b200.halo2 import ParamsKZG, BackendError
+    k = 6; n = 1 << k
+    params = ParamsKZG.setup(be, k, orc.srs_tau())
+    sets = _open_sets(orc, n, [((0,), 1), ((1,), 1)], 3)
+    d = [_dev(torch, st[1][0]) for st in sets]
+    y, v = orc.fr_random_chacha(2, 5)
+    dup = np.stack([sets[0][0][0], sets[0][0][0]])
+    with pytest.raises(BackendError):                               # a point listed twice in one rotation set
+        be.shplonk_begin_dev(params, n, [(dup, [d[0].data_ptr()], np.concatenate([sets[0][2], sets[0][2]], axis=1))], y, v)
+    dsets = [(st[0], [t.data_ptr()], st[2]) for st, t in zip(sets, d)]
+    _, handle = be.shplonk_begin_dev(params, n, dsets, y, v)
+    with pytest.raises(BackendError):                               # u on an opening point outside set 0: Z_{T \ S_0}(u) = 0 has no inverse
+        be.shplonk_finish_dev(handle, sets[1][0][0])

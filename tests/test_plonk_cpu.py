@@ -1,0 +1,82 @@
+"""The proof driver (spectre_b200/plonk.py) bound to the CPU oracle: proofs of synthetic circuits are accepted by the
+independent verifier (tests/plonk_verifier.py), tampering is rejected, and the transcript layout of the
+aggregation-shaped circuit is the one the reference's verifier contract hashes."""
+import numpy as np
+import pytest
+
+from spectre_b200 import plonk
+from spectre_b200.transcript import EvmTranscriptWrite, keccak256
+from tests import plonk_circuits, plonk_verifier
+from tests.plonk_oracle_engine import OracleEngine, SeededRng
+
+
+def prove(E, cs, k, fixed, advice, copies, instances, seed, digest=None):
+    pk = plonk.keygen(E, cs, k, fixed, copies, vk_digest=digest)
+    T = EvmTranscriptWrite(pk.vk_digest)
+    proof = plonk.create_proof(E, pk, [instances], advice, SeededRng(seed), T)
+    return pk, proof, T
+
+
+def test_keccak_known_answers():
+    assert keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert keccak256(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+
+
+@pytest.mark.parametrize("k", [6, 8])
+def test_aggregation_shape_proof_verifies(orc, k):
+    cs = plonk_circuits.aggregation_shape()
+    assert (cs.degree(), cs.blinding_factors(), cs.chunk_len()) == (5, 6, 3)
+    instances = [11, 22, 33 + k]
+    fixed, adv, copies = plonk_circuits.aggregation_witness(cs, k, instances, lookup_bits=3, groups=40)
+    E = OracleEngine(k, cs.degree())
+    pk, proof, T = prove(E, cs, k, fixed, [adv], copies, instances, seed=k)
+    tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
+    assert len(proof) == 12 * 64 + 19 * 32                   # the 0x560 proof bytes of the 0x720 calldata (12 points, 19 evals)
+    assert plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, [instances], proof, tau)
+    # any flipped evaluation or a wrong public input is rejected
+    bad = bytearray(proof); bad[10 * 64 + 5] ^= 1
+    with pytest.raises((AssertionError, ValueError)):
+        plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, [instances], bytes(bad), tau)
+    with pytest.raises(AssertionError):
+        plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, [[11, 22, 34 + k]], proof, tau)
+
+
+def test_unsatisfied_witness_is_rejected(orc):
+    k = 6
+    cs = plonk_circuits.aggregation_shape()
+    instances = [5]
+    fixed, adv, copies = plonk_circuits.aggregation_witness(cs, k, instances, lookup_bits=3, groups=8)
+    adv[7] = plonk.fr_mont(12345)                               # break d of the second group
+    E = OracleEngine(k, cs.degree())
+    pk, proof, _ = prove(E, cs, k, fixed, [adv], copies, instances, seed=3)
+    tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
+    with pytest.raises(AssertionError):
+        plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, [instances], proof, tau)
+
+
+def test_wide_shape_two_permutation_sets_and_theta_lookup(orc):
+    k = 7
+    cs = plonk_circuits.wide_shape(3)
+    assert cs.degree() == 5 and len(cs.permutation) == 5
+    instances = [7, 9]
+    fixed, adv, copies = plonk_circuits.wide_witness(cs, k, instances, lookup_bits=3, groups=20)
+    E = OracleEngine(k, cs.degree())
+    pk, proof, _ = prove(E, cs, k, fixed, adv, copies, instances, seed=9)
+    tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
+    assert plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, [instances], proof, tau)
+
+
+def test_transcript_layout_matches_the_verifier_contract(kats):
+    """With 14 public inputs the aggregation shape absorbs exactly the byte counts the committed contract hashes
+    (tests/golden/verifier_kats.json "transcript_schedule", extracted from sync_step_verifier.sol's keccak256 calls)."""
+    k = 7
+    cs = plonk_circuits.aggregation_shape()
+    instances = list(range(1, 15))
+    fixed, adv, copies = plonk_circuits.aggregation_witness(cs, k, instances, lookup_bits=3, groups=14)
+    E = OracleEngine(k, cs.degree())
+    _, proof, T = prove(E, cs, k, fixed, [adv], copies, instances, seed=1)
+    want = kats["transcript_schedule"]["sync_step_verifier"]
+    assert T.absorbed == want["keccak_lengths"][:len(T.absorbed)]
+    assert 32 * len(instances) + len(proof) == want["calldata_bytes"] and len(instances) == want["num_instances"]
+    # the constants multiplying beta * x in the contract's permutation identity are DELTA and DELTA^2, in column order
+    assert [int(d) for d in want["permutation_deltas"]] == [plonk.DELTA, plonk.DELTA * plonk.DELTA % plonk.R_MOD]
