@@ -238,7 +238,7 @@ typedef struct {
   const spb_fr* evals;
 } spb_rotation_set;
 typedef struct spb_shplonk spb_shplonk;
-/* After squeezing y and v: h(X) = sum_i v^(s-1-i) * [sum_j y^(m_i-1-j) (P_ij(X) - R_ij(X))] / Z_{S_i}(X), committed with
+/* After squeezing y and v: h(X) = sum_i v^i * [sum_j y^j (P_ij(X) - R_ij(X))] / Z_{S_i}(X), committed with
  * `g`; the handle keeps h(X) on the device until the second call. The caller's polynomials must stay alive and
  * unchanged until then. */
 int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_rotation_set* sets, uint32_t n_sets, const spb_fr* y, const spb_fr* v,

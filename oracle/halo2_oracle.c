@@ -1010,28 +1010,33 @@ static size_t div_by_vanishing(fe* poly, size_t len, const fe* roots, uint32_t m
 }
 static int fe_same(const fe* a, const fe* b) { return memcmp(a, b, sizeof(fe)) == 0; }
 
-/* h_x (n coefficients) = fold over sets with v of [ fold over commitments with y of (P - R) ] / Z_set */
+/* h_x (n coefficients) = sum over sets, weighted by powers(v), of [ sum over commitments, weighted by powers(y), of (P - R) ] / Z_set
+ * (upstream: `.zip(powers(*y)).map(|(q, p)| q * p).reduce(+)`, ascending powers starting at 1) */
 void orc_shplonk_quotient(size_t n, const orc_rotation_set* sets, uint32_t n_sets, const fe* y, const fe* v, fe* h_x) {
   fe* n_x = (fe*)malloc(n * sizeof(fe)); fe* scratch = (fe*)malloc(n * sizeof(fe));
   memset(h_x, 0, n * sizeof(fe));
+  fe power_of_v = FR.r;
   for (uint32_t s = 0; s < n_sets; s++) {
     const orc_rotation_set* rs = &sets[s];
     memset(n_x, 0, n * sizeof(fe));
+    fe power_of_y = FR.r;
     for (uint32_t j = 0; j < rs->n_polys; j++) {
       fe r[8]; lagrange_interpolate(rs->points, rs->evals + (size_t)j * rs->n_points, rs->n_points, r);
-      for (size_t i = 0; i < n; i++) {          /* acc * y + (poly - low_degree_equivalent) */
+      for (size_t i = 0; i < n; i++) {          /* acc + (poly - low_degree_equivalent) * power_of_y */
         fe q = rs->polys[j][i];
         if (i < rs->n_points) q = f_sub(&FR, q, r[i]);
-        n_x[i] = f_add(&FR, f_mul(&FR, n_x[i], *y), q);
+        n_x[i] = f_add(&FR, n_x[i], f_mul(&FR, q, power_of_y));
       }
+      power_of_y = f_mul(&FR, power_of_y, *y);
     }
     size_t len = div_by_vanishing(n_x, n, rs->points, rs->n_points, scratch);
     for (size_t i = len; i < n; i++) memset(&n_x[i], 0, sizeof(fe));   /* poly.resize(n, 0) */
-    for (size_t i = 0; i < n; i++) h_x[i] = f_add(&FR, f_mul(&FR, h_x[i], *v), n_x[i]);
+    for (size_t i = 0; i < n; i++) h_x[i] = f_add(&FR, h_x[i], f_mul(&FR, n_x[i], power_of_v));
+    power_of_v = f_mul(&FR, power_of_v, *v);
   }
   free(n_x); free(scratch);
 }
-/* final (n - 1 coefficients): ((fold_v [ z_i * fold_y (P - R(u)) ]) - zt_eval * h_x) / (X - u) / z_0 */
+/* final (n - 1 coefficients): ((sum_i v^i [ z_i * sum_j y^j (P_ij - R_ij(u)) ]) - zt_eval * h_x) / (X - u) / z_0 */
 int orc_shplonk_linearisation(size_t n, const orc_rotation_set* sets, uint32_t n_sets, const fe* y, const fe* v, const fe* u, const fe* h_x, fe* out) {
   fe super[64]; uint32_t n_super = 0;
   for (uint32_t s = 0; s < n_sets; s++) for (uint32_t p = 0; p < sets[s].n_points; p++) {
@@ -1041,6 +1046,7 @@ int orc_shplonk_linearisation(size_t n, const orc_rotation_set* sets, uint32_t n
   }
   fe* l_x = (fe*)calloc(n, sizeof(fe)); fe* inner = (fe*)malloc(n * sizeof(fe));
   fe z_0_diff; memset(&z_0_diff, 0, sizeof z_0_diff);
+  fe power_of_v = FR.r;
   for (uint32_t s = 0; s < n_sets; s++) {
     const orc_rotation_set* rs = &sets[s];
     fe diffs[64]; uint32_t nd = 0;
@@ -1048,16 +1054,19 @@ int orc_shplonk_linearisation(size_t n, const orc_rotation_set* sets, uint32_t n
     fe z_i = evaluate_vanishing_polynomial(diffs, nd, *u);
     if (s == 0) z_0_diff = z_i;
     memset(inner, 0, n * sizeof(fe));
+    fe power_of_y = FR.r;
     for (uint32_t j = 0; j < rs->n_polys; j++) {
       fe r[8]; lagrange_interpolate(rs->points, rs->evals + (size_t)j * rs->n_points, rs->n_points, r);
       fe r_eval; orc_eval_polynomial(&r_eval, r, rs->n_points, u);
       for (size_t i = 0; i < n; i++) {
         fe q = rs->polys[j][i];
         if (i == 0) q = f_sub(&FR, q, r_eval);
-        inner[i] = f_add(&FR, f_mul(&FR, inner[i], *y), q);
+        inner[i] = f_add(&FR, inner[i], f_mul(&FR, q, power_of_y));
       }
+      power_of_y = f_mul(&FR, power_of_y, *y);
     }
-    for (size_t i = 0; i < n; i++) l_x[i] = f_add(&FR, f_mul(&FR, l_x[i], *v), f_mul(&FR, inner[i], z_i));
+    for (size_t i = 0; i < n; i++) l_x[i] = f_add(&FR, l_x[i], f_mul(&FR, f_mul(&FR, inner[i], z_i), power_of_v));
+    power_of_v = f_mul(&FR, power_of_v, *v);
   }
   fe zt_eval = evaluate_vanishing_polynomial(super, n_super, *u);
   for (size_t i = 0; i < n; i++) l_x[i] = f_sub(&FR, l_x[i], f_mul(&FR, h_x[i], zt_eval));

@@ -1,4 +1,5 @@
-"""Synthetic circuits for the proof-driver tests.
+"""Synthetic circuits (constraint system + satisfying witness) for the proof driver: the workload of the parity tests and of
+`bench.py --prove`.
 
 `aggregation_shape()` is the constraint system of Spectre's aggregation circuits as their committed verifier contract
 spells it out (contracts/snark-verifiers/sync_step_verifier.sol:507-590):
@@ -15,8 +16,8 @@ import random
 
 import numpy as np
 
-from spectre_b200 import plonk
-from spectre_b200.plonk import Advice, Fixed, Neg, Prod, Sum
+from . import plonk
+from .plonk import Advice, Fixed, Neg, Prod, Sum
 
 R = plonk.R_MOD
 
@@ -30,8 +31,10 @@ def aggregation_shape():
                                   fixed_queries=[(0, 0), (1, 0), (2, 0), (3, 0)])
 
 
-def aggregation_witness(cs, k, instances, lookup_bits, groups, seed=1):
-    """-> (fixed columns [4 x (n,4)], advice column (n,4), copies). instances: list of ints (instance column 0)."""
+def aggregation_witness(cs, k, instances, lookup_bits, groups, seed=1, dense=False):
+    """-> (fixed columns [4 x (n,4)], advice column (n,4), copies). instances: list of ints (instance column 0).
+    dense: fill the unconstrained advice / constants rows (no gate, no lookup, no copy on them) with random residues, so
+    the commitments see a full column as they do in the real circuit."""
     n = 1 << k
     usable = n - (cs.blinding_factors() + 1)
     groups = min(groups, (usable - 4) // 4)
@@ -66,7 +69,14 @@ def aggregation_witness(cs, k, instances, lookup_bits, groups, seed=1):
             if v:
                 out[i] = plonk.fr_mont(v)
         return out
-    return [mont(const), mont(table), mont(q_lookup), mont(q_gate)], mont(adv), copies
+    fixed, advice = [mont(const), mont(table), mont(q_lookup), mont(q_gate)], mont(adv)
+    if dense:
+        g = np.random.default_rng(seed)
+        for col, lo in ((advice, 4 * groups), (fixed[0], 1)):
+            fill = g.integers(0, 1 << 63, size=(usable - lo, 4), dtype=np.uint64)
+            fill[:, 3] &= np.uint64((1 << 60) - 1)           # < 2^252 < r: valid Montgomery residues
+            col[lo:usable] = fill
+    return fixed, advice, copies
 
 
 def wide_shape(num_advice=3):

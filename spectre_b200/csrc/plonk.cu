@@ -73,12 +73,12 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(const Fr* const* poly
   for (uint32_t p = 0; p < count; p++) acc = fp_add(acc, fp_mul(w[p], ntt_ld_stream(polys[p] + i)));
   ntt_stg(out + i, acc);
 }
-// h[i] = alpha * h[i] + (i < nx ? x[i] : 0)
-__global__ void __launch_bounds__(256) scale_add_kernel(Fr* h, Fr alpha, const Fr* x, uint64_t nx, uint64_t n) {
+// h[i] = alpha * h[i] + beta * (i < nx ? x[i] : 0)
+__global__ void __launch_bounds__(256) scale_add_kernel(Fr* h, Fr alpha, const Fr* x, Fr beta, uint64_t nx, uint64_t n) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr v = fp_mul(alpha, ntt_ld_stream(h + i));
-  if (i < nx) v = fp_add(v, ntt_ld_stream(x + i));
+  if (i < nx) v = fp_add(v, fp_mul(beta, ntt_ld_stream(x + i)));
   ntt_stg(h + i, v);
 }
 struct SmallPoly { Fr c[8]; uint32_t n; };
@@ -109,7 +109,7 @@ struct spb_shplonk {
   int device = 0;
   size_t n = 0;
   const spb_srs* srs = nullptr;
-  Fr* d_h = nullptr;            // h(X) = sum_i v^(s-1-i) Q_i(X), n coefficients
+  Fr* d_h = nullptr;            // h(X) = sum_i v^i Q_i(X), n coefficients
   Fr* d_tmp[2] = {nullptr, nullptr};
   const Fr** d_ptrs = nullptr;  // all opened polynomials, set by set
   Fr* d_w = nullptr;            // their weights
@@ -297,13 +297,14 @@ int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_
     SHP_CUDA(cudaMemcpyAsync((void*)s->d_ptrs, ptrs.data(), (size_t)total * sizeof(void*), cudaMemcpyHostToDevice, d.stream));
     SHP_CUDA(cudaMemsetAsync(s->d_h, 0, n * 32, d.stream));
     uint32_t base = 0;
+    Fr vpow = fp_one<FrParams>();
     for (uint32_t i = 0; i < n_sets; i++) {
       spb_shplonk::Set& st = s->sets[i];
       const uint32_t m = st.n_polys, np = (uint32_t)st.points.size();
-      // N_i(X) = sum_j y^(m-1-j) (P_ij(X) - R_ij(X))
+      // N_i(X) = sum_j y^j (P_ij(X) - R_ij(X))      (upstream: numerators.zip(powers(y)))
       std::vector<Fr> w(m);
       Fr pw = fp_one<FrParams>();
-      for (uint32_t j = m; j-- > 0;) { w[j] = pw; pw = fp_mul(pw, s->y); }
+      for (uint32_t j = 0; j < m; j++) { w[j] = pw; pw = fp_mul(pw, s->y); }
       SmallPoly rsum; rsum.n = np;
       for (uint32_t t = 0; t < np; t++) rsum.c[t] = fp_zero<FrParams>();
       for (uint32_t j = 0; j < m; j++) for (uint32_t t = 0; t < np; t++) rsum.c[t] = fp_add(rsum.c[t], fp_mul(w[j], st.r[j][t]));
@@ -317,8 +318,9 @@ int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_
         if ((rc = dev_kate_division(ctx, d, s->d_tmp[cur], len, st.points[p], s->d_tmp[cur ^ 1])) != 0) return fail(rc);
         cur ^= 1; len--;
       }
-      // h <- h * v + Q_i (zero-extended to n)
-      scale_add_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(s->d_h, s->v, s->d_tmp[cur], len, n);
+      // h <- h + v^i * Q_i (Q_i zero-extended to n)   (upstream: quotient_polynomials.zip(powers(v)))
+      scale_add_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(s->d_h, fp_one<FrParams>(), s->d_tmp[cur], vpow, len, n);
+      vpow = fp_mul(vpow, s->v);
       ctx->n_kernel_launches++;
       SHP_CUDA(cudaStreamSynchronize(d.stream));   // w (host vector) must outlive the copy
       base += m;
@@ -337,12 +339,12 @@ int spb_shplonk_finish_dev(spb_ctx* ctx, spb_shplonk* s, const spb_fr* u, spb_g1
   const Fr uu = fr_load(u);
   const size_t n = s->n;
   const uint32_t n_sets = (uint32_t)s->sets.size();
-  // weights w_ij = v^(s-1-i) * Z_{T \ S_i}(u) * y^(m_i-1-j); constant = sum w_ij * R_ij(u); and -Z_T(u) on h
+  // weights w_ij = v^i * Z_{T \ S_i}(u) * y^j; constant = sum w_ij * R_ij(u); and -Z_T(u) on h
   std::vector<Fr> w; w.reserve(s->n_polys);
   Fr constant = fp_zero<FrParams>(), z0 = fp_one<FrParams>();
   Fr vpow = fp_one<FrParams>();
   std::vector<Fr> vp(n_sets);
-  for (uint32_t i = n_sets; i-- > 0;) { vp[i] = vpow; vpow = fp_mul(vpow, s->v); }
+  for (uint32_t i = 0; i < n_sets; i++) { vp[i] = vpow; vpow = fp_mul(vpow, s->v); }
   for (uint32_t i = 0; i < n_sets; i++) {
     const spb_shplonk::Set& st = s->sets[i];
     std::vector<Fr> diffs;
@@ -352,7 +354,7 @@ int spb_shplonk_finish_dev(spb_ctx* ctx, spb_shplonk* s, const spb_fr* u, spb_g1
     Fr outer = fp_mul(vp[i], zi);
     std::vector<Fr> yp(st.n_polys);
     Fr pw = fp_one<FrParams>();
-    for (uint32_t j = st.n_polys; j-- > 0;) { yp[j] = pw; pw = fp_mul(pw, s->y); }
+    for (uint32_t j = 0; j < st.n_polys; j++) { yp[j] = pw; pw = fp_mul(pw, s->y); }
     for (uint32_t j = 0; j < st.n_polys; j++) {
       Fr wij = fp_mul(outer, yp[j]);
       w.push_back(wij);
@@ -374,11 +376,11 @@ int spb_shplonk_finish_dev(spb_ctx* ctx, spb_shplonk* s, const spb_fr* u, spb_g1
     SmallPoly c0; c0.n = 1; c0.c[0] = constant;
     sub_small_kernel<<<1, 8, 0, d.stream>>>(s->d_tmp[0], c0);
     // tmp0 <- 1 * tmp0 + (-zt) * h  ==  scale_add on a copy of h: h <- (-zt) * h + tmp0
-    scale_add_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(s->d_h, fp_neg(zt), s->d_tmp[0], n, n);
+    scale_add_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(s->d_h, fp_neg(zt), s->d_tmp[0], fp_one<FrParams>(), n, n);
     ctx->n_kernel_launches += 3;
     // (L(X) / (X - u)) / Z_{T \ S_0}(u)
     if ((rc = dev_kate_division(ctx, d, s->d_h, n, uu, s->d_tmp[1])) != 0) return fail(rc);
-    scale_add_kernel<<<nblk(n - 1, 256), 256, 0, d.stream>>>(s->d_tmp[1], z0_inv, nullptr, 0, n - 1);
+    scale_add_kernel<<<nblk(n - 1, 256), 256, 0, d.stream>>>(s->d_tmp[1], z0_inv, nullptr, fp_zero<FrParams>(), 0, n - 1);
     ctx->n_kernel_launches++;
     SHP_CUDA(cudaGetLastError());
     SHP_CUDA(cudaStreamSynchronize(d.stream));

@@ -164,9 +164,9 @@ def verify(cs, k, vk_digest, fixed_commitments, sigma_commitments, instances, pr
         for p in super_pts:
             if p not in pts: zi = zi * (u - p) % R
         if i == 0: z0 = zi
-        outer = pow(v, len(sets) - 1 - i, R) * zi % R
+        outer = pow(v, i, R) * zi % R
         for j, pid in enumerate(pids):
-            wij = outer * pow(y2, len(pids) - 1 - j, R) % R
+            wij = outer * pow(y2, j, R) % R
             acc_pt = ec_add(acc_pt, ec_mul(commits[pid], wij))
             acc_const = (acc_const + wij * interp_eval(pts, evs[j], u)) % R
     zt = 1

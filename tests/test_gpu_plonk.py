@@ -147,3 +147,72 @@ def test_shplonk_argument_errors(be, orc):
     _, handle = be.shplonk_begin_dev(params, n, dsets, y, v)
     with pytest.raises(BackendError):                               # u on an opening point outside set 0: Z_{T \ S_0}(u) = 0 has no inverse
         be.shplonk_finish_dev(handle, sets[1][0][0])
+
+
+# ---- the whole driver: create_proof on the device ---------------------------------------------------------------------
+def _prove_both(be, orc, cs, k, fixed, advice, copies, instances, seed):
+    from spectre_b200 import plonk
+    from spectre_b200.halo2 import ParamsKZG
+    from spectre_b200.transcript import EvmTranscriptWrite
+    from tests.plonk_oracle_engine import OracleEngine, SeededRng
+    out = []
+    params = ParamsKZG.setup(be, k, orc.srs_tau())
+    for E in (plonk.DeviceEngine(be, params, k, cs.degree()), OracleEngine(k, cs.degree())):
+        pk = plonk.keygen(E, cs, k, fixed, copies)
+        T = EvmTranscriptWrite(pk.vk_digest)
+        out.append((pk, plonk.create_proof(E, pk, [instances], advice, SeededRng(seed), T)))
+    return out
+
+
+@pytest.mark.parametrize("shape,k", [("aggregation", 7), ("aggregation", 11), ("wide", 8), ("wide", 12)])
+def test_device_proof_is_byte_identical_to_the_oracle_proof_and_verifies(be, orc, shape, k):
+    from spectre_b200 import circuits as plonk_circuits
+    from tests import plonk_verifier
+    instances = [3, 1, 4, 1, 5]
+    if shape == "aggregation":
+        cs = plonk_circuits.aggregation_shape()
+        fixed, adv, copies = plonk_circuits.aggregation_witness(cs, k, instances, lookup_bits=4, groups=300)
+        adv = [adv]
+    else:
+        cs = plonk_circuits.wide_shape(3)
+        fixed, adv, copies = plonk_circuits.wide_witness(cs, k, instances, lookup_bits=4, groups=300)
+    (pk_d, proof_d), (pk_o, proof_o) = _prove_both(be, orc, cs, k, fixed, adv, copies, instances, seed=100 + k)
+    assert pk_d.fixed_commitments == pk_o.fixed_commitments and pk_d.sigma_commitments == pk_o.sigma_commitments
+    assert proof_d == proof_o
+    tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
+    assert plonk_verifier.verify(cs, k, pk_d.vk_digest, pk_d.fixed_commitments, pk_d.sigma_commitments, [instances], proof_d, tau)
+
+
+def test_k23_proof_equals_the_contract_accepted_fixture(be, orc, kats):
+    """K = 23: the device regenerates, byte for byte, the proof in tests/golden/aggregation_k23_proof.json -- the one the
+    reference's sync_step verifier contract accepted when replayed by tests/yul_harness.py (tools/make_k23_fixture.py)."""
+    import json
+    import os
+    import time
+    from spectre_b200 import plonk
+    from spectre_b200.halo2 import ParamsKZG
+    from spectre_b200.transcript import EvmTranscriptWrite
+    from spectre_b200 import circuits as plonk_circuits
+    from tests.plonk_oracle_engine import SeededRng
+    path = os.path.join(os.path.dirname(__file__), "golden", "aggregation_k23_proof.json")
+    with open(path) as f:
+        fx = json.load(f)
+    k = fx["k"]
+    instances = [int(v, 16) for v in fx["instances"]]
+    cs = plonk_circuits.aggregation_shape()
+    fixed, adv, copies = plonk_circuits.aggregation_witness(cs, k, instances, fx["lookup_bits"], fx["groups"], seed=fx["seed"])
+    params = ParamsKZG.setup(be, k, orc.srs_tau()).precompute()
+    E = plonk.DeviceEngine(be, params, k, cs.degree())
+    t0 = time.perf_counter()
+    pk = plonk.keygen(E, cs, k, fixed, copies, vk_digest=int(fx["vk_digest"]))
+    t1 = time.perf_counter()
+    timings = {}
+    proof = plonk.create_proof(E, pk, [instances], [adv], SeededRng(fx["seed"]), EvmTranscriptWrite(pk.vk_digest), timings)
+    t2 = time.perf_counter()
+    print("K=%d keygen %.2fs create_proof %.2fs %s" % (k, t1 - t0, t2 - t1, {a: round(b, 3) for a, b in timings.items()}))
+    assert [[hex(x), hex(y)] for x, y in pk.fixed_commitments + pk.sigma_commitments] == fx["vk_points"]
+    assert pk.fixed_commitments[1] == tuple(int(v, 16) for v in kats["range_table_commit_k23_bits19"]["xy"])   # the contract's own VK constant
+    assert proof.hex() == fx["proof"]
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/k23_proof_timings.json", "w") as f:
+        json.dump({"k": k, "keygen_s": t1 - t0, "create_proof_s": t2 - t1, "stages": timings}, f)

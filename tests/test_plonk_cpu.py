@@ -6,7 +6,8 @@ import pytest
 
 from spectre_b200 import plonk
 from spectre_b200.transcript import EvmTranscriptWrite, keccak256
-from tests import plonk_circuits, plonk_verifier
+from spectre_b200 import circuits as plonk_circuits
+from tests import plonk_verifier
 from tests.plonk_oracle_engine import OracleEngine, SeededRng
 
 
@@ -80,3 +81,29 @@ def test_transcript_layout_matches_the_verifier_contract(kats):
     assert 32 * len(instances) + len(proof) == want["calldata_bytes"] and len(instances) == want["num_instances"]
     # the constants multiplying beta * x in the contract's permutation identity are DELTA and DELTA^2, in column order
     assert [int(d) for d in want["permutation_deltas"]] == [plonk.DELTA, plonk.DELTA * plonk.DELTA % plonk.R_MOD]
+
+
+@pytest.mark.skipif(not __import__("tests.yul_harness", fromlist=["x"]).available(), reason="reference tree not present")
+def test_reference_verifier_contract_accepts_the_k23_fixture(orc, kats):
+    """contracts/snark-verifiers/sync_step_verifier.sol, interpreted as it stands in the reference tree, accepts the
+    committed K = 23 proof (VK commitments substituted, pairing decided with the known tau: tests/yul_harness.py), and
+    rejects it after a one-bit change or with a different public input."""
+    import json, os
+    from tests import yul_harness
+    path = os.path.join(os.path.dirname(__file__), "golden", "aggregation_k23_proof.json")
+    with open(path) as f:
+        fx = json.load(f)
+    instances = [int(v, 16) for v in fx["instances"]]
+    proof = bytes.fromhex(fx["proof"])
+    vk_points = [(int(x, 16), int(y, 16)) for x, y in fx["vk_points"]]
+    tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
+    ok, m = yul_harness.run_contract("sync_step_verifier", instances, proof, vk_points, tau, kats)
+    assert ok and m.pairing_calls == 1 and m.precompile_counts[7] == 21
+    bad = bytearray(proof); bad[11 * 64 - 1 + 32 * 3] ^= 1         # one bit of an evaluation
+    assert not yul_harness.run_contract("sync_step_verifier", instances, bytes(bad), vk_points, tau, kats)[0]
+    assert not yul_harness.run_contract("sync_step_verifier", instances[:13] + [instances[13] + 1], proof, vk_points, tau, kats)[0]
+    # and the independent Python verifier agrees on the same bytes
+    from spectre_b200 import circuits as plonk_circuits
+    from tests import plonk_verifier
+    cs = plonk_circuits.aggregation_shape()
+    assert plonk_verifier.verify(cs, fx["k"], int(fx["vk_digest"]), vk_points[:4], vk_points[4:], [instances], proof, tau)
