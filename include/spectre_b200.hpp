@@ -136,6 +136,7 @@ class ParamsKZG {
   ~ParamsKZG() { if (h_) spb_srs_free(be_.ctx(), h_); }
   uint32_t k() const { return k_; }
   uint64_t n() const { return 1ull << k_; }
+  const spb_srs* handle() const { return h_; }
   void precompute() { be_.check(spb_srs_precompute(be_.ctx(), h_), "spb_srs_precompute"); }
   // Params::commit / commit_lagrange (the blind is ignored by the KZG scheme upstream, so it is not taken here)
   G1 commit(const std::vector<Fr>& poly) const { return msm(SPB_BASIS_G, poly); }
@@ -160,5 +161,61 @@ class ParamsKZG {
 };
 
 }  // namespace kzg
+
+// ProverSHPLONK::create_proof over device-resident polynomials (coefficient form, n each). RotationSet mirrors what
+// construct_intermediate_sets yields; open() returns the first commitment, finish(u) the second.
+namespace shplonk {
+
+struct RotationSet {
+  std::vector<Fr> points;
+  std::vector<const Fr*> d_polys;   // device pointers
+  std::vector<Fr> evals;            // d_polys.size() x points.size()
+};
+
+class Prover {
+ public:
+  Prover(const Backend& be, const kzg::ParamsKZG& params, size_t n, const std::vector<RotationSet>& sets, const Fr& y, const Fr& v, G1* h_commitment) : be_(be) {
+    std::vector<spb_rotation_set> raw;
+    for (const RotationSet& rs : sets) {
+      if (rs.evals.size() != rs.d_polys.size() * rs.points.size()) throw std::invalid_argument("shplonk: evals must be polys x points");
+      raw.push_back(spb_rotation_set{rs.points.data(), (uint32_t)rs.points.size(), rs.d_polys.data(), (uint32_t)rs.d_polys.size(), rs.evals.data()});
+    }
+    be.check(spb_shplonk_begin_dev(be.ctx(), params.handle(), n, raw.data(), (uint32_t)raw.size(), &y, &v, h_commitment, &s_), "spb_shplonk_begin_dev");
+  }
+  ~Prover() { if (s_) spb_shplonk_abort(be_.ctx(), s_); }
+  Prover(const Prover&) = delete;
+  G1 finish(const Fr& u) {
+    G1 out;
+    spb_shplonk* s = s_;
+    s_ = nullptr;                     // consumed by the call, also on error
+    be_.check(spb_shplonk_finish_dev(be_.ctx(), s, &u, &out), "spb_shplonk_finish_dev");
+    return out;
+  }
+
+ private:
+  const Backend& be_;
+  spb_shplonk* s_ = nullptr;
+};
+
+}  // namespace shplonk
 }  // namespace poly
+
+// plonk::{permutation,lookup}::prover grand products over device-resident Lagrange columns
+namespace plonk {
+
+inline Fr permutation_product(const Backend& be, uint32_t k, const std::vector<const Fr*>& d_values, const std::vector<const Fr*>& d_sigma, uint32_t first_col,
+                              const Fr& beta, const Fr& gamma, const std::vector<Fr>& blinds, Fr last_z, Fr* d_z) {
+  if (d_values.size() != d_sigma.size()) throw std::invalid_argument("permutation_product: one sigma per column");
+  be.check(spb_permutation_product_dev(be.ctx(), k, d_values.data(), d_sigma.data(), (uint32_t)d_values.size(), first_col, &beta, &gamma,
+                                       blinds.empty() ? nullptr : blinds.data(), (uint32_t)blinds.size(), &last_z, d_z), "spb_permutation_product_dev");
+  return last_z;
+}
+
+inline void lookup_product(const Backend& be, size_t n, const Fr* d_compressed_input, const Fr* d_compressed_table, const Fr* d_permuted_input, const Fr* d_permuted_table,
+                           const Fr& beta, const Fr& gamma, const std::vector<Fr>& blinds, Fr* d_z) {
+  be.check(spb_lookup_product_dev(be.ctx(), n, d_compressed_input, d_compressed_table, d_permuted_input, d_permuted_table, &beta, &gamma,
+                                  blinds.empty() ? nullptr : blinds.data(), (uint32_t)blinds.size(), d_z), "spb_lookup_product_dev");
+}
+
+}  // namespace plonk
 }  // namespace halo2
