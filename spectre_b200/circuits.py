@@ -127,3 +127,95 @@ def wide_witness(cs, k, instances, lookup_bits, groups, seed=2):
             if v: out[i] = plonk.fr_mont(v)
         return out
     return [mont(f) for f in fixed], [mont(a) for a in adv], copies
+
+
+# ---- halo2-lib's multi-column layout: the shape of Spectre's sync-step circuit -----------------------------------------
+def halo2lib_shape(num_gate_advice=15, num_lookup_advice=2, spread=True):
+    """The constraint-system shape SURVEY.md section 8 (table row 1) derives for the sync-step circuit from
+    lightclient-circuits/config/sync_step_20.json:3-16 and the SHA spread config (sha256_flex/spread.rs:40-80,89):
+    `num_gate_advice` basic-gate columns q_c * (a + b*c - d), `num_lookup_advice` dedicated range-lookup columns (no
+    selector: degree-4 lookups), one two-column spread lookup compressed with theta, and one permutation over every advice
+    column, the constants column and the instance column. With the defaults: 19 advice columns, 3 lookups, degree 4
+    (extended domain 4n, 3 quotient pieces), 21 permutation columns in 11 sets of 2 -- the 45-MSM schedule of that row.
+    advice columns: [gate 0..G) [lookup G..G+L) [spread dense, spread spread]; fixed: [q_gate 0..G) constants, range table,
+    spread table (2 columns)."""
+    G, L = num_gate_advice, num_lookup_advice
+    A = G + L + (2 if spread else 0)
+    gates = []
+    for c in range(G):
+        a = [Advice(c, r) for r in range(4)]
+        gates.append(Prod(Fixed(c), Sum(Sum(a[0], Prod(a[1], a[2])), Neg(a[3]))))
+    lookups = [([Advice(G + l)], [Fixed(G + 1)]) for l in range(L)]
+    if spread:
+        lookups.append(([Advice(G + L), Advice(G + L + 1)], [Fixed(G + 2), Fixed(G + 3)]))
+    perm = [("advice", c) for c in range(A)] + [("fixed", G), ("instance", 0)]
+    return plonk.ConstraintSystem(num_fixed=G + 2 + (2 if spread else 0), num_advice=A, num_instance=1, gates=gates, lookups=lookups, permutation=perm)
+
+
+def halo2lib_witness(cs, k, instances, lookup_bits, groups, seed=3, num_gate_advice=15, num_lookup_advice=2):
+    """A satisfying witness with full columns: `groups` chained gate groups per gate column (copy constraints d -> next b,
+    first b = a constant cell, some c = public inputs, every looked-up a copied into a range-lookup column), every other
+    usable row of the gate / constants columns filled with random residues (they are unconstrained), and every usable
+    row of the lookup columns a random table entry. -> (fixed columns, advice columns, copies)."""
+    G, L = num_gate_advice, num_lookup_advice
+    spread = cs.num_advice == G + L + 2
+    n = 1 << k
+    usable = n - (cs.blinding_factors() + 1)
+    groups = min(groups, (usable - 4) // 4)
+    T = 1 << lookup_bits
+    assert T < usable and len(instances) <= groups
+    rng, g = random.Random(seed), np.random.default_rng(seed)
+
+    def residues(rows):
+        a = g.integers(0, 1 << 63, size=(rows, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 60) - 1)
+        return a
+    small = np.stack([plonk.fr_mont(i) for i in range(T)])                  # Montgomery forms of 0..T-1
+    spread_of = lambda i: (i * i + 1) % R
+    spread_mont = np.stack([plonk.fr_mont(spread_of(i)) for i in range(T)]) if spread else None
+    fixed = [np.zeros((n, 4), dtype=np.uint64) for _ in range(cs.num_fixed)]
+    advice = [np.zeros((n, 4), dtype=np.uint64) for _ in range(cs.num_advice)]
+    one = plonk.fr_mont(1)
+    fixed[G][1:usable] = residues(usable - 1)                                # constants column: free cells
+    c0 = rng.randrange(R); fixed[G][0] = plonk.fr_mont(c0)
+    fixed[G + 1][:T] = small                                                 # range table, zero padded
+    if spread:
+        fixed[G + 2][:T] = small; fixed[G + 3][:T] = spread_mont
+        fixed[G + 3][T:] = 0
+    A = cs.num_advice
+    CONST_COL, INST_COL = A, A + 1                                           # indices in cs.permutation
+    copies = []
+    # lookup columns: every usable row a table entry
+    look_vals = []
+    for l in range(L):
+        idx = g.integers(0, T, size=usable)
+        advice[G + l][:usable] = small[idx]
+        look_vals.append(idx)
+    if spread:
+        idx = g.integers(0, T, size=usable)
+        advice[G + L][:usable] = small[idx]; advice[G + L + 1][:usable] = spread_mont[idx]
+    next_lookup_row = [0] * L
+    for c in range(G):
+        col = advice[c]
+        col[4 * groups:usable] = residues(usable - 4 * groups)
+        prev_d = None
+        for gi in range(groups):
+            r = 4 * gi
+            a = rng.randrange(T)
+            b = c0 if gi == 0 else prev_d
+            cc = instances[gi] if (c == 0 and gi < len(instances)) else rng.randrange(R)
+            d = (a + b * cc) % R
+            for off, v in enumerate((a, b, cc, d)):
+                col[r + off] = plonk.fr_mont(v)
+            fixed[c][r] = one
+            copies.append(((c, r + 1), (CONST_COL, 0)) if gi == 0 else ((c, r + 1), (c, r - 1)))
+            if c == 0 and gi < len(instances):
+                copies.append(((c, r + 2), (INST_COL, gi)))
+            if L and gi % 4 == 0:                                            # range-check a: copy it into a lookup column
+                l = (c + gi) % L
+                row = next_lookup_row[l]
+                if row < usable:
+                    advice[G + l][row] = small[a]
+                    copies.append(((c, r), (G + l, row)))
+                    next_lookup_row[l] = row + 1
+            prev_d = d
+    return fixed, advice, copies

@@ -164,7 +164,7 @@ def _prove_both(be, orc, cs, k, fixed, advice, copies, instances, seed):
     return out
 
 
-@pytest.mark.parametrize("shape,k", [("aggregation", 7), ("aggregation", 11), ("wide", 8), ("wide", 12)])
+@pytest.mark.parametrize("shape,k", [("aggregation", 7), ("aggregation", 11), ("wide", 8), ("wide", 12), ("halo2lib", 10)])
 def test_device_proof_is_byte_identical_to_the_oracle_proof_and_verifies(be, orc, shape, k):
     from spectre_b200 import circuits as plonk_circuits
     from tests import plonk_verifier
@@ -173,9 +173,12 @@ def test_device_proof_is_byte_identical_to_the_oracle_proof_and_verifies(be, orc
         cs = plonk_circuits.aggregation_shape()
         fixed, adv, copies = plonk_circuits.aggregation_witness(cs, k, instances, lookup_bits=4, groups=300)
         adv = [adv]
-    else:
+    elif shape == "wide":
         cs = plonk_circuits.wide_shape(3)
         fixed, adv, copies = plonk_circuits.wide_witness(cs, k, instances, lookup_bits=4, groups=300)
+    else:                                                       # the sync-step circuit's multi-column shape, 11 permutation sets
+        cs = plonk_circuits.halo2lib_shape()
+        fixed, adv, copies = plonk_circuits.halo2lib_witness(cs, k, instances, lookup_bits=5, groups=100)
     (pk_d, proof_d), (pk_o, proof_o) = _prove_both(be, orc, cs, k, fixed, adv, copies, instances, seed=100 + k)
     assert pk_d.fixed_commitments == pk_o.fixed_commitments and pk_d.sigma_commitments == pk_o.sigma_commitments
     assert proof_d == proof_o

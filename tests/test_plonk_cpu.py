@@ -107,3 +107,19 @@ def test_reference_verifier_contract_accepts_the_k23_fixture(orc, kats):
     from tests import plonk_verifier
     cs = plonk_circuits.aggregation_shape()
     assert plonk_verifier.verify(cs, fx["k"], int(fx["vk_digest"]), vk_points[:4], vk_points[4:], [instances], proof, tau)
+
+
+def test_halo2lib_sync_step_shape_proof_verifies(orc):
+    """the multi-column shape of the sync-step circuit, scaled down: 4 gate columns, 2 range-lookup
+    columns, the spread lookup, permutation sets of two columns"""
+    k = 8
+    cs = plonk_circuits.halo2lib_shape(4, 2)
+    assert (cs.degree(), cs.chunk_len(), len(cs.permutation)) == (4, 2, 10)
+    full = plonk_circuits.halo2lib_shape()
+    assert (full.num_advice, len(full.lookups), full.degree(), len(full.permutation), -(-len(full.permutation) // full.chunk_len())) == (19, 3, 4, 21, 11)
+    instances = [5, 6, 7]
+    fixed, adv, copies = plonk_circuits.halo2lib_witness(cs, k, instances, lookup_bits=4, groups=30, num_gate_advice=4, num_lookup_advice=2)
+    E = OracleEngine(k, cs.degree())
+    pk, proof, _ = prove(E, cs, k, fixed, adv, copies, instances, seed=21)
+    tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
+    assert plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, [instances], proof, tau)
