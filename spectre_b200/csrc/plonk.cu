@@ -11,8 +11,14 @@
 #include "common.cuh"
 #include "ntt.cuh"
 #include <string.h>
+#include <chrono>
+#include <stdlib.h>
 
 using namespace spb;
+
+// SPB_PLONK_DEBUG=1: wall-clock of the SHPLONK phases on stderr
+static bool plonk_debug() { static int v = -1; if (v < 0) { const char* e = getenv("SPB_PLONK_DEBUG"); v = e && *e && *e != '0'; } return v == 1; }
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 namespace {
 
@@ -245,6 +251,7 @@ int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_
   if (!ctx) return SPB_ERR_ARG;
   if (!srs || !sets || !n_sets || !y || !v || !h_commitment || !out || n < 2) return set_error(ctx, SPB_ERR_ARG, "spb_shplonk_begin_dev: null argument");
   *out = nullptr;
+  const double t_start = now_s();
   uint32_t total = 0;
   for (uint32_t i = 0; i < n_sets; i++) {
     const spb_rotation_set& rs = sets[i];
@@ -265,6 +272,7 @@ int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_
     if (e == cudaSuccess) e = cudaMalloc(&s->d_w, (size_t)total * 32);
     if (e != cudaSuccess) { shplonk_release(s); return set_error(ctx, SPB_ERR_OOM, "spb_shplonk_begin_dev: %s", cudaGetErrorString(e)); }
   }
+  const double t_alloc = now_s();
   // host side: the sets, the low-degree equivalents R_ij and the super point set
   std::vector<const Fr*> ptrs; ptrs.reserve(total);
   for (uint32_t i = 0; i < n_sets; i++) {
@@ -327,7 +335,9 @@ int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_
     }
     SHP_CUDA(cudaGetLastError());
   }
+  const double t_polys = now_s();
   rc = spb_msm_dev(ctx, srs, SPB_BASIS_G, (const spb_fr*)s->d_h, n, h_commitment);
+  if (plonk_debug()) fprintf(stderr, "[spb] shplonk begin n=%zu polys=%u: alloc %.1f ms, quotients %.1f ms, msm %.1f ms\n", n, total, (t_alloc - t_start) * 1e3, (t_polys - t_alloc) * 1e3, (now_s() - t_polys) * 1e3);
   if (rc != 0) { std::lock_guard<std::mutex> lk(ctx->mu); shplonk_release(s); return rc; }
   *out = s;
   return 0;
@@ -338,6 +348,7 @@ int spb_shplonk_finish_dev(spb_ctx* ctx, spb_shplonk* s, const spb_fr* u, spb_g1
   if (!s || !u || !commitment) return set_error(ctx, SPB_ERR_ARG, "spb_shplonk_finish_dev: null argument");
   const Fr uu = fr_load(u);
   const size_t n = s->n;
+  const double t_start = now_s();
   const uint32_t n_sets = (uint32_t)s->sets.size();
   // weights w_ij = v^i * Z_{T \ S_i}(u) * y^j; constant = sum w_ij * R_ij(u); and -Z_T(u) on h
   std::vector<Fr> w; w.reserve(s->n_polys);
@@ -385,8 +396,11 @@ int spb_shplonk_finish_dev(spb_ctx* ctx, spb_shplonk* s, const spb_fr* u, spb_g1
     SHP_CUDA(cudaGetLastError());
     SHP_CUDA(cudaStreamSynchronize(d.stream));
   }
+  const double t_polys = now_s();
   rc = spb_msm_dev(ctx, s->srs, SPB_BASIS_G, (const spb_fr*)s->d_tmp[1], n - 1, commitment);
+  const double t_msm = now_s();
   { std::lock_guard<std::mutex> lk(ctx->mu); shplonk_release(s); }
+  if (plonk_debug()) fprintf(stderr, "[spb] shplonk finish: linearisation %.1f ms, msm %.1f ms, release %.1f ms\n", (t_polys - t_start) * 1e3, (t_msm - t_polys) * 1e3, (now_s() - t_msm) * 1e3);
   return rc;
 }
 

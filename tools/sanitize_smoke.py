@@ -44,5 +44,18 @@ assert np.array_equal(be.batch_invert(p), orc.batch_invert(p))
 assert np.array_equal(be.eval_polynomial(p, x), orc.eval_polynomial(p, x))
 assert np.array_equal(be.kate_division(p, x), orc.kate_division(p, x))
 be.grand_product(p); be.vec_mul(p, p); be.vec_axpy(p, x, p); be.vec_scale(p, x)
-print("sanitize smoke ok, kernels launched:", be.kernel_launches)
+# one whole proof of the multi-column shape: graph / permutation / lookup constraint kernels, the lookup sort, the argument
+# provers and the SHPLONK opener (device buffers through torch), byte-compared with the oracle-engine proof
+from spectre_b200 import circuits, plonk  # noqa: E402
+from spectre_b200.transcript import EvmTranscriptWrite  # noqa: E402
+from tests.plonk_oracle_engine import OracleEngine, SeededRng  # noqa: E402
+kp, inst = 7, [3, 1, 4]
+cs = circuits.halo2lib_shape(3, 1)
+fixed, adv, copies = circuits.halo2lib_witness(cs, kp, inst, lookup_bits=3, groups=12, num_gate_advice=3, num_lookup_advice=1)
+proofs = []
+for E in (plonk.DeviceEngine(be, halo2.ParamsKZG.setup(be, kp, orc.srs_tau()), kp, cs.degree()), OracleEngine(kp, cs.degree())):
+    pk = plonk.keygen(E, cs, kp, fixed, copies)
+    proofs.append(plonk.create_proof(E, pk, [inst], adv, SeededRng(1), EvmTranscriptWrite(pk.vk_digest)))
+assert proofs[0] == proofs[1]
+print("sanitize smoke ok (incl. a %d-byte proof), kernels launched:" % len(proofs[0]), be.kernel_launches)
 be.close()
