@@ -123,7 +123,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ntt", action="store_true")
-    ap.add_argument("--prove", action="store_true", help="also run keygen + create_proof of the aggregation-shaped circuit (spectre_b200/plonk.py) on rank 0")
+    ap.add_argument("--no-prove", action="store_true", help="skip keygen + create_proof of the two circuit shapes (spectre_b200/plonk.py; N=1 only)")
     ap.add_argument("--prove-k", type=int, default=23, help="k of the aggregation-shaped proof")
     ap.add_argument("--prove-k-step", type=int, default=20, help="k of the sync-step-shaped proof")
     ap.add_argument("--replay", action="store_true", help="also run the proof-shaped replays (sync-step k=20, aggregation K=23) on rank 0")
@@ -344,52 +344,55 @@ def main():
 
     # ---- real proofs: keygen + create_proof of the two circuit shapes of a sync-step-compressed proof, every polynomial
     # resident in HBM (spectre_b200/plonk.py; the aggregation shape is the one the reference's verifier contract accepts) ----
-    if args.prove and world == 1:
-        from spectre_b200 import circuits, plonk
-        from spectre_b200.transcript import EvmTranscriptWrite
-        if "dev_sets" in dir():
-            del dev_sets
-        torch.cuda.empty_cache()
-        g = np.random.default_rng(7)
-
-        def draw(count):
-            a = g.integers(0, 1 << 63, size=(count, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 60) - 1)
-            return a
-        proofs = {}
-        for name, pk_ in (("sync_step_shape", args.prove_k_step), ("aggregation_shape", args.prove_k)):
-            t0 = time.perf_counter()
-            srs = halo2.ParamsKZG.setup(be, pk_, plonk.fr_mont(0x5eed7a75)).precompute()   # any secret: timings do not depend on it
-            torch.cuda.synchronize(); t_srs = time.perf_counter() - t0
-            inst = list(range(1, 15))
-            t0 = time.perf_counter()
-            if name == "aggregation_shape":
-                cs = circuits.aggregation_shape()
-                fixed_cols, adv_cols, copies = circuits.aggregation_witness(cs, pk_, inst, min(19, pk_ - 2), 2000, seed=1, dense=True)
-                adv_cols = [adv_cols]
-            else:
-                cs = circuits.halo2lib_shape()
-                fixed_cols, adv_cols, copies = circuits.halo2lib_witness(cs, pk_, inst, min(16, pk_ - 2), 500, seed=1)
-            t_witness = time.perf_counter() - t0
-            E = plonk.DeviceEngine(be, srs, pk_, cs.degree())
-            t0 = time.perf_counter()
-            pkey = plonk.keygen(E, cs, pk_, fixed_cols, copies)
-            E.sync(); t_keygen = time.perf_counter() - t0
-            runs = []
-            for rep in range(2):                              # the second pass is the warm one (lazy kernel loading, allocator)
-                stages = {}
-                t0 = time.perf_counter()
-                proof = plonk.create_proof(E, pkey, [inst], adv_cols, draw, EvmTranscriptWrite(pkey.vk_digest), stages)
-                E.sync(); runs.append((time.perf_counter() - t0, stages))
-            proofs[name] = {"k": pk_, "advice_columns": cs.num_advice, "lookups": len(cs.lookups), "permutation_columns": len(cs.permutation), "degree": cs.degree(),
-                            "create_proof_s": runs[1][0], "first_create_proof_s": runs[0][0], "keygen_s": t_keygen, "srs_setup_and_tables_s": t_srs,
-                            "synthetic_witness_python_s": t_witness, "proof_bytes": len(proof), "stages_s": {a: round(b, 4) for a, b in runs[1][1].items()}}
-            del E, pkey, srs, fixed_cols, adv_cols
+    if not args.no_prove and args.impl == "ours" and world == 1:
+        try:
+            from spectre_b200 import circuits, plonk
+            from spectre_b200.transcript import EvmTranscriptWrite
+            if "dev_sets" in dir():
+                del dev_sets
             torch.cuda.empty_cache()
-        proofs["sync_step_compressed_shape_total_s"] = proofs["sync_step_shape"]["create_proof_s"] + proofs["aggregation_shape"]["create_proof_s"]
-        proofs["what"] = ("create_proof wall seconds, warm second pass: witness H2D, blinding, every commitment, evaluate_h, evaluations, SHPLONK, Keccak transcript; "
-                          "host driver in Python; synthetic witnesses with full columns; constraint-system shapes per SURVEY.md section 8 (aggregation: read off "
-                          "the committed verifier contract; sync-step: estimate from the pinning JSON)")
-        line["proof"] = proofs
+            g = np.random.default_rng(7)
+
+            def draw(count):
+                a = g.integers(0, 1 << 63, size=(count, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 60) - 1)
+                return a
+            proofs = {}
+            for name, pk_ in (("sync_step_shape", args.prove_k_step), ("aggregation_shape", args.prove_k)):
+                t0 = time.perf_counter()
+                srs = halo2.ParamsKZG.setup(be, pk_, plonk.fr_mont(0x5eed7a75)).precompute()   # any secret: timings do not depend on it
+                torch.cuda.synchronize(); t_srs = time.perf_counter() - t0
+                inst = list(range(1, 15))
+                t0 = time.perf_counter()
+                if name == "aggregation_shape":
+                    cs = circuits.aggregation_shape()
+                    fixed_cols, adv_cols, copies = circuits.aggregation_witness(cs, pk_, inst, min(19, pk_ - 2), 2000, seed=1, dense=True)
+                    adv_cols = [adv_cols]
+                else:
+                    cs = circuits.halo2lib_shape()
+                    fixed_cols, adv_cols, copies = circuits.halo2lib_witness(cs, pk_, inst, min(16, pk_ - 2), 500, seed=1)
+                t_witness = time.perf_counter() - t0
+                E = plonk.DeviceEngine(be, srs, pk_, cs.degree())
+                t0 = time.perf_counter()
+                pkey = plonk.keygen(E, cs, pk_, fixed_cols, copies)
+                E.sync(); t_keygen = time.perf_counter() - t0
+                runs = []
+                for rep in range(2):                              # the second pass is the warm one (lazy kernel loading, allocator)
+                    stages = {}
+                    t0 = time.perf_counter()
+                    proof = plonk.create_proof(E, pkey, [inst], adv_cols, draw, EvmTranscriptWrite(pkey.vk_digest), stages)
+                    E.sync(); runs.append((time.perf_counter() - t0, stages))
+                proofs[name] = {"k": pk_, "advice_columns": cs.num_advice, "lookups": len(cs.lookups), "permutation_columns": len(cs.permutation), "degree": cs.degree(),
+                                "create_proof_s": runs[1][0], "first_create_proof_s": runs[0][0], "keygen_s": t_keygen, "srs_setup_and_tables_s": t_srs,
+                                "synthetic_witness_python_s": t_witness, "proof_bytes": len(proof), "stages_s": {a: round(b, 4) for a, b in runs[1][1].items()}}
+                del E, pkey, srs, fixed_cols, adv_cols
+                torch.cuda.empty_cache()
+            proofs["sync_step_compressed_shape_total_s"] = proofs["sync_step_shape"]["create_proof_s"] + proofs["aggregation_shape"]["create_proof_s"]
+            proofs["what"] = ("create_proof wall seconds, warm second pass: witness H2D, blinding, every commitment, evaluate_h, evaluations, SHPLONK, Keccak transcript; "
+                              "host driver in Python; synthetic witnesses with full columns; constraint-system shapes per SURVEY.md section 8 (aggregation: read off "
+                              "the committed verifier contract; sync-step: estimate from the pinning JSON)")
+            line["proof"] = proofs
+        except Exception as e:   # the MSM line must survive a failure of this optional section
+            line["proof"] = {"error": repr(e)}
 
     # ---- CPU baseline (oracle port of best_multiexp) on this box's cores, bounded sample ----------------------
     if not args.no_cpu_baseline and world == 1:
