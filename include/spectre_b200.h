@@ -165,6 +165,11 @@ int spb_batch_invert_dev(spb_ctx* ctx, spb_fr* d_a, size_t n);
 int spb_eval_polynomial_dev(spb_ctx* ctx, const spb_fr* d_poly, size_t n, const spb_fr* point, spb_fr* out);
 int spb_kate_division_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, const spb_fr* b, spb_fr* d_q);
 int spb_grand_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* d_z);
+/* row-sharded grand product: each rank takes spb_product_dev of its rows, the 32-byte totals are
+ * exchanged, and the rank scans its rows seeded with the product of the totals before it:
+ * d_z[i] = init * prod_{j<i} d_a[j]. */
+int spb_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* out);
+int spb_grand_product_seeded_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, const spb_fr* init, spb_fr* d_z);
 int spb_vec_mul_dev(spb_ctx* ctx, spb_fr* d_a, const spb_fr* d_b, size_t n);
 int spb_vec_axpy_dev(spb_ctx* ctx, spb_fr* d_y, const spb_fr* alpha, const spb_fr* d_x, size_t n);
 int spb_vec_scale_dev(spb_ctx* ctx, spb_fr* d_a, const spb_fr* alpha, size_t n);

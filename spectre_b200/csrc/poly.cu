@@ -85,6 +85,20 @@ __global__ void __launch_bounds__(1024) carry_product_kernel(Fr* part, uint64_t 
   Fr run = tid ? sh[tid - 1] : fp_one<FrParams>();
   for (uint64_t i = lo; i < hi; i++) { Fr t = part[i]; part[i] = run; run = fp_mul(run, t); }
 }
+// out[0] = prod of part[0..m): one block (row-sharded grand products exchange this one value per rank)
+__global__ void __launch_bounds__(1024) total_product_kernel(const Fr* part, uint64_t m, Fr* out) {
+  __shared__ Fr sh[1024];
+  const uint32_t tid = threadIdx.x;
+  Fr local = fp_one<FrParams>();
+  for (uint64_t i = tid; i < m; i += 1024) local = fp_mul(local, part[i]);
+  sh[tid] = local;
+  __syncthreads();
+  for (uint32_t stride = 512; stride >= 1; stride >>= 1) {
+    if (tid < stride) sh[tid] = fp_mul(sh[tid], sh[tid + stride]);
+    __syncthreads();
+  }
+  if (tid == 0) out[0] = sh[0];
+}
 // Kate: chunk recurrence t_c = head_c + B_c * t_{c+1}, t_m = 0, B_c = b^64 except the last chunk (b_last).
 // carry[c] <- t_{c+1}. Affine maps (H, B): t_lo = H + B * t_hi compose associatively, scanned from the right.
 __global__ void __launch_bounds__(512) carry_kate_kernel(const Fr* heads, Fr* carry, uint64_t m, Fr b_chunk, Fr b_last) {
@@ -347,6 +361,33 @@ int spb_grand_product(spb_ctx* ctx, const spb_fr* a, size_t n, spb_fr* z) {
   SPB_TRY(dev_grand_product(ctx, d, da, n, dz, fp_one<FrParams>()));
   SPB_CUDA(ctx, cudaMemcpyAsync(z, dz, n * 32, cudaMemcpyDeviceToHost, d.stream));
   SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+
+int spb_grand_product_seeded_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, const spb_fr* init, spb_fr* d_z) {
+  if (!ctx || !d_a || !d_z || !init) return SPB_ERR_ARG;
+  if (!n) return 0;
+  SPB_ENTER(ctx);
+  Fr seed; memcpy(&seed, init, 32);
+  SPB_TRY(dev_grand_product(ctx, d, (const Fr*)d_a, n, (Fr*)d_z, seed));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+int spb_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* out) {
+  if (!ctx || !out || (n && !d_a)) return SPB_ERR_ARG;
+  SPB_ENTER(ctx);
+  Fr total = fp_one<FrParams>();
+  if (n) {
+    size_t m = (n + kScanChunk - 1) / kScanChunk;
+    Fr* dp = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32 + 32);
+    if (!dp) return SPB_ERR_OOM;
+    chunk_product_kernel<<<nblk(m, 128), 128, 0, d.stream>>>((const Fr*)d_a, n, dp);
+    total_product_kernel<<<1, 1024, 0, d.stream>>>(dp, m, dp + 2 * m);
+    ctx->n_kernel_launches += 2;
+    SPB_CUDA(ctx, cudaMemcpyAsync(&total, dp + 2 * m, 32, cudaMemcpyDeviceToHost, d.stream));
+    SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  }
+  memcpy(out, &total, 32);
   return 0;
 }
 

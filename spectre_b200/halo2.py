@@ -211,6 +211,14 @@ class Backend:
     def grand_product_dev(self, d_a, n, d_z):
         self.check(self.lib.spb_grand_product_dev(self.ctx, _p(d_a), ctypes.c_size_t(n), _p(d_z)), "spb_grand_product_dev")
 
+    def product_dev(self, d_a, n):
+        out = np.empty(4, dtype=np.uint64)
+        self.check(self.lib.spb_product_dev(self.ctx, _p(d_a), ctypes.c_size_t(n), _p(out)), "spb_product_dev")
+        return out
+
+    def grand_product_seeded_dev(self, d_a, n, init, d_z):
+        self.check(self.lib.spb_grand_product_seeded_dev(self.ctx, _p(d_a), ctypes.c_size_t(n), _p(_fr_array(init, 1)), _p(d_z)), "spb_grand_product_seeded_dev")
+
     def vec_mul_dev(self, d_a, d_b, n):
         self.check(self.lib.spb_vec_mul_dev(self.ctx, _p(d_a), _p(d_b), ctypes.c_size_t(n)), "spb_vec_mul_dev")
 

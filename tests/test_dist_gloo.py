@@ -60,3 +60,53 @@ def test_shard_ranges_cover():
             spans = [spb_dist.shard_range(n, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def _scan_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from spectre_b200 import dist as spb_dist
+    orc.build(); orc.lib()
+    R = orc.R_MOD
+    a = orc.fr_ints(orc.fr_random_chacha(n, 0x5eed0777))
+    lo, hi = spb_dist.shard_range(n, rank, world)
+    local = a[lo:hi]
+    z = {}
+
+    def local_total():                      # on the box: spb_product_dev
+        p = 1
+        for v in local:
+            p = p * v % R
+        return orc.fr([p])[0]
+
+    def seeded_scan(seed):                  # on the box: spb_grand_product_seeded_dev
+        run = orc.fr_ints(seed.reshape(1, 4))[0]
+        out = []
+        for v in local:
+            out.append(run); run = run * v % R
+        z["rows"] = out
+    init = orc.fr([7])[0]
+    _, total = spb_dist.sharded_grand_product(local_total, seeded_scan, rank, world, init=init)
+    want, run = [], 7
+    for v in a:
+        want.append(run); run = run * v % R
+    ok = z["rows"] == want[lo:hi] and orc.fr_ints(total.reshape(1, 4))[0] == run
+    q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_grand_product_world2():
+    """SURVEY.md 8e "grand product": one all_gather of the ranks' 32-byte totals, then a seeded local scan."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_scan_worker, args=(r, 2, port, 1001, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True and q.get(timeout=5) is True

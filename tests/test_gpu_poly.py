@@ -80,3 +80,28 @@ def test_proof_replay_tiny_runs(be, orc):
     out = replay.replay(be, "tiny_k10", orc.srs_tau())
     assert out["msm_count"] == 3 + 2 + 3 + 1 + 3 + 2 and out["total_s"] > 0
     assert set(out["stages_s"]) >= {"3_advice_commit", "4_lookup_permute_and_commit", "7_lagrange_to_coeff", "8a_coeff_to_extended", "8b_evaluate_h", "9_vanishing_construct_commit", "11_shplonk"}
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 5000, 70001])
+def test_row_sharded_grand_product_pieces(be, orc, n):
+    """spb_product_dev / spb_grand_product_seeded_dev: three row blocks scanned with exchanged totals give the same
+    running product as one scan over all rows (the SURVEY 8e recipe, the collective replaced by a loop)."""
+    import torch
+    a = orc.fr_random_chacha(n, 0x5eed0900 + n)
+    want = be.grand_product(a)
+    bounds = [0, n // 3, (2 * n) // 3, n]
+    da = torch.from_numpy(a.view(np.int64)).cuda()
+    dz = torch.empty_like(da)
+    R = pyref.R_MOD
+    seed = 1
+    for lo, hi in zip(bounds, bounds[1:]):
+        blk = da[lo:hi]
+        if hi > lo:
+            be.grand_product_seeded_dev(blk.data_ptr(), hi - lo, orc.fr([seed])[0], dz[lo:hi].data_ptr())
+        total = orc.fr_ints(be.product_dev(blk.data_ptr() if hi > lo else 0, hi - lo).reshape(1, 4))[0]
+        prod = 1
+        for v in orc.fr_ints(a[lo:hi]):
+            prod = prod * v % R
+        assert total == prod
+        seed = seed * total % R
+    assert np.array_equal(dz.cpu().numpy().view(np.uint64), want)
