@@ -353,9 +353,14 @@ def main():
             torch.cuda.empty_cache()
             g = np.random.default_rng(7)
 
-            def draw(count):
-                a = g.integers(0, 1 << 63, size=(count, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 60) - 1)
-                return a
+            class Draw:                                      # blinding rows from the host stream, the random polynomial on the device
+                def __call__(self, count):
+                    a = g.integers(0, 1 << 63, size=(count, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 60) - 1)
+                    return a
+
+                def device_rows(self, E, count):
+                    return E.random_rows(count)
+            draw = Draw()
             proofs = {}
             for name, pk_ in (("sync_step_shape", args.prove_k_step), ("aggregation_shape", args.prove_k)):
                 t0 = time.perf_counter()

@@ -181,6 +181,22 @@ class ConstraintSystem:
         return p.finish()
 
 
+def uniform_residues(torch, rows, device, generator=None):
+    """(rows, 4) int64 tensor of uniformly random Fr elements generated ON `device` (rejection sampling of 254-bit
+    candidates against r; a uniform residue is a uniform field element in Montgomery form too). Used for the vanishing
+    argument's random polynomial: at K = 23 that is 256 MiB that never has to be drawn on the host or cross PCIe.
+    Candidates whose top limb equals r's top limb are rejected outright (probability 2^-62)."""
+    r3 = R_MOD >> 192
+    out, have = [], 0
+    while have < rows:
+        m = int((rows - have) * 1.4) + 64
+        c = torch.randint(-(1 << 63), (1 << 63) - 1, (m, 4), dtype=torch.int64, device=device, generator=generator)
+        c[:, 3] = torch.randint(0, 1 << 62, (m,), dtype=torch.int64, device=device, generator=generator)
+        keep = c[c[:, 3] < r3]
+        out.append(keep); have += keep.shape[0]
+    return torch.cat(out)[:rows].contiguous()
+
+
 # ---- the engine bound to libspectre_b200.so -----------------------------------------------------------------------
 class DeviceEngine:
     """Buffers are torch int64 tensors of shape (rows, 4) on the context's first device (PyTorch = device memory only)."""
@@ -203,6 +219,7 @@ class DeviceEngine:
         if rows.shape[0]:
             b[start:start + rows.shape[0]] = self.upload(rows)
     def read_rows(self, b, start, count): return self.download(b[start:start + count])
+    def random_rows(self, rows, generator=None): return uniform_residues(self.torch, rows, self.dev, generator)
     def sync(self): self.torch.cuda.synchronize()
 
     # commitments -> affine integer pairs
@@ -475,7 +492,8 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
     lap("lookup_product")
 
     # 6. vanishing argument: random polynomial
-    random_poly = E.upload(rng(n))
+    # an rng that offers device_rows(E, count) draws the n coefficients on the device; otherwise they come from the host stream
+    random_poly = rng.device_rows(E, n) if hasattr(rng, "device_rows") else E.upload(rng(n))
     rng(1)
     transcript.write_ec_point(E.commit(G, [random_poly], n)[0])
     lap("vanishing_commit")

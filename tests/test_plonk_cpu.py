@@ -123,3 +123,15 @@ def test_halo2lib_sync_step_shape_proof_verifies(orc):
     pk, proof, _ = prove(E, cs, k, fixed, adv, copies, instances, seed=21)
     tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
     assert plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, [instances], proof, tau)
+
+
+def test_device_side_blinding_sampler_is_in_range():
+    """uniform_residues (the on-device generator of the vanishing argument's random polynomial), run on torch's CPU device"""
+    import torch
+    g = torch.Generator().manual_seed(5)
+    t = plonk.uniform_residues(torch, 50000, "cpu", g)
+    a = t.numpy().view(np.uint64)
+    assert a.shape == (50000, 4)
+    vals = [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in a]
+    assert max(vals) < plonk.R_MOD and len(set(vals)) == len(vals)
+    assert 0.70 < sum(v > plonk.R_MOD // 4 for v in vals) / len(vals) < 0.80      # uniform over [0, r): three quarters above r/4

@@ -31,9 +31,14 @@ def main():
     pk = plonk.keygen(E, cs, k, fixed, copies)
     g = np.random.default_rng(7)
 
-    def draw(count):
-        a = g.integers(0, 1 << 63, size=(count, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 60) - 1)
-        return a
+    class Draw:
+        def __call__(self, count):
+            a = g.integers(0, 1 << 63, size=(count, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 60) - 1)
+            return a
+
+        def device_rows(self, E, count):
+            return E.random_rows(count)
+    draw = Draw() if os.environ.get("SPB_HOST_RNG", "0") == "0" else Draw().__call__
     for rep in range(reps):
         stages = {}
         t0 = time.perf_counter()
