@@ -50,6 +50,7 @@ struct spb_ctx {
   uint64_t n_kernel_launches = 0;
   float last_kernel_ms = 0.f;
   uint64_t last_msm_adds = 0;  // G1 additions of the last MSM call / batch
+  bool shplonk_slots_busy = false;  // the context's SHPLONK workspace slots are held by an open spb_shplonk handle
   float msm_stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};  // count, scan, scatter, accumulate, stitch, segment, window (device 0)
 };
 

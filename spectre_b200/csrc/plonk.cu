@@ -112,6 +112,8 @@ int fraction_product(spb_ctx* ctx, DeviceState& d, Fr* num, Fr* den, size_t n, c
 
 // ---- SHPLONK state kept between the two transcript round trips ------------------------------------------------------
 struct spb_shplonk {
+  spb_ctx* ctx = nullptr;
+  bool from_slots = false;      // buffers are the context's grow-only workspace slots (one open handle at a time), else cudaMalloc'd
   int device = 0;
   size_t n = 0;
   const spb_srs* srs = nullptr;
@@ -168,10 +170,15 @@ bool contains(const std::vector<Fr>& v, const Fr& x) {
   for (const Fr& e : v) if (fp_eq(e, x)) return true;
   return false;
 }
+// call with the context lock held
 void shplonk_release(spb_shplonk* s) {
   if (!s) return;
-  cudaSetDevice(s->device);
-  cudaFree(s->d_h); cudaFree(s->d_tmp[0]); cudaFree(s->d_tmp[1]); cudaFree((void*)s->d_ptrs); cudaFree(s->d_w);
+  if (s->from_slots) {
+    s->ctx->shplonk_slots_busy = false;
+  } else {
+    cudaSetDevice(s->device);
+    cudaFree(s->d_h); cudaFree(s->d_tmp[0]); cudaFree(s->d_tmp[1]); cudaFree((void*)s->d_ptrs); cudaFree(s->d_w);
+  }
   delete s;
 }
 
@@ -260,18 +267,7 @@ int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_
     total += rs.n_polys;
   }
   spb_shplonk* s = new spb_shplonk();
-  {
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    DeviceState& d = ctx->dev[0];
-    s->device = d.device; s->n = n; s->srs = srs; s->n_polys = total; s->y = fr_load(y); s->v = fr_load(v);
-    cudaSetDevice(d.device);
-    cudaError_t e = cudaMalloc(&s->d_h, n * 32);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_tmp[0], n * 32);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_tmp[1], n * 32);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ptrs, (size_t)total * sizeof(void*));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_w, (size_t)total * 32);
-    if (e != cudaSuccess) { shplonk_release(s); return set_error(ctx, SPB_ERR_OOM, "spb_shplonk_begin_dev: %s", cudaGetErrorString(e)); }
-  }
+  s->ctx = ctx; s->n = n; s->srs = srs; s->n_polys = total; s->y = fr_load(y); s->v = fr_load(v);
   const double t_alloc = now_s();
   // host side: the sets, the low-degree equivalents R_ij and the super point set
   std::vector<const Fr*> ptrs; ptrs.reserve(total);
@@ -281,7 +277,7 @@ int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_
     st.n_polys = rs.n_polys;
     for (uint32_t p = 0; p < rs.n_points; p++) {
       Fr pt = fr_load(rs.points + p);
-      if (contains(st.points, pt)) { shplonk_release(s); return set_error(ctx, SPB_ERR_ARG, "spb_shplonk_begin_dev: repeated point in rotation set %u", i); }
+      if (contains(st.points, pt)) { delete s; return set_error(ctx, SPB_ERR_ARG, "spb_shplonk_begin_dev: repeated point in rotation set %u", i); }
       st.points.push_back(pt);
       if (!contains(s->super_points, pt)) s->super_points.push_back(pt);
     }
@@ -301,7 +297,25 @@ int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_
     DeviceState& d = ctx->dev[0];
     auto fail = [&](int code) { shplonk_release(s); return code; };
 #define SHP_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { shplonk_release(s); return set_error(ctx, SPB_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
+    s->device = d.device;
     SHP_CUDA(cudaSetDevice(d.device));
+    // workspace: the context's grow-only slots when no other handle holds them (no allocation in the steady state)
+    if (!ctx->shplonk_slots_busy) {
+      s->d_h = (Fr*)slot(ctx, d, "shplonk_h", n * 32);
+      s->d_tmp[0] = (Fr*)slot(ctx, d, "shplonk_t0", n * 32);
+      s->d_tmp[1] = (Fr*)slot(ctx, d, "shplonk_t1", n * 32);
+      s->d_ptrs = (const Fr**)slot(ctx, d, "shplonk_ptrs", (size_t)total * sizeof(void*));
+      s->d_w = (Fr*)slot(ctx, d, "shplonk_w", (size_t)total * 32);
+      if (!s->d_h || !s->d_tmp[0] || !s->d_tmp[1] || !s->d_ptrs || !s->d_w) { delete s; return SPB_ERR_OOM; }
+      s->from_slots = true; ctx->shplonk_slots_busy = true;
+    } else {
+      cudaError_t e = cudaMalloc(&s->d_h, n * 32);
+      if (e == cudaSuccess) e = cudaMalloc(&s->d_tmp[0], n * 32);
+      if (e == cudaSuccess) e = cudaMalloc(&s->d_tmp[1], n * 32);
+      if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ptrs, (size_t)total * sizeof(void*));
+      if (e == cudaSuccess) e = cudaMalloc(&s->d_w, (size_t)total * 32);
+      if (e != cudaSuccess) { shplonk_release(s); return set_error(ctx, SPB_ERR_OOM, "spb_shplonk_begin_dev: %s", cudaGetErrorString(e)); }
+    }
     SHP_CUDA(cudaMemcpyAsync((void*)s->d_ptrs, ptrs.data(), (size_t)total * sizeof(void*), cudaMemcpyHostToDevice, d.stream));
     SHP_CUDA(cudaMemsetAsync(s->d_h, 0, n * 32, d.stream));
     uint32_t base = 0;
