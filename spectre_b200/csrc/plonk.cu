@@ -46,10 +46,14 @@ struct PermTermArgs {
 }  // namespace
 
 // num[i] = prod_c (v_c[i] + beta * delta^(first_col + c) * omega^i + gamma),  den[i] = prod_c (v_c[i] + beta * sigma_c[i] + gamma)
+// omega^i = omega^(256 * block) * omega^thread: one long power per block (thread 0), an 8-bit power per thread.
 __global__ void __launch_bounds__(256) perm_terms_kernel(PermTermArgs a, uint64_t n, Fr* num, Fr* den) {
+  __shared__ Fr block_base;
+  if (threadIdx.x == 0) block_base = fp_pow_u64(a.omega, blockIdx.x * (uint64_t)blockDim.x);
+  __syncthreads();
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fr term = fp_mul(a.delta_start, fp_pow_u64(a.omega, i));
+  Fr term = fp_mul(a.delta_start, fp_mul(block_base, fp_pow_u64(a.omega, threadIdx.x)));
   Fr nu = fp_one<FrParams>(), de = fp_one<FrParams>();
   for (uint32_t c = 0; c < a.n_cols; c++) {
     Fr v = ntt_ld_stream(a.values[c] + i);
