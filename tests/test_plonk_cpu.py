@@ -83,27 +83,32 @@ def test_transcript_layout_matches_the_verifier_contract(kats):
     assert [int(d) for d in want["permutation_deltas"]] == [plonk.DELTA, plonk.DELTA * plonk.DELTA % plonk.R_MOD]
 
 
+def _fixtures():
+    import glob, os
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "aggregation_k*_proof.json")))
+
+
 @pytest.mark.skipif(not __import__("tests.yul_harness", fromlist=["x"]).available(), reason="reference tree not present")
-def test_reference_verifier_contract_accepts_the_k23_fixture(orc, kats):
-    """contracts/snark-verifiers/sync_step_verifier.sol, interpreted as it stands in the reference tree, accepts the
-    committed K = 23 proof (VK commitments substituted, pairing decided with the known tau: tests/yul_harness.py), and
-    rejects it after a one-bit change or with a different public input."""
-    import json, os
+@pytest.mark.parametrize("path", _fixtures(), ids=lambda p: p.split("_")[-2])
+def test_reference_verifier_contract_accepts_the_fixture(orc, kats, path):
+    """contracts/snark-verifiers/{sync_step,committee_update}_verifier.sol, interpreted as they stand in the reference tree,
+    accept the committed proofs (VK commitments substituted, pairing decided with the known tau: tests/yul_harness.py), and
+    reject them after a one-bit change or with a different public input."""
+    import json
     from tests import yul_harness
-    path = os.path.join(os.path.dirname(__file__), "golden", "aggregation_k23_proof.json")
     with open(path) as f:
         fx = json.load(f)
+    contract = fx.get("contract", "sync_step_verifier")
     instances = [int(v, 16) for v in fx["instances"]]
     proof = bytes.fromhex(fx["proof"])
     vk_points = [(int(x, 16), int(y, 16)) for x, y in fx["vk_points"]]
     tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
-    ok, m = yul_harness.run_contract("sync_step_verifier", instances, proof, vk_points, tau, kats)
+    ok, m = yul_harness.run_contract(contract, instances, proof, vk_points, tau, kats)
     assert ok and m.pairing_calls == 1 and m.precompile_counts[7] == 21
     bad = bytearray(proof); bad[11 * 64 - 1 + 32 * 3] ^= 1         # one bit of an evaluation
-    assert not yul_harness.run_contract("sync_step_verifier", instances, bytes(bad), vk_points, tau, kats)[0]
-    assert not yul_harness.run_contract("sync_step_verifier", instances[:13] + [instances[13] + 1], proof, vk_points, tau, kats)[0]
+    assert not yul_harness.run_contract(contract, instances, bytes(bad), vk_points, tau, kats)[0]
+    assert not yul_harness.run_contract(contract, instances[:-1] + [instances[-1] + 1], proof, vk_points, tau, kats)[0]
     # and the independent Python verifier agrees on the same bytes
-    from spectre_b200 import circuits as plonk_circuits
     from tests import plonk_verifier
     cs = plonk_circuits.aggregation_shape()
     assert plonk_verifier.verify(cs, fx["k"], int(fx["vk_digest"]), vk_points[:4], vk_points[4:], [instances], proof, tau)
