@@ -186,9 +186,20 @@ def test_device_proof_is_byte_identical_to_the_oracle_proof_and_verifies(be, orc
     assert plonk_verifier.verify(cs, k, pk_d.vk_digest, pk_d.fixed_commitments, pk_d.sigma_commitments, [instances], proof_d, tau)
 
 
-def test_k23_proof_equals_the_contract_accepted_fixture(be, orc, kats):
-    """K = 23: the device regenerates, byte for byte, the proof in tests/golden/aggregation_k23_proof.json -- the one the
-    reference's sync_step verifier contract accepted when replayed by tests/yul_harness.py (tools/make_k23_fixture.py)."""
+def _fixture_paths():
+    import glob
+    import os
+    paths = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "aggregation_k*_proof.json")))
+    if os.environ.get("SPB_TEST_K24", "0") == "0":           # the K = 24 regeneration (about a minute) is opt-in
+        paths = [p for p in paths if "k24" not in p]
+    return paths
+
+
+@pytest.mark.parametrize("path", _fixture_paths(), ids=lambda p: p.split("_")[-2])
+def test_k23_proof_equals_the_contract_accepted_fixture(be, orc, kats, path):
+    """K = 23 / K = 24: the device regenerates, byte for byte, the proofs in tests/golden/aggregation_k2{3,4}_proof.json -- the
+    ones the reference's sync_step / committee_update verifier contracts accepted when replayed by tests/yul_harness.py
+    (tools/make_k23_fixture.py)."""
     import json
     import os
     import time
@@ -197,7 +208,6 @@ def test_k23_proof_equals_the_contract_accepted_fixture(be, orc, kats):
     from spectre_b200.transcript import EvmTranscriptWrite
     from spectre_b200 import circuits as plonk_circuits
     from tests.plonk_oracle_engine import SeededRng
-    path = os.path.join(os.path.dirname(__file__), "golden", "aggregation_k23_proof.json")
     with open(path) as f:
         fx = json.load(f)
     k = fx["k"]
@@ -214,8 +224,12 @@ def test_k23_proof_equals_the_contract_accepted_fixture(be, orc, kats):
     t2 = time.perf_counter()
     print("K=%d keygen %.2fs create_proof %.2fs %s" % (k, t1 - t0, t2 - t1, {a: round(b, 3) for a, b in timings.items()}))
     assert [[hex(x), hex(y)] for x, y in pk.fixed_commitments + pk.sigma_commitments] == fx["vk_points"]
-    assert pk.fixed_commitments[1] == tuple(int(v, 16) for v in kats["range_table_commit_k23_bits19"]["xy"])   # the contract's own VK constant
+    kat = "range_table_commit_k%d_bits%d" % (k, fx["lookup_bits"])
+    assert pk.fixed_commitments[1] == tuple(int(v, 16) for v in kats[kat]["xy"])                                # the contract's own VK constant
     assert proof.hex() == fx["proof"]
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/k23_proof_timings.json", "w") as f:
+    del E, pk, params
+    import torch
+    torch.cuda.empty_cache()
+    with open("gpurun_out/k%d_proof_timings.json" % k, "w") as f:
         json.dump({"k": k, "keygen_s": t1 - t0, "create_proof_s": t2 - t1, "stages": timings}, f)
