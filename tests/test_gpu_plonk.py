@@ -189,10 +189,7 @@ def test_device_proof_is_byte_identical_to_the_oracle_proof_and_verifies(be, orc
 def _fixture_paths():
     import glob
     import os
-    paths = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "aggregation_k*_proof.json")))
-    if os.environ.get("SPB_TEST_K24", "0") == "0":           # the K = 24 regeneration (about a minute) is opt-in
-        paths = [p for p in paths if "k24" not in p]
-    return paths
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "aggregation_k*_proof.json")))
 
 
 @pytest.mark.parametrize("path", _fixture_paths(), ids=lambda p: p.split("_")[-2])
