@@ -230,3 +230,43 @@ def test_k23_proof_equals_the_contract_accepted_fixture(be, orc, kats, path):
     torch.cuda.empty_cache()
     with open("gpurun_out/k%d_proof_timings.json" % k, "w") as f:
         json.dump({"k": k, "keygen_s": t1 - t0, "create_proof_s": t2 - t1, "stages": timings}, f)
+
+
+def test_proof_with_msm_sharded_over_two_devices_if_available(orc):
+    """One context driving two GPUs: every commitment of create_proof is an MSM sharded by point range (scalar ranges
+    peer-copied over NVLink), the polynomial arithmetic stays on the first device; the proof bytes do not change."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from spectre_b200 import circuits, halo2, plonk
+    from spectre_b200.transcript import EvmTranscriptWrite
+    from tests.plonk_oracle_engine import OracleEngine, SeededRng
+    k, instances = 12, [3, 1, 4]
+    cs = circuits.halo2lib_shape(4, 1)
+    fixed, adv, copies = circuits.halo2lib_witness(cs, k, instances, lookup_bits=5, groups=200, num_gate_advice=4, num_lookup_advice=1)
+    be2 = halo2.Backend([0, 1])
+    try:
+        proofs = []
+        for E in (plonk.DeviceEngine(be2, halo2.ParamsKZG.setup(be2, k, orc.srs_tau()).precompute(), k, cs.degree()), OracleEngine(k, cs.degree())):
+            pk = plonk.keygen(E, cs, k, fixed, copies)
+            proofs.append(plonk.create_proof(E, pk, [instances], adv, SeededRng(5), EvmTranscriptWrite(pk.vk_digest)))
+        assert proofs[0] == proofs[1]
+    finally:
+        be2.close()
+
+
+def test_lookup_violation_is_reported_like_upstream(be, orc):
+    """an advice value outside the table: permute_expression_pair fails (upstream: Error::ConstraintSystemFailure) and
+    create_proof raises instead of producing a proof"""
+    from spectre_b200 import circuits, plonk
+    from spectre_b200.halo2 import BackendError, ParamsKZG
+    from spectre_b200.transcript import EvmTranscriptWrite
+    from tests.plonk_oracle_engine import SeededRng
+    k, instances = 7, [1]
+    cs = circuits.aggregation_shape()
+    fixed, adv, copies = circuits.aggregation_witness(cs, k, instances, lookup_bits=3, groups=10)
+    adv[4] = plonk.fr_mont(99)                                  # a looked-up cell (q_lookup = 1 on row 4) outside [0, 8)
+    E = plonk.DeviceEngine(be, ParamsKZG.setup(be, k, orc.srs_tau()), k, cs.degree())
+    pk = plonk.keygen(E, cs, k, fixed, copies)
+    with pytest.raises(BackendError):
+        plonk.create_proof(E, pk, [instances], [adv], SeededRng(2), EvmTranscriptWrite(pk.vk_digest))

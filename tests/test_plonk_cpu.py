@@ -140,3 +140,15 @@ def test_device_side_blinding_sampler_is_in_range():
     vals = [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in a]
     assert max(vals) < plonk.R_MOD and len(set(vals)) == len(vals)
     assert 0.70 < sum(v > plonk.R_MOD // 4 for v in vals) / len(vals) < 0.80      # uniform over [0, r): three quarters above r/4
+
+
+def test_lookup_violation_is_reported_like_upstream(orc):
+    """an advice value outside the table makes commit_permuted fail (upstream: Error::ConstraintSystemFailure)"""
+    k, instances = 7, [1]
+    cs = plonk_circuits.aggregation_shape()
+    fixed, adv, copies = plonk_circuits.aggregation_witness(cs, k, instances, lookup_bits=3, groups=10)
+    adv[4] = plonk.fr_mont(99)
+    E = OracleEngine(k, cs.degree())
+    pk = plonk.keygen(E, cs, k, fixed, copies)
+    with pytest.raises(ValueError):
+        plonk.create_proof(E, pk, [instances], [adv], SeededRng(2), EvmTranscriptWrite(pk.vk_digest))
