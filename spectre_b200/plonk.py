@@ -461,7 +461,7 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
 
     # 4. permutation grand products, one per chunk of columns
     col_values = [{"fixed": pk.fixed_values, "advice": advice_values, "instance": inst_values}[kind][c] for kind, c in cs.permutation]
-    chunk = cs.chunk_len()
+    chunk = max(1, cs.chunk_len())                           # without permutation columns the degree can be below 3
     perm_z, last_z = [], fr_mont(1)
     for lo in range(0, len(col_values), chunk):
         hi = min(lo + chunk, len(col_values))

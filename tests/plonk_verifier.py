@@ -60,7 +60,7 @@ def verify(cs, k, vk_digest, fixed_commitments, sigma_commitments, instances, pr
     theta = T.squeeze_challenge()
     permuted_c = [(T.read_ec_point(), T.read_ec_point()) for _ in cs.lookups]
     beta = T.squeeze_challenge(); gamma = T.squeeze_challenge()
-    chunk = cs.chunk_len()
+    chunk = max(1, cs.chunk_len())
     n_sets = -(-len(cs.permutation) // chunk) if cs.permutation else 0
     perm_c = [T.read_ec_point() for _ in range(n_sets)]
     lookz_c = [T.read_ec_point() for _ in cs.lookups]

@@ -152,3 +152,60 @@ def test_lookup_violation_is_reported_like_upstream(orc):
     pk = plonk.keygen(E, cs, k, fixed, copies)
     with pytest.raises(ValueError):
         plonk.create_proof(E, pk, [instances], [adv], SeededRng(2), EvmTranscriptWrite(pk.vk_digest))
+
+
+@pytest.mark.parametrize("variant", ["no_lookup", "no_permutation", "gates_only_negative_rotation", "two_instance_columns"])
+def test_driver_edge_shapes(orc, variant):
+    """constraint systems without a lookup / without a permutation, a gate reaching back with rotation -1 and a fixed query
+    at rotation 1, two instance columns: proof accepted by the independent verifier"""
+    from spectre_b200.plonk import Advice, Const, ConstraintSystem, Fixed, Instance, Neg, Prod, Scaled, Sum
+    k = 6
+    n = 1 << k
+    R = plonk.R_MOD
+    rows = 40
+    import random
+    rng = random.Random(hash(variant) & 0xffff)
+    a = [rng.randrange(R) for _ in range(rows)]
+    if variant == "gates_only_negative_rotation":
+        # q(X) * (a(X) - 3*a(w^-1 X) - f(wX)) on rows 1..rows-1; f is a fixed column read one row ahead
+        f = [0] * n
+        for i in range(1, rows):
+            f[i + 1] = (a[i] - 3 * a[i - 1]) % R
+        q = [1 if 1 <= i < rows else 0 for i in range(n)]
+        cs = ConstraintSystem(2, 1, 0, [Prod(Fixed(0), Sum(Sum(Advice(0), Neg(Scaled(Advice(0, -1), 3))), Neg(Fixed(1, 1))))], [], [])
+        fixed, advice, copies, instances = [q, f], [a + [0] * (n - rows)], [], []
+    elif variant == "no_lookup":
+        # a * a = b with b copied from the instance column; permutation over (advice 0, advice 1, instance)
+        inst = [a[i] * a[i] % R for i in range(3)]
+        b = [a[i] * a[i] % R for i in range(rows)]
+        q = [1 if i < rows else 0 for i in range(n)]
+        cs = ConstraintSystem(1, 2, 1, [Prod(Fixed(0), Sum(Prod(Advice(0), Advice(0)), Neg(Advice(1))))], [], [("advice", 0), ("advice", 1), ("instance", 0)])
+        fixed, advice, instances = [q], [a + [0] * (n - rows), b + [0] * (n - rows)], [inst]
+        copies = [((1, i), (2, i)) for i in range(3)] + [((0, 5), (0, 6))]
+        advice[0][6] = advice[0][5]; advice[1][6] = advice[1][5]
+    elif variant == "no_permutation":
+        t = 8
+        table = list(range(t)) + [0] * (n - t)
+        small = [rng.randrange(t) for _ in range(rows)]
+        cs = ConstraintSystem(1, 1, 0, [], [([Sum(Advice(0), Const(0))], [Fixed(0)])], [])
+        fixed, advice, copies, instances = [table], [small + [0] * (n - rows)], [], []
+    else:
+        # a + i0 = b on row 0..2, b * i1 = c; instances in two columns, both in the permutation
+        i0, i1 = [rng.randrange(R) for _ in range(3)], [rng.randrange(R) for _ in range(3)]
+        bcol = [0] * n; ccol = [0] * n; acol = a + [0] * (n - rows)
+        x0 = [0] * n; x1 = [0] * n
+        for i in range(3):
+            x0[i], x1[i] = i0[i], i1[i]
+            bcol[i] = (acol[i] + i0[i]) % R; ccol[i] = bcol[i] * i1[i] % R
+        q = [1 if i < 3 else 0 for i in range(n)]
+        cs = ConstraintSystem(1, 5, 2, [Prod(Fixed(0), Sum(Sum(Advice(0), Advice(3)), Neg(Advice(1)))), Prod(Fixed(0), Sum(Prod(Advice(1), Advice(4)), Neg(Advice(2))))], [],
+                              [("advice", 3), ("advice", 4), ("instance", 0), ("instance", 1)])
+        fixed, advice, instances = [q], [acol, bcol, ccol, x0, x1], [i0, i1]
+        copies = [((0, i), (2, i)) for i in range(3)] + [((1, i), (3, i)) for i in range(3)]
+    to_m = lambda col: np.stack([plonk.fr_mont(v) for v in col]) if len(col) else np.zeros((n, 4), np.uint64)
+    E = OracleEngine(k, cs.degree())
+    pk = plonk.keygen(E, cs, k, [to_m(c) for c in fixed], copies)
+    T = EvmTranscriptWrite(pk.vk_digest)
+    proof = plonk.create_proof(E, pk, instances, [to_m(c) for c in advice], SeededRng(7), T)
+    tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
+    assert plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, instances, proof, tau)
