@@ -407,12 +407,17 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
             E.sync(); t = time.perf_counter(); timings[name] = timings.get(name, 0.0) + t - t_last[0]; t_last[0] = t
 
     # 1. vk, instances
+    if len(instances) != cs.num_instance:
+        raise ValueError("create_proof: %d instance columns given, the circuit has %d (upstream: Error::InvalidInstances)" % (len(instances), cs.num_instance))
+    if len(advice_columns) != cs.num_advice:
+        raise ValueError("create_proof: %d advice columns given, the circuit has %d" % (len(advice_columns), cs.num_advice))
     for col in instances:
         for v in col:
             transcript.common_scalar(v)                      # KZG: instances enter the transcript, no commitments
     inst_values = []
     for col in instances:
-        assert len(col) <= usable, "too many instances"     # upstream: Error::InstanceTooLarge
+        if len(col) > usable:
+            raise ValueError("create_proof: an instance column has more than %d values (upstream: Error::InstanceTooLarge)" % usable)
         b = E.alloc(n); E.write_rows(b, 0, fr_mont_rows(col)); inst_values.append(b)
     inst_polys = [E.clone(b) for b in inst_values]
     for p in inst_polys:

@@ -209,3 +209,18 @@ def test_driver_edge_shapes(orc, variant):
     proof = plonk.create_proof(E, pk, instances, [to_m(c) for c in advice], SeededRng(7), T)
     tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
     assert plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, instances, proof, tau)
+
+
+def test_create_proof_argument_errors(orc):
+    k = 6
+    cs = plonk_circuits.aggregation_shape()
+    fixed, adv, copies = plonk_circuits.aggregation_witness(cs, k, [1], lookup_bits=3, groups=4)
+    E = OracleEngine(k, cs.degree())
+    pk = plonk.keygen(E, cs, k, fixed, copies)
+    new_t = lambda: EvmTranscriptWrite(pk.vk_digest)
+    with pytest.raises(ValueError, match="InvalidInstances"):
+        plonk.create_proof(E, pk, [], [adv], SeededRng(1), new_t())
+    with pytest.raises(ValueError, match="InstanceTooLarge"):
+        plonk.create_proof(E, pk, [list(range(1 << k))], [adv], SeededRng(1), new_t())
+    with pytest.raises(ValueError, match="advice columns"):
+        plonk.create_proof(E, pk, [[1]], [adv, adv], SeededRng(1), new_t())
