@@ -95,6 +95,7 @@ def test_reference_verifier_contract_accepts_the_fixture(orc, kats, path):
     accept the committed proofs (VK commitments substituted, pairing decided with the known tau: tests/yul_harness.py), and
     reject them after a one-bit change or with a different public input."""
     import json
+    import os
     from tests import yul_harness
     with open(path) as f:
         fx = json.load(f)
@@ -108,6 +109,13 @@ def test_reference_verifier_contract_accepts_the_fixture(orc, kats, path):
     bad = bytearray(proof); bad[11 * 64 - 1 + 32 * 3] ^= 1         # one bit of an evaluation
     assert not yul_harness.run_contract(contract, instances, bytes(bad), vk_points, tau, kats)[0]
     assert not yul_harness.run_contract(contract, instances[:-1] + [instances[-1] + 1], proof, vk_points, tau, kats)[0]
+    # control: with the contract's own VK constants (the real circuit's fixed columns, not ours) the same proof must fail,
+    # and so must a wrong tau in the pairing decision
+    with open(os.path.join(yul_harness.REF_DIR, contract + ".sol")) as f:
+        own = yul_harness.vk_literals(f.read())
+    assert own[1] == vk_points[1] and own[0] != vk_points[0]      # only the range table coincides
+    assert not yul_harness.run_contract(contract, instances, proof, own, tau, kats)[0]
+    assert not yul_harness.run_contract(contract, instances, proof, vk_points, tau + 1, kats)[0]
     # and the independent Python verifier agrees on the same bytes
     from tests import plonk_verifier
     cs = plonk_circuits.aggregation_shape()
