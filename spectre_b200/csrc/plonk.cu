@@ -9,7 +9,7 @@
 // Every polynomial stays in HBM; what crosses the ABI per call is challenges, blinding values and 96-byte commitments.
 // All passes are HBM-streaming: algorithmic bytes per row = 32 B x (columns read + 1 written).
 #include "common.cuh"
-#include "ntt.cuh"
+#include "quotient.cuh"
 #include <string.h>
 #include <chrono>
 #include <stdlib.h>
@@ -33,43 +33,20 @@ inline Fr fr_omega(uint32_t k) {
   return w;
 }
 
-const uint32_t kMaxSetCols = 16;   // columns of one permutation set (chunk_len = degree - 2; halo2-lib circuits: 2..7)
-struct PermTermArgs {
-  const Fr* values[kMaxSetCols];
-  const Fr* sigma[kMaxSetCols];
-  uint32_t n_cols;
-  Fr beta, gamma, delta;
-  Fr delta_start;   // beta * delta^first_col
-  Fr omega;
-};
-
 }  // namespace
 
-// num[i] = prod_c (v_c[i] + beta * delta^(first_col + c) * omega^i + gamma),  den[i] = prod_c (v_c[i] + beta * sigma_c[i] + gamma)
-// omega^i = omega^(256 * block) * omega^thread: one long power per block (thread 0), an 8-bit power per thread.
+// omega^i = omega^(256 * block) * omega^thread: one long power per block (thread 0), an 8-bit power per thread; the row
+// bodies are perm_terms_row / lookup_terms_row in quotient.cuh.
 __global__ void __launch_bounds__(256) perm_terms_kernel(PermTermArgs a, uint64_t n, Fr* num, Fr* den) {
   __shared__ Fr block_base;
   if (threadIdx.x == 0) block_base = fp_pow_u64(a.omega, blockIdx.x * (uint64_t)blockDim.x);
   __syncthreads();
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr term = fp_mul(a.delta_start, fp_mul(block_base, fp_pow_u64(a.omega, threadIdx.x)));
-  Fr nu = fp_one<FrParams>(), de = fp_one<FrParams>();
-  for (uint32_t c = 0; c < a.n_cols; c++) {
-    Fr v = ntt_ld_stream(a.values[c] + i);
-    de = fp_mul(de, fp_add(fp_add(fp_mul(a.beta, ntt_ld_stream(a.sigma[c] + i)), a.gamma), v));
-    nu = fp_mul(nu, fp_add(fp_add(term, a.gamma), v));
-    term = fp_mul(term, a.delta);
-  }
-  ntt_stg(num + i, nu);
-  ntt_stg(den + i, de);
+  if (i < n) perm_terms_row(a, i, fp_mul(block_base, fp_pow_u64(a.omega, threadIdx.x)), num, den);
 }
-// num[i] = (a[i] + beta)(s[i] + gamma),  den[i] = (a'[i] + beta)(s'[i] + gamma)
 __global__ void __launch_bounds__(256) lookup_terms_kernel(const Fr* ci, const Fr* ct, const Fr* pi, const Fr* pt, Fr beta, Fr gamma, uint64_t n, Fr* num, Fr* den) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  ntt_stg(num + i, fp_mul(fp_add(ntt_ld_stream(ci + i), beta), fp_add(ntt_ld_stream(ct + i), gamma)));
-  ntt_stg(den + i, fp_mul(fp_add(ntt_ld_stream(pi + i), beta), fp_add(ntt_ld_stream(pt + i), gamma)));
+  if (i < n) lookup_terms_row(ci, ct, pi, pt, beta, gamma, i, num, den);
 }
 __global__ void __launch_bounds__(256) frac_mul_kernel(Fr* num, const Fr* den_inv, uint64_t n) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;

@@ -8,125 +8,28 @@
 // read + 1 write of `values`) per extended row. The gate graph arrives in the flat encoding documented at
 // include/spectre_b200.h (spb_graph) -- what the Rust shim produces from GraphEvaluator's `calculations`.
 // Intermediates live in a device scratch laid out [intermediate][thread slot] (coalesced), rows are grid-strided.
+// The per-row bodies are in quotient.cuh (host+device: tests/hostemu runs them on the CPU).
 // Parity: bit-exact against the CPU restatement on synthetic constraint systems (tests/test_gpu_quotient.py);
 // not pinned by any reference-owned vector (none exists for this row).
 #include "common.cuh"
-#include "ntt.cuh"
+#include "quotient.cuh"
 #include <string.h>
 
 using namespace spb;
 
-struct GraphArgs {
-  const uint32_t* prog; uint32_t ncalc;
-  const Fr* constants; const int32_t* rotations;
-  const Fr* const* fixed; const Fr* const* advice; const Fr* const* instance;
-  const Fr* scalars;   // [beta, gamma, theta, y, challenges...]
-  Fr* values; Fr* scratch; uint64_t size; int32_t rot_scale;
-};
-
-__device__ __forceinline__ uint64_t rotation_idx(uint64_t idx, int32_t rot, int32_t rot_scale, uint64_t size) {
-  long long v = ((long long)idx + (long long)rot * rot_scale) % (long long)size;
-  if (v < 0) v += (long long)size;
-  return (uint64_t)v;
-}
-
-__device__ __forceinline__ Fr graph_src(const GraphArgs& a, const uint32_t* w, uint64_t row, uint32_t slot, uint32_t nslots, const Fr& previous) {
-  const uint32_t kind = w[0], idx = w[1] & 0xffffu, rot = w[1] >> 16;
-  switch (kind) {
-    case 0: return ntt_ldg(a.constants + idx);
-    case 1: return a.scratch[(uint64_t)idx * nslots + slot];
-    case 2: return ntt_ldg(a.fixed[idx] + rotation_idx(row, a.rotations[rot], a.rot_scale, a.size));
-    case 3: return ntt_ldg(a.advice[idx] + rotation_idx(row, a.rotations[rot], a.rot_scale, a.size));
-    case 4: return ntt_ldg(a.instance[idx] + rotation_idx(row, a.rotations[rot], a.rot_scale, a.size));
-    case 5: return ntt_ldg(a.scalars + 4 + idx);
-    case 6: return ntt_ldg(a.scalars + 0);
-    case 7: return ntt_ldg(a.scalars + 1);
-    case 8: return ntt_ldg(a.scalars + 2);
-    case 9: return ntt_ldg(a.scalars + 3);
-    default: return previous;
-  }
-}
-
 __global__ void __launch_bounds__(256) graph_evaluate_kernel(GraphArgs a) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x, nslots = gridDim.x * blockDim.x;
-  for (uint64_t row = slot; row < a.size; row += nslots) {
-    const Fr previous = a.values[row];
-    const uint32_t* w = a.prog;
-    Fr last = fp_zero<FrParams>();
-    for (uint32_t c = 0; c < a.ncalc; c++) {
-      const uint32_t op = w[0] & 0xffu, nparts = w[0] >> 8, target = w[1];
-      Fr r;
-      if (op <= 2) {
-        Fr x = graph_src(a, w + 2, row, slot, nslots, previous), y = graph_src(a, w + 4, row, slot, nslots, previous);
-        r = op == 0 ? fp_add(x, y) : op == 1 ? fp_sub(x, y) : fp_mul(x, y);
-        w += 6;
-      } else if (op == 6) {
-        Fr acc = graph_src(a, w + 2, row, slot, nslots, previous), factor = graph_src(a, w + 4, row, slot, nslots, previous);
-        for (uint32_t p = 0; p < nparts; p++) acc = fp_add(fp_mul(acc, factor), graph_src(a, w + 6 + 2 * p, row, slot, nslots, previous));
-        r = acc; w += 6 + 2 * nparts;
-      } else {
-        Fr x = graph_src(a, w + 2, row, slot, nslots, previous);
-        r = op == 3 ? fp_sqr(x) : op == 4 ? fp_dbl(x) : op == 5 ? fp_neg(x) : x;
-        w += 4;
-      }
-      a.scratch[(uint64_t)target * nslots + slot] = r;
-      last = r;
-    }
-    a.values[row] = last;
-  }
+  for (uint64_t row = slot; row < a.size; row += nslots) graph_evaluate_row(a, row, slot, nslots);
 }
-
-struct PermArgs {
-  Fr* values; uint64_t size; int32_t rot_scale, last_rotation; uint32_t n_sets, chunk_len, n_cols;
-  const Fr* const* z; const Fr* const* col_values; const Fr* const* sigma;
-  const Fr* l0; const Fr* l_last; const Fr* l_active;
-  Fr beta, gamma, y, delta_start, delta, extended_omega;
-};
 
 __global__ void __launch_bounds__(256) permutation_constraints_kernel(PermArgs a) {
   uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (idx >= a.size) return;
-  const uint64_t r_next = rotation_idx(idx, 1, a.rot_scale, a.size), r_last = rotation_idx(idx, a.last_rotation, a.rot_scale, a.size);
-  const Fr one = fp_one<FrParams>();
-  Fr v = ntt_ld_stream(a.values + idx);
-  const Fr l0 = ntt_ldg(a.l0 + idx), l_last = ntt_ldg(a.l_last + idx), l_active = ntt_ldg(a.l_active + idx);
-  v = fp_add(fp_mul(v, a.y), fp_mul(fp_sub(one, ntt_ldg(a.z[0] + idx)), l0));
-  { Fr zl = ntt_ldg(a.z[a.n_sets - 1] + idx); v = fp_add(fp_mul(v, a.y), fp_mul(fp_sub(fp_sqr(zl), zl), l_last)); }
-  for (uint32_t s = 1; s < a.n_sets; s++)
-    v = fp_add(fp_mul(v, a.y), fp_mul(fp_sub(ntt_ldg(a.z[s] + idx), ntt_ldg(a.z[s - 1] + r_last)), l0));
-  Fr current_delta = fp_mul(a.delta_start, fp_pow_u64(a.extended_omega, idx));
-  for (uint32_t s = 0; s < a.n_sets; s++) {
-    const uint32_t lo = s * a.chunk_len, hi = lo + a.chunk_len < a.n_cols ? lo + a.chunk_len : a.n_cols;
-    Fr left = ntt_ldg(a.z[s] + r_next), right = ntt_ldg(a.z[s] + idx);
-    for (uint32_t c = lo; c < hi; c++) {
-      Fr val = ntt_ldg(a.col_values[c] + idx);
-      left = fp_mul(left, fp_add(fp_add(val, fp_mul(a.beta, ntt_ldg(a.sigma[c] + idx))), a.gamma));
-      right = fp_mul(right, fp_add(fp_add(val, current_delta), a.gamma));
-      current_delta = fp_mul(current_delta, a.delta);
-    }
-    v = fp_add(fp_mul(v, a.y), fp_mul(fp_sub(left, right), l_active));
-  }
-  ntt_stg(a.values + idx, v);
+  if (idx < a.size) permutation_constraints_row(a, idx);
 }
 
-__global__ void __launch_bounds__(256) lookup_constraints_kernel(Fr* values, uint64_t size, int32_t rot_scale, const Fr* product, const Fr* permuted_input,
-                                                                 const Fr* permuted_table, const Fr* table_value, const Fr* l0p, const Fr* l_lastp,
-                                                                 const Fr* l_activep, Fr beta, Fr gamma, Fr y) {
+__global__ void __launch_bounds__(256) lookup_constraints_kernel(LookupArgs a) {
   uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (idx >= size) return;
-  const uint64_t r_next = rotation_idx(idx, 1, rot_scale, size), r_prev = rotation_idx(idx, -1, rot_scale, size);
-  const Fr one = fp_one<FrParams>();
-  const Fr l0 = ntt_ldg(l0p + idx), l_last = ntt_ldg(l_lastp + idx), l_active = ntt_ldg(l_activep + idx);
-  const Fr a_in = ntt_ldg(permuted_input + idx), s_tb = ntt_ldg(permuted_table + idx), zp = ntt_ldg(product + idx);
-  const Fr a_minus_s = fp_sub(a_in, s_tb);
-  Fr v = ntt_ld_stream(values + idx);
-  v = fp_add(fp_mul(v, y), fp_mul(fp_sub(one, zp), l0));
-  v = fp_add(fp_mul(v, y), fp_mul(fp_sub(fp_sqr(zp), zp), l_last));
-  Fr lhs = fp_mul(fp_mul(ntt_ldg(product + r_next), fp_add(a_in, beta)), fp_add(s_tb, gamma));
-  v = fp_add(fp_mul(v, y), fp_mul(fp_sub(lhs, fp_mul(zp, ntt_ldg(table_value + idx))), l_active));
-  v = fp_add(fp_mul(v, y), fp_mul(a_minus_s, l0));
-  v = fp_add(fp_mul(v, y), fp_mul(fp_mul(a_minus_s, fp_sub(a_in, ntt_ldg(permuted_input + r_prev))), l_active));
-  ntt_stg(values + idx, v);
+  if (idx < a.size) lookup_constraints_row(a, idx);
 }
 
 extern "C" {
@@ -212,10 +115,12 @@ int spb_lookup_constraints_dev(spb_ctx* ctx, spb_fr* d_values, uint64_t size, in
   if (!ctx || !d_values || !d_product || !d_permuted_input || !d_permuted_table || !d_table_value || !d_l0 || !d_l_last || !d_l_active || !beta || !gamma || !y)
     return SPB_ERR_ARG;
   SPB_ENTER(ctx);
-  Fr b, g, yy; memcpy(&b, beta, 32); memcpy(&g, gamma, 32); memcpy(&yy, y, 32);
-  lookup_constraints_kernel<<<(unsigned)((size + 255) / 256), 256, 0, d.stream>>>((Fr*)d_values, size, rot_scale, (const Fr*)d_product, (const Fr*)d_permuted_input,
-                                                                                 (const Fr*)d_permuted_table, (const Fr*)d_table_value, (const Fr*)d_l0,
-                                                                                 (const Fr*)d_l_last, (const Fr*)d_l_active, b, g, yy);
+  LookupArgs a;
+  a.values = (Fr*)d_values; a.size = size; a.rot_scale = rot_scale;
+  a.product = (const Fr*)d_product; a.permuted_input = (const Fr*)d_permuted_input; a.permuted_table = (const Fr*)d_permuted_table;
+  a.table_value = (const Fr*)d_table_value; a.l0 = (const Fr*)d_l0; a.l_last = (const Fr*)d_l_last; a.l_active = (const Fr*)d_l_active;
+  memcpy(&a.beta, beta, 32); memcpy(&a.gamma, gamma, 32); memcpy(&a.y, y, 32);
+  lookup_constraints_kernel<<<(unsigned)((size + 255) / 256), 256, 0, d.stream>>>(a);
   SPB_CUDA(ctx, cudaGetLastError());
   ctx->n_kernel_launches++;
   SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));

@@ -161,3 +161,57 @@ int he_ntt(const Fr* in, Fr* out, uint32_t k, const Fr* omega, uint32_t max_digi
   return (int)plan.npass;
 }
 }
+
+// ---- quotient numerator / argument-prover term kernels: the per-row bodies run serially ---------------------------------
+#include "../../spectre_b200/csrc/quotient.cuh"
+namespace {
+Fr fr_macro(const uint32_t (&v)[8]) { Fr a; for (int i = 0; i < 8; i++) a.l[i] = v[i]; return a; }
+}  // namespace
+extern "C" {
+// scalars: beta, gamma, theta, y, then challenges. nslots: how many "threads" share the scratch (any value >= 1).
+void he_graph_evaluate(const uint32_t* prog, uint32_t ncalc, uint32_t n_inter, const Fr* constants, const int32_t* rotations, const Fr* const* fixed,
+                       const Fr* const* advice, const Fr* const* instance, const Fr* scalars, Fr* values, uint64_t size, int32_t rot_scale, uint32_t nslots) {
+  std::vector<Fr> scratch((size_t)(n_inter ? n_inter : 1) * nslots);
+  GraphArgs a; memset(&a, 0, sizeof a);
+  a.prog = prog; a.ncalc = ncalc; a.constants = constants; a.rotations = rotations; a.fixed = fixed; a.advice = advice; a.instance = instance;
+  a.scalars = scalars; a.values = values; a.scratch = scratch.data(); a.size = size; a.rot_scale = rot_scale;
+  for (uint32_t slot = 0; slot < nslots; slot++)
+    for (uint64_t row = slot; row < size; row += nslots) graph_evaluate_row(a, row, slot, nslots);
+}
+void he_permutation_constraints(Fr* values, uint64_t size, int32_t rot_scale, int32_t last_rotation, uint32_t n_sets, uint32_t chunk_len, const Fr* const* z,
+                                uint32_t n_cols, const Fr* const* col_values, const Fr* const* sigma, const Fr* l0, const Fr* l_last, const Fr* l_active,
+                                const Fr* beta, const Fr* gamma, const Fr* y, const Fr* extended_omega) {
+  if (!n_sets) return;
+  PermArgs a; memset(&a, 0, sizeof a);
+  a.values = values; a.size = size; a.rot_scale = rot_scale; a.last_rotation = last_rotation; a.n_sets = n_sets; a.chunk_len = chunk_len; a.n_cols = n_cols;
+  a.z = z; a.col_values = col_values; a.sigma = sigma; a.l0 = l0; a.l_last = l_last; a.l_active = l_active;
+  a.beta = *beta; a.gamma = *gamma; a.y = *y; a.extended_omega = *extended_omega;
+  constexpr uint32_t zeta[8] = SPB_FR_ZETA_MONT; constexpr uint32_t delta[8] = SPB_FR_DELTA_MONT;
+  a.delta = fr_macro(delta); a.delta_start = fp_mul(a.beta, fr_macro(zeta));
+  for (uint64_t idx = 0; idx < size; idx++) permutation_constraints_row(a, idx);
+}
+void he_lookup_constraints(Fr* values, uint64_t size, int32_t rot_scale, const Fr* product, const Fr* permuted_input, const Fr* permuted_table, const Fr* table_value,
+                           const Fr* l0, const Fr* l_last, const Fr* l_active, const Fr* beta, const Fr* gamma, const Fr* y) {
+  LookupArgs a;
+  a.values = values; a.size = size; a.rot_scale = rot_scale; a.product = product; a.permuted_input = permuted_input; a.permuted_table = permuted_table;
+  a.table_value = table_value; a.l0 = l0; a.l_last = l_last; a.l_active = l_active; a.beta = *beta; a.gamma = *gamma; a.y = *y;
+  for (uint64_t idx = 0; idx < size; idx++) lookup_constraints_row(a, idx);
+}
+// the two term kernels of the grand products, with the block/thread split of omega^i the kernel uses (block = 256 rows)
+void he_perm_terms(uint32_t k, const Fr* const* values, const Fr* const* sigma, uint32_t n_cols, uint32_t first_col, const Fr* beta, const Fr* gamma,
+                   const Fr* omega, Fr* num, Fr* den) {
+  PermTermArgs a;
+  for (uint32_t c = 0; c < n_cols; c++) { a.values[c] = values[c]; a.sigma[c] = sigma[c]; }
+  constexpr uint32_t delta[8] = SPB_FR_DELTA_MONT;
+  a.n_cols = n_cols; a.beta = *beta; a.gamma = *gamma; a.delta = fr_macro(delta); a.omega = *omega;
+  a.delta_start = fp_mul(a.beta, fp_pow_u64(a.delta, first_col));
+  const uint64_t n = 1ull << k;
+  for (uint64_t block = 0; block * 256 < n; block++) {
+    Fr base = fp_pow_u64(a.omega, block * 256);
+    for (uint32_t t = 0; t < 256 && block * 256 + t < n; t++) perm_terms_row(a, block * 256 + t, fp_mul(base, fp_pow_u64(a.omega, t)), num, den);
+  }
+}
+void he_lookup_terms(const Fr* ci, const Fr* ct, const Fr* pi, const Fr* pt, const Fr* beta, const Fr* gamma, uint64_t n, Fr* num, Fr* den) {
+  for (uint64_t i = 0; i < n; i++) lookup_terms_row(ci, ct, pi, pt, *beta, *gamma, i, num, den);
+}
+}

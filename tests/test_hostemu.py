@@ -20,7 +20,7 @@ HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu")
 def _build(name, flags):
     so = os.path.join(HERE, name)
     src = os.path.join(HERE, "hostemu.cpp")
-    hdrs = [os.path.join(HERE, "..", "..", "spectre_b200", "csrc", h) for h in ("ptx.cuh", "field.cuh", "curve.cuh")]
+    hdrs = [os.path.join(HERE, "..", "..", "spectre_b200", "csrc", h) for h in ("ptx.cuh", "field.cuh", "curve.cuh", "msm.cuh", "ntt.cuh", "quotient.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + flags + ["-o", so, src])
