@@ -14,8 +14,10 @@
 // STATUS (round 1): validated on the CPU against the Python driver through the shim; not yet run against libspectre_b200.so
 // on a GPU (the Python driver is the GPU-validated one).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -182,5 +184,629 @@ class EvmTranscriptWrite {
   std::vector<uint8_t> buf_, proof_;
   std::vector<size_t> absorbed_;
 };
+
+
+// =====================================================================================================================
+// keygen_pk / create_proof over the C ABI (the C++ twin of spectre_b200/plonk.py; stage numbers as there)
+// =====================================================================================================================
+namespace plonk {
+
+using U256 = hostfield::U256;
+using Fr = spb_fr;   // Montgomery limbs, the ABI representation
+
+inline const hostfield::Params& FrP() { return hostfield::fr_params(); }
+inline Fr fr_mont(const U256& canonical) { U256 m = hostfield::to_mont(FrP(), canonical); Fr o; memcpy(&o, m.data(), 32); return o; }
+inline U256 fr_int(const Fr& a) { U256 m; memcpy(m.data(), &a, 32); return hostfield::from_mont(FrP(), m); }
+inline U256 u256(uint64_t v) { return {v, 0, 0, 0}; }
+inline U256 mulmod(const U256& a, const U256& b) {   // canonical * canonical -> canonical
+  return hostfield::from_mont(FrP(), hostfield::mul(FrP(), hostfield::to_mont(FrP(), a), hostfield::to_mont(FrP(), b)));
+}
+inline U256 powmod(const U256& a, uint64_t e) { return hostfield::from_mont(FrP(), hostfield::pow_u64(FrP(), hostfield::to_mont(FrP(), a), e)); }
+inline U256 root_of_unity() { return hostfield::from_mont(FrP(), {0x9632c7c5b639feb8ull, 0x985ce3400d0ff299ull, 0xb2dd880001b0ecd8ull, 0x1d69070d6d98ce29ull}); }
+inline U256 delta() { return hostfield::from_mont(FrP(), {0x9a0c322befd78855ull, 0x46e82d14249b563cull, 0x5983a663e0b0b7a7ull, 0x22ab452baaa111adull}); }
+inline U256 omega_of(uint32_t k) { U256 w = root_of_unity(); for (uint32_t i = k; i < 28; i++) w = mulmod(w, w); return w; }
+
+// ---- expressions ----------------------------------------------------------------------------------------------------
+struct Expr;
+using ExprP = std::shared_ptr<const Expr>;
+struct Expr {
+  enum Kind { Const, Fixed, Advice, Instance, Neg, Sum, Prod, Scaled } kind;
+  U256 value{};          // Const / Scaled
+  uint32_t col = 0; int32_t rot = 0;
+  ExprP a, b;
+};
+inline ExprP Const(const U256& v) { auto e = std::make_shared<Expr>(); e->kind = Expr::Const; e->value = v; return e; }
+inline ExprP Fixed(uint32_t c, int32_t r = 0) { auto e = std::make_shared<Expr>(); e->kind = Expr::Fixed; e->col = c; e->rot = r; return e; }
+inline ExprP Advice(uint32_t c, int32_t r = 0) { auto e = std::make_shared<Expr>(); e->kind = Expr::Advice; e->col = c; e->rot = r; return e; }
+inline ExprP Instance(uint32_t c, int32_t r = 0) { auto e = std::make_shared<Expr>(); e->kind = Expr::Instance; e->col = c; e->rot = r; return e; }
+inline ExprP Neg(ExprP x) { auto e = std::make_shared<Expr>(); e->kind = Expr::Neg; e->a = x; return e; }
+inline ExprP Sum(ExprP x, ExprP y) { auto e = std::make_shared<Expr>(); e->kind = Expr::Sum; e->a = x; e->b = y; return e; }
+inline ExprP Prod(ExprP x, ExprP y) { auto e = std::make_shared<Expr>(); e->kind = Expr::Prod; e->a = x; e->b = y; return e; }
+inline ExprP Scaled(ExprP x, const U256& v) { auto e = std::make_shared<Expr>(); e->kind = Expr::Scaled; e->a = x; e->value = v; return e; }
+
+inline int degree(const ExprP& e) {
+  switch (e->kind) {
+    case Expr::Const: return 0;
+    case Expr::Fixed: case Expr::Advice: case Expr::Instance: return 1;
+    case Expr::Neg: case Expr::Scaled: return degree(e->a);
+    case Expr::Sum: return std::max(degree(e->a), degree(e->b));
+    default: return degree(e->a) + degree(e->b);
+  }
+}
+using Query = std::pair<uint32_t, int32_t>;   // (column, rotation)
+struct Queries { std::vector<Query> fixed, advice, instance; };
+inline void add_query(std::vector<Query>& v, Query q) { for (auto& x : v) if (x == q) return; v.push_back(q); }
+inline void collect_queries(const ExprP& e, Queries& out) {
+  switch (e->kind) {
+    case Expr::Fixed: add_query(out.fixed, {e->col, e->rot}); break;
+    case Expr::Advice: add_query(out.advice, {e->col, e->rot}); break;
+    case Expr::Instance: add_query(out.instance, {e->col, e->rot}); break;
+    case Expr::Neg: case Expr::Scaled: collect_queries(e->a, out); break;
+    case Expr::Sum: case Expr::Prod: collect_queries(e->a, out); collect_queries(e->b, out); break;
+    default: break;
+  }
+}
+
+// ---- flat GraphEvaluator programs (encoding of include/spectre_b200.h) --------------------------------------------------
+enum { OP_ADD = 0, OP_SUB, OP_MUL, OP_SQUARE, OP_DOUBLE, OP_NEGATE, OP_HORNER, OP_STORE };
+enum { K_CONST = 0, K_INTER, K_FIXED, K_ADVICE, K_INSTANCE, K_CHALLENGE, K_BETA, K_GAMMA, K_THETA, K_Y, K_PREV };
+struct Graph {
+  std::vector<uint32_t> words; uint32_t ncalc = 0;
+  std::vector<Fr> constants; std::vector<int32_t> rotations;
+  spb_graph abi() const { return spb_graph{words.data(), words.size(), ncalc, ncalc, constants.data(), (uint32_t)constants.size(), rotations.data(), (uint32_t)rotations.size()}; }
+};
+class Program {
+ public:
+  using Src = std::pair<uint32_t, uint32_t>;
+  Program() { constants_ = {u256(0), u256(1)}; }
+  Src constant(const U256& v) {
+    for (size_t i = 0; i < constants_.size(); i++) if (constants_[i] == v) return {K_CONST, (uint32_t)i};
+    constants_.push_back(v); return {K_CONST, (uint32_t)constants_.size() - 1};
+  }
+  Src emit(uint32_t op, const std::vector<Src>& srcs, uint32_t nparts = 0) {
+    words_.push_back(op | (nparts << 8)); words_.push_back(ncalc_);
+    for (auto& s : srcs) { words_.push_back(s.first); words_.push_back(s.second); }
+    return {K_INTER, ncalc_++};
+  }
+  Src src(const ExprP& e) {
+    switch (e->kind) {
+      case Expr::Const: return constant(e->value);
+      case Expr::Fixed: return {K_FIXED, e->col | (rot(e->rot) << 16)};
+      case Expr::Advice: return {K_ADVICE, e->col | (rot(e->rot) << 16)};
+      case Expr::Instance: return {K_INSTANCE, e->col | (rot(e->rot) << 16)};
+      case Expr::Neg: return emit(OP_NEGATE, {src(e->a)});
+      case Expr::Sum: { Src x = src(e->a), y = src(e->b); return emit(OP_ADD, {x, y}); }
+      case Expr::Prod: { Src x = src(e->a), y = src(e->b); return emit(OP_MUL, {x, y}); }
+      default: { Src x = src(e->a); return emit(OP_MUL, {x, constant(e->value)}); }
+    }
+  }
+  Src horner(Src start, Src factor, const std::vector<ExprP>& exprs) {
+    std::vector<Src> srcs = {start, factor};
+    for (auto& e : exprs) srcs.push_back(src(e));
+    return emit(OP_HORNER, srcs, (uint32_t)exprs.size());
+  }
+  Graph finish() const {
+    Graph g; g.words = words_; g.ncalc = ncalc_;
+    for (auto& c : constants_) g.constants.push_back(fr_mont(c));
+    g.rotations = rotations_.empty() ? std::vector<int32_t>{0} : rotations_;
+    return g;
+  }
+
+ private:
+  uint32_t rot(int32_t r) {
+    for (size_t i = 0; i < rotations_.size(); i++) if (rotations_[i] == r) return (uint32_t)i;
+    rotations_.push_back(r); return (uint32_t)rotations_.size() - 1;
+  }
+  std::vector<uint32_t> words_; uint32_t ncalc_ = 0;
+  std::vector<U256> constants_; std::vector<int32_t> rotations_;
+};
+
+// ---- ConstraintSystem ---------------------------------------------------------------------------------------------------
+enum class Col { Fixed, Advice, Instance };
+struct Lookup { std::vector<ExprP> inputs, tables; };
+struct ConstraintSystem {
+  uint32_t num_fixed = 0, num_advice = 0, num_instance = 0;
+  std::vector<ExprP> gates;
+  std::vector<Lookup> lookups;
+  std::vector<std::pair<Col, uint32_t>> permutation;
+  std::vector<Query> fixed_queries, advice_queries, instance_queries;
+
+  // call after filling the members above (explicit fixed/advice query prefixes may be set beforehand)
+  void finalize() {
+    Queries q; q.fixed = fixed_queries; q.advice = advice_queries;
+    for (auto& g : gates) collect_queries(g, q);
+    for (auto& l : lookups) { for (auto& e : l.inputs) collect_queries(e, q); for (auto& e : l.tables) collect_queries(e, q); }
+    for (auto& pc : permutation) {
+      auto& v = pc.first == Col::Fixed ? q.fixed : pc.first == Col::Advice ? q.advice : q.instance;
+      add_query(v, {pc.second, 0});
+    }
+    fixed_queries = q.fixed; advice_queries = q.advice; instance_queries = q.instance;
+  }
+  int degree() const {
+    int d = permutation.empty() ? 1 : 3;
+    for (auto& l : lookups) {
+      int di = 0, dt = 0;
+      for (auto& e : l.inputs) di = std::max(di, plonk::degree(e));
+      for (auto& e : l.tables) dt = std::max(dt, plonk::degree(e));
+      d = std::max(d, std::max(4, 2 + di + dt));
+    }
+    for (auto& g : gates) d = std::max(d, plonk::degree(g));
+    return d;
+  }
+  uint32_t blinding_factors() const {
+    uint32_t mx = num_advice ? 0 : 1;
+    for (uint32_t c = 0; c < num_advice; c++) { uint32_t cnt = 0; for (auto& q : advice_queries) if (q.first == c) cnt++; mx = std::max(mx, cnt); }
+    return std::max<uint32_t>(3, mx) + 2;
+  }
+  uint32_t chunk_len() const { return (uint32_t)std::max(1, degree() - 2); }
+  Graph gates_program() const { Program p; p.horner({K_PREV, 0}, {K_Y, 0}, gates); return p.finish(); }
+  Graph lookup_compress_program(const std::vector<ExprP>& exprs) const { Program p; p.horner(p.constant(u256(0)), {K_THETA, 0}, exprs); return p.finish(); }
+  Graph lookup_value_program(size_t li) const {
+    Program p;
+    auto a = p.horner(p.constant(u256(0)), {K_THETA, 0}, lookups[li].inputs);
+    auto s = p.horner(p.constant(u256(0)), {K_THETA, 0}, lookups[li].tables);
+    auto l = p.emit(OP_ADD, {a, {K_BETA, 0}}); auto r = p.emit(OP_ADD, {s, {K_GAMMA, 0}});
+    p.emit(OP_MUL, {l, r});
+    return p.finish();
+  }
+};
+
+// ---- device memory ----------------------------------------------------------------------------------------------------
+struct DeviceMemory {
+  virtual ~DeviceMemory() {}
+  virtual Fr* alloc(size_t rows) = 0;                        // zero-initialised
+  virtual void free(Fr* p) = 0;
+  virtual void upload(Fr* dst, const Fr* src, size_t rows) = 0;
+  virtual void download(Fr* dst, const Fr* src, size_t rows) = 0;
+  virtual void copy(Fr* dst, const Fr* src, size_t rows) = 0;
+};
+struct HostMemory : DeviceMemory {                           // "device" = host: the CPU tests' binding (tests/abi_shim)
+  Fr* alloc(size_t rows) override { return (Fr*)calloc(rows ? rows : 1, sizeof(Fr)); }
+  void free(Fr* p) override { ::free(p); }
+  void upload(Fr* d, const Fr* s, size_t rows) override { memcpy(d, s, rows * sizeof(Fr)); }
+  void download(Fr* d, const Fr* s, size_t rows) override { memcpy(d, s, rows * sizeof(Fr)); }
+  void copy(Fr* d, const Fr* s, size_t rows) override { memcpy(d, s, rows * sizeof(Fr)); }
+};
+#ifdef SPB_PROVER_WITH_CUDART
+struct CudaMemory : DeviceMemory {
+  static void ck(cudaError_t e) { if (e != cudaSuccess) throw std::runtime_error(std::string("cuda: ") + cudaGetErrorString(e)); }
+  Fr* alloc(size_t rows) override { void* p; ck(cudaMalloc(&p, (rows ? rows : 1) * sizeof(Fr))); ck(cudaMemset(p, 0, (rows ? rows : 1) * sizeof(Fr))); return (Fr*)p; }
+  void free(Fr* p) override { cudaFree(p); }
+  void upload(Fr* d, const Fr* s, size_t rows) override { ck(cudaMemcpy(d, s, rows * sizeof(Fr), cudaMemcpyHostToDevice)); }
+  void download(Fr* d, const Fr* s, size_t rows) override { ck(cudaMemcpy(d, s, rows * sizeof(Fr), cudaMemcpyDeviceToHost)); }
+  void copy(Fr* d, const Fr* s, size_t rows) override { ck(cudaMemcpy(d, s, rows * sizeof(Fr), cudaMemcpyDeviceToDevice)); }
+};
+#endif
+
+class Buffer {                                               // owning device buffer (or a non-owning view into one)
+ public:
+  Buffer() {}
+  Buffer(DeviceMemory& m, size_t rows) : mem_(&m), p_(m.alloc(rows)), rows_(rows), owns_(true) {}
+  Buffer(Buffer&& o) noexcept { *this = std::move(o); }
+  Buffer& operator=(Buffer&& o) noexcept { release(); mem_ = o.mem_; p_ = o.p_; rows_ = o.rows_; owns_ = o.owns_; o.p_ = nullptr; o.owns_ = false; return *this; }
+  Buffer(const Buffer&) = delete;
+  ~Buffer() { release(); }
+  static Buffer view(const Buffer& b, size_t lo, size_t hi) { Buffer v; v.mem_ = b.mem_; v.p_ = b.p_ + lo; v.rows_ = hi - lo; v.owns_ = false; return v; }
+  Fr* ptr() const { return p_; }
+  size_t rows() const { return rows_; }
+  void release() { if (owns_ && p_) mem_->free(p_); p_ = nullptr; owns_ = false; }
+
+ private:
+  DeviceMemory* mem_ = nullptr; Fr* p_ = nullptr; size_t rows_ = 0; bool owns_ = false;
+};
+
+struct Point { U256 x, y; };                                 // canonical affine coordinates; identity = (0, 0)
+
+// ---- the engine: one method per driver step, each a handful of C ABI calls -----------------------------------------------
+class Engine {
+ public:
+  Engine(spb_ctx* ctx, DeviceMemory& mem, spb_srs* srs, uint32_t k, uint32_t j) : ctx_(ctx), mem_(mem), srs_(srs), k(k), n((size_t)1 << k) {
+    check(spb_domain_new(ctx, j, k, &dom_), "spb_domain_new");
+    extended_k = spb_domain_extended_k(dom_);
+  }
+  ~Engine() { spb_domain_free(ctx_, dom_); }
+  Engine(const Engine&) = delete;
+  void check(int rc, const char* what) const { if (rc != 0) throw std::runtime_error(std::string(what) + " failed: " + spb_last_error(ctx_)); }
+
+  Buffer alloc(size_t rows) { return Buffer(mem_, rows); }
+  Buffer upload(const Fr* host, size_t rows) { Buffer b(mem_, rows); mem_.upload(b.ptr(), host, rows); return b; }
+  Buffer clone(const Buffer& b) { Buffer c(mem_, b.rows()); mem_.copy(c.ptr(), b.ptr(), b.rows()); return c; }
+  void write_rows(Buffer& b, size_t start, const Fr* rows, size_t count) { if (count) mem_.upload(b.ptr() + start, rows, count); }
+
+  std::vector<Point> commit(int basis, const std::vector<const Fr*>& bufs, size_t len) {
+    std::vector<spb_g1> jac(bufs.size());
+    check(spb_msm_batch_dev(ctx_, srs_, basis, bufs.data(), len, bufs.size(), jac.data()), "spb_msm_batch_dev");
+    std::vector<Point> out;
+    for (auto& p : jac) out.push_back(to_affine(p));
+    return out;
+  }
+  static Point to_affine(const spb_g1& p) {
+    const auto& Q = hostfield::fq_params();
+    U256 x, y, z; memcpy(x.data(), &p.x, 32); memcpy(y.data(), &p.y, 32); memcpy(z.data(), &p.z, 32);
+    if (!(z[0] | z[1] | z[2] | z[3])) return Point{u256(0), u256(0)};
+    U256 zi = hostfield::inv(Q, z), zi2 = hostfield::mul(Q, zi, zi), zi3 = hostfield::mul(Q, zi2, zi);
+    return Point{hostfield::from_mont(Q, hostfield::mul(Q, x, zi2)), hostfield::from_mont(Q, hostfield::mul(Q, y, zi3))};
+  }
+
+  void lagrange_to_coeff(Buffer& b) { check(spb_lagrange_to_coeff_dev(ctx_, dom_, b.ptr()), "spb_lagrange_to_coeff_dev"); }
+  void coeff_to_lagrange(Buffer& b) { Fr w = fr_mont(omega_of(k)); check(spb_ntt_dev(ctx_, b.ptr(), k, &w), "spb_ntt_dev"); }
+  Buffer coeff_to_extended(const Buffer& b) { Buffer o(mem_, (size_t)1 << extended_k); check(spb_coeff_to_extended_dev(ctx_, dom_, b.ptr(), o.ptr()), "spb_coeff_to_extended_dev"); return o; }
+  Buffer extended_to_coeff(const Buffer& e, size_t rows) { Buffer o(mem_, rows); check(spb_extended_to_coeff_dev(ctx_, dom_, e.ptr(), o.ptr()), "spb_extended_to_coeff_dev"); return o; }
+  void divide_by_vanishing(Buffer& e) { check(spb_divide_by_vanishing_dev(ctx_, dom_, e.ptr()), "spb_divide_by_vanishing_dev"); }
+
+  void graph_evaluate(const Graph& g, const std::vector<const Fr*>& fixed, const std::vector<const Fr*>& advice, const std::vector<const Fr*>& instance,
+                      const Fr& beta, const Fr& gamma, const Fr& theta, const Fr& y, Buffer& values, uint64_t size, int32_t rot_scale) {
+    spb_graph abi = g.abi();
+    Fr zero{};
+    check(spb_graph_evaluate_dev(ctx_, &abi, fixed.data(), (uint32_t)fixed.size(), advice.data(), (uint32_t)advice.size(), instance.data(), (uint32_t)instance.size(),
+                                 &zero, 1, &beta, &gamma, &theta, &y, values.ptr(), size, rot_scale), "spb_graph_evaluate_dev");
+  }
+  void permutation_constraints(Buffer& values, uint64_t size, int32_t rot_scale, int32_t last_rotation, uint32_t chunk_len, const std::vector<const Fr*>& z,
+                               const std::vector<const Fr*>& cols, const std::vector<const Fr*>& sigma, const Buffer& l0, const Buffer& l_last, const Buffer& l_active,
+                               const Fr& beta, const Fr& gamma, const Fr& y, const Fr& ext_omega) {
+    check(spb_permutation_constraints_dev(ctx_, values.ptr(), size, rot_scale, last_rotation, (uint32_t)z.size(), chunk_len, z.data(), (uint32_t)cols.size(), cols.data(),
+                                          sigma.data(), l0.ptr(), l_last.ptr(), l_active.ptr(), &beta, &gamma, &y, &ext_omega), "spb_permutation_constraints_dev");
+  }
+  void lookup_constraints(Buffer& values, uint64_t size, int32_t rot_scale, const Buffer& product, const Buffer& pin, const Buffer& ptab, const Buffer& table_value,
+                          const Buffer& l0, const Buffer& l_last, const Buffer& l_active, const Fr& beta, const Fr& gamma, const Fr& y) {
+    check(spb_lookup_constraints_dev(ctx_, values.ptr(), size, rot_scale, product.ptr(), pin.ptr(), ptab.ptr(), table_value.ptr(), l0.ptr(), l_last.ptr(), l_active.ptr(),
+                                     &beta, &gamma, &y), "spb_lookup_constraints_dev");
+  }
+  void permute_expression_pair(const Buffer& a, const Buffer& s, size_t usable, Buffer& out_a, Buffer& out_s) {
+    check(spb_permute_expression_pair_dev(ctx_, a.ptr(), s.ptr(), usable, out_a.ptr(), out_s.ptr()), "spb_permute_expression_pair_dev");
+  }
+  Fr permutation_product(const std::vector<const Fr*>& values, const std::vector<const Fr*>& sigma, uint32_t first_col, const Fr& beta, const Fr& gamma,
+                         const std::vector<Fr>& blinds, Fr last_z, Buffer& z) {
+    check(spb_permutation_product_dev(ctx_, k, values.data(), sigma.data(), (uint32_t)values.size(), first_col, &beta, &gamma, blinds.empty() ? nullptr : blinds.data(),
+                                      (uint32_t)blinds.size(), &last_z, z.ptr()), "spb_permutation_product_dev");
+    return last_z;
+  }
+  void lookup_product(const Buffer& ci, const Buffer& ct, const Buffer& pi, const Buffer& pt, const Fr& beta, const Fr& gamma, const std::vector<Fr>& blinds, Buffer& z) {
+    check(spb_lookup_product_dev(ctx_, n, ci.ptr(), ct.ptr(), pi.ptr(), pt.ptr(), &beta, &gamma, blinds.empty() ? nullptr : blinds.data(), (uint32_t)blinds.size(), z.ptr()),
+          "spb_lookup_product_dev");
+  }
+  U256 eval_polynomial(const Fr* poly, size_t len, const U256& point) {
+    Fr pt = fr_mont(point), out;
+    check(spb_eval_polynomial_dev(ctx_, poly, len, &pt, &out), "spb_eval_polynomial_dev");
+    return fr_int(out);
+  }
+  void lincomb(const std::vector<const Fr*>& polys, const Fr& y, Buffer& out, size_t len) { check(spb_lincomb_dev(ctx_, polys.data(), polys.size(), &y, out.ptr(), len), "spb_lincomb_dev"); }
+  void vec_scale(Buffer& b, const Fr& alpha, size_t len) { check(spb_vec_scale_dev(ctx_, b.ptr(), &alpha, len), "spb_vec_scale_dev"); }
+
+  struct OpenSet { std::vector<Fr> points; std::vector<const Fr*> polys; std::vector<Fr> evals; };
+  Point shplonk_begin(const std::vector<OpenSet>& sets, const Fr& y, const Fr& v, spb_shplonk** handle) {
+    std::vector<spb_rotation_set> raw;
+    for (auto& s : sets) raw.push_back(spb_rotation_set{s.points.data(), (uint32_t)s.points.size(), s.polys.data(), (uint32_t)s.polys.size(), s.evals.data()});
+    spb_g1 h;
+    check(spb_shplonk_begin_dev(ctx_, srs_, n, raw.data(), (uint32_t)raw.size(), &y, &v, &h, handle), "spb_shplonk_begin_dev");
+    return to_affine(h);
+  }
+  Point shplonk_finish(spb_shplonk* handle, const Fr& u) {
+    spb_g1 c;
+    check(spb_shplonk_finish_dev(ctx_, handle, &u, &c), "spb_shplonk_finish_dev");
+    return to_affine(c);
+  }
+
+  const uint32_t k; const size_t n; uint32_t extended_k = 0;
+
+ private:
+  spb_ctx* ctx_; DeviceMemory& mem_; spb_srs* srs_; spb_domain* dom_ = nullptr;
+};
+
+// ---- keygen ---------------------------------------------------------------------------------------------------------------
+using Cell = std::pair<uint32_t, uint64_t>;                  // (index in cs.permutation, row)
+struct ProvingKey {
+  const ConstraintSystem* cs = nullptr;
+  uint32_t k = 0; size_t n = 0; uint32_t blinding_factors = 0; size_t usable_rows = 0;
+  std::vector<Buffer> fixed_values, fixed_polys, fixed_cosets, sigma_values, sigma_polys, sigma_cosets;
+  Buffer l0, l_last, l_active;
+  std::vector<Point> fixed_commitments, sigma_commitments;
+  U256 vk_digest{};
+};
+inline std::vector<const Fr*> ptrs(const std::vector<Buffer>& v) { std::vector<const Fr*> o; for (auto& b : v) o.push_back(b.ptr()); return o; }
+
+inline std::vector<Buffer> build_sigma(Engine& E, const ConstraintSystem& cs, const std::vector<std::pair<Cell, Cell>>& copies) {
+  const size_t n = E.n;
+  std::vector<Fr> x_poly(n, Fr{});
+  if (n > 1) x_poly[1] = fr_mont(u256(1));
+  Buffer base = E.upload(x_poly.data(), n);
+  E.coeff_to_lagrange(base);                                 // omega^i
+  std::vector<Buffer> sigma;
+  for (size_t c = 0; c < cs.permutation.size(); c++) {
+    Buffer s = E.clone(base);
+    if (c) E.vec_scale(s, fr_mont(powmod(delta(), c)), n);
+    sigma.push_back(std::move(s));
+  }
+  std::map<Cell, Cell> nxt;
+  auto next = [&](const Cell& c) { auto it = nxt.find(c); return it == nxt.end() ? c : it->second; };
+  for (auto& cp : copies) {
+    const Cell &a = cp.first, &b = cp.second;
+    bool same = (a == b);
+    for (Cell cur = next(a); !same && cur != a; cur = next(cur)) if (cur == b) same = true;
+    if (same) continue;
+    Cell na = next(a), nb = next(b);
+    nxt[a] = nb; nxt[b] = na;
+  }
+  const U256 w = omega_of(E.k);
+  for (auto& kv : nxt) {
+    Fr v = fr_mont(mulmod(powmod(delta(), kv.second.first), powmod(w, kv.second.second)));
+    E.write_rows(sigma[kv.first.first], kv.first.second, &v, 1);
+  }
+  return sigma;
+}
+
+inline U256 default_vk_digest(const ProvingKey& pk) {
+  std::vector<uint8_t> data = {(uint8_t)pk.k, (uint8_t)(pk.k >> 8), (uint8_t)(pk.k >> 16), (uint8_t)(pk.k >> 24)};
+  auto put = [&](const U256& v) { uint8_t b[32]; hostfield::to_be(v, b); data.insert(data.end(), b, b + 32); };
+  for (auto& p : pk.fixed_commitments) { put(p.x); put(p.y); }
+  for (auto& p : pk.sigma_commitments) { put(p.x); put(p.y); }
+  auto h = keccak256(data.data(), data.size());
+  return hostfield::reduce(FrP(), hostfield::from_be(h.data()));
+}
+
+// fixed_columns: host arrays of n Montgomery elements (Lagrange basis)
+inline ProvingKey keygen(Engine& E, const ConstraintSystem& cs, const std::vector<const Fr*>& fixed_columns, const std::vector<std::pair<Cell, Cell>>& copies,
+                         const U256* vk_digest = nullptr) {
+  ProvingKey pk;
+  pk.cs = &cs; pk.k = E.k; pk.n = E.n;
+  pk.blinding_factors = cs.blinding_factors(); pk.usable_rows = E.n - (pk.blinding_factors + 1);
+  for (auto* c : fixed_columns) pk.fixed_values.push_back(E.upload(c, E.n));
+  pk.sigma_values = build_sigma(E, cs, copies);
+  if (!pk.fixed_values.empty()) pk.fixed_commitments = E.commit(SPB_BASIS_G_LAGRANGE, ptrs(pk.fixed_values), E.n);
+  if (!pk.sigma_values.empty()) pk.sigma_commitments = E.commit(SPB_BASIS_G_LAGRANGE, ptrs(pk.sigma_values), E.n);
+  auto poly_and_coset = [&](const Buffer& values, std::vector<Buffer>* polys, std::vector<Buffer>* cosets) {
+    Buffer p = E.clone(values); E.lagrange_to_coeff(p);
+    Buffer c = E.coeff_to_extended(p);
+    if (polys) polys->push_back(std::move(p));
+    cosets->push_back(std::move(c));
+  };
+  for (auto& v : pk.fixed_values) poly_and_coset(v, &pk.fixed_polys, &pk.fixed_cosets);
+  for (auto& v : pk.sigma_values) poly_and_coset(v, &pk.sigma_polys, &pk.sigma_cosets);
+  const Fr one = fr_mont(u256(1));
+  std::vector<Buffer> ls;
+  { Buffer l0 = E.alloc(E.n); E.write_rows(l0, 0, &one, 1); poly_and_coset(l0, nullptr, &ls); }
+  { Buffer ll = E.alloc(E.n); E.write_rows(ll, pk.usable_rows, &one, 1); poly_and_coset(ll, nullptr, &ls); }
+  { Buffer la = E.alloc(E.n); std::vector<Fr> ones(pk.usable_rows, one); E.write_rows(la, 0, ones.data(), ones.size()); poly_and_coset(la, nullptr, &ls); }
+  pk.l0 = std::move(ls[0]); pk.l_last = std::move(ls[1]); pk.l_active = std::move(ls[2]);
+  pk.vk_digest = vk_digest ? *vk_digest : default_vk_digest(pk);
+  return pk;
+}
+
+// ---- multi-open bookkeeping: construct_intermediate_sets --------------------------------------------------------------------
+struct OpenQuery { int poly; U256 point, eval; };            // poly: caller-assigned id
+struct RotationSet { std::vector<U256> points; std::vector<int> polys; std::vector<std::vector<U256>> evals; };
+inline std::vector<RotationSet> rotation_sets(const std::vector<OpenQuery>& queries) {
+  std::vector<int> order; std::map<int, std::vector<U256>> per_poly;
+  auto has = [](const std::vector<U256>& v, const U256& x) { for (auto& e : v) if (e == x) return true; return false; };
+  for (auto& q : queries) {
+    if (!per_poly.count(q.poly)) { per_poly[q.poly] = {}; order.push_back(q.poly); }
+    if (!has(per_poly[q.poly], q.point)) per_poly[q.poly].push_back(q.point);
+  }
+  auto sorted = [](std::vector<U256> v) { std::sort(v.begin(), v.end(), hostfield::less); return v; };
+  std::vector<RotationSet> sets;
+  for (int pid : order) {
+    std::vector<U256> key = sorted(per_poly[pid]);
+    bool placed = false;
+    for (auto& s : sets) if (s.points == key) { s.polys.push_back(pid); placed = true; break; }
+    if (!placed) sets.push_back(RotationSet{key, {pid}, {}});
+  }
+  for (auto& s : sets)
+    for (int pid : s.polys) {
+      std::vector<U256> row;
+      for (auto& pt : s.points)
+        for (auto& q : queries) if (q.poly == pid && q.point == pt) { row.push_back(q.eval); break; }
+      s.evals.push_back(row);
+    }
+  return sets;
+}
+
+// ---- create_proof ---------------------------------------------------------------------------------------------------------
+// rng(count, out): `count` Montgomery field elements, consumed in upstream's order. instances: canonical integers.
+using Rng = std::function<void(size_t, Fr*)>;
+inline std::vector<uint8_t> create_proof(Engine& E, const ProvingKey& pk, const std::vector<std::vector<U256>>& instances, const std::vector<const Fr*>& advice_columns,
+                                         const Rng& rng, EvmTranscriptWrite& transcript) {
+  const ConstraintSystem& cs = *pk.cs;
+  const size_t n = pk.n, usable = pk.usable_rows;
+  const uint32_t bf = pk.blinding_factors;
+  const uint64_t ext_n = (uint64_t)1 << E.extended_k; const int32_t rot_scale = 1 << (E.extended_k - pk.k);
+  const U256 w = omega_of(pk.k);
+  auto draw = [&](size_t count) { std::vector<Fr> v(count); if (count) rng(count, v.data()); return v; };
+  auto write_point = [&](const Point& p) { transcript.write_ec_point(p.x, p.y); };
+
+  // 1. instances
+  if (instances.size() != cs.num_instance) throw std::invalid_argument("create_proof: wrong number of instance columns (upstream: Error::InvalidInstances)");
+  if (advice_columns.size() != cs.num_advice) throw std::invalid_argument("create_proof: wrong number of advice columns");
+  for (auto& col : instances) for (auto& v : col) transcript.common_scalar(v);
+  std::vector<Buffer> inst_values, inst_polys;
+  for (auto& col : instances) {
+    if (col.size() > usable) throw std::invalid_argument("create_proof: instance column too long (upstream: Error::InstanceTooLarge)");
+    Buffer b = E.alloc(n);
+    std::vector<Fr> rows; for (auto& v : col) rows.push_back(fr_mont(v));
+    E.write_rows(b, 0, rows.data(), rows.size());
+    inst_values.push_back(std::move(b));
+  }
+  for (auto& b : inst_values) { Buffer p = E.clone(b); E.lagrange_to_coeff(p); inst_polys.push_back(std::move(p)); }
+
+  // 2. advice
+  std::vector<Buffer> advice_values, advice_polys;
+  for (auto* col : advice_columns) {
+    Buffer b = E.upload(col, n);
+    auto blind = draw(bf + 1);
+    E.write_rows(b, usable, blind.data(), blind.size());
+    advice_values.push_back(std::move(b));
+  }
+  draw(advice_values.size());
+  for (auto& pt : E.commit(SPB_BASIS_G_LAGRANGE, ptrs(advice_values), n)) write_point(pt);
+  for (auto& b : advice_values) { Buffer p = E.clone(b); E.lagrange_to_coeff(p); advice_polys.push_back(std::move(p)); }
+
+  const Fr theta = fr_mont(transcript.squeeze_challenge());
+  const Fr zero4{};
+
+  // 3. lookups: compress, permute, commit
+  struct L { Buffer compressed_input, compressed_table, permuted_input, permuted_table, permuted_input_poly, permuted_table_poly, product; };
+  std::vector<L> lookups(cs.lookups.size());
+  for (size_t li = 0; li < cs.lookups.size(); li++) {
+    L& l = lookups[li];
+    l.compressed_input = E.alloc(n); l.compressed_table = E.alloc(n);
+    E.graph_evaluate(cs.lookup_compress_program(cs.lookups[li].inputs), ptrs(pk.fixed_values), ptrs(advice_values), ptrs(inst_values), zero4, zero4, theta, zero4, l.compressed_input, n, 1);
+    E.graph_evaluate(cs.lookup_compress_program(cs.lookups[li].tables), ptrs(pk.fixed_values), ptrs(advice_values), ptrs(inst_values), zero4, zero4, theta, zero4, l.compressed_table, n, 1);
+    l.permuted_input = E.alloc(n); l.permuted_table = E.alloc(n);
+    E.permute_expression_pair(l.compressed_input, l.compressed_table, usable, l.permuted_input, l.permuted_table);
+    { auto b = draw(bf + 1); E.write_rows(l.permuted_input, usable, b.data(), b.size()); }
+    { auto b = draw(bf + 1); E.write_rows(l.permuted_table, usable, b.data(), b.size()); }
+    draw(2);
+    for (auto& pt : E.commit(SPB_BASIS_G_LAGRANGE, {l.permuted_input.ptr(), l.permuted_table.ptr()}, n)) write_point(pt);
+    l.permuted_input_poly = E.clone(l.permuted_input); l.permuted_table_poly = E.clone(l.permuted_table);
+    E.lagrange_to_coeff(l.permuted_input_poly); E.lagrange_to_coeff(l.permuted_table_poly);
+  }
+
+  const Fr beta = fr_mont(transcript.squeeze_challenge());
+  const Fr gamma = fr_mont(transcript.squeeze_challenge());
+
+  // 4. permutation grand products
+  auto column = [&](const std::pair<Col, uint32_t>& pc, const std::vector<Buffer>& fixed, const std::vector<Buffer>& advice, const std::vector<Buffer>& inst) {
+    return (pc.first == Col::Fixed ? fixed : pc.first == Col::Advice ? advice : inst)[pc.second].ptr();
+  };
+  std::vector<const Fr*> col_values;
+  for (auto& pc : cs.permutation) col_values.push_back(column(pc, pk.fixed_values, advice_values, inst_values));
+  const uint32_t chunk = cs.chunk_len();
+  std::vector<Buffer> perm_polys;
+  Fr last_z = fr_mont(u256(1));
+  for (size_t lo = 0; lo < col_values.size(); lo += chunk) {
+    size_t hi = std::min(lo + chunk, col_values.size());
+    Buffer z = E.alloc(n);
+    std::vector<const Fr*> vals(col_values.begin() + lo, col_values.begin() + hi), sig;
+    for (size_t c = lo; c < hi; c++) sig.push_back(pk.sigma_values[c].ptr());
+    last_z = E.permutation_product(vals, sig, (uint32_t)lo, beta, gamma, draw(bf), last_z, z);
+    draw(1);
+    perm_polys.push_back(std::move(z));
+  }
+  if (!perm_polys.empty()) for (auto& pt : E.commit(SPB_BASIS_G_LAGRANGE, ptrs(perm_polys), n)) write_point(pt);
+  for (auto& p : perm_polys) E.lagrange_to_coeff(p);
+
+  // 5. lookup grand products
+  for (auto& l : lookups) {
+    l.product = E.alloc(n);
+    E.lookup_product(l.compressed_input, l.compressed_table, l.permuted_input, l.permuted_table, beta, gamma, draw(bf), l.product);
+    draw(1);
+  }
+  if (!lookups.empty()) {
+    std::vector<const Fr*> zs; for (auto& l : lookups) zs.push_back(l.product.ptr());
+    for (auto& pt : E.commit(SPB_BASIS_G_LAGRANGE, zs, n)) write_point(pt);
+  }
+  for (auto& l : lookups) {
+    E.lagrange_to_coeff(l.product);
+    l.compressed_input.release(); l.compressed_table.release(); l.permuted_input.release(); l.permuted_table.release();
+  }
+
+  // 6. vanishing argument: random polynomial
+  Buffer random_poly;
+  { auto r = draw(n); random_poly = E.upload(r.data(), n); }
+  draw(1);
+  write_point(E.commit(SPB_BASIS_G, {random_poly.ptr()}, n)[0]);
+
+  const Fr y = fr_mont(transcript.squeeze_challenge());
+
+  // 7. quotient
+  Buffer h_coeff;
+  const uint32_t pieces_n = (uint32_t)cs.degree() - 1;
+  {
+    std::vector<Buffer> advice_cosets, inst_cosets;
+    for (auto& p : advice_polys) advice_cosets.push_back(E.coeff_to_extended(p));
+    for (auto& p : inst_polys) inst_cosets.push_back(E.coeff_to_extended(p));
+    Buffer values = E.alloc(ext_n);
+    if (!cs.gates.empty()) E.graph_evaluate(cs.gates_program(), ptrs(pk.fixed_cosets), ptrs(advice_cosets), ptrs(inst_cosets), beta, gamma, theta, y, values, ext_n, rot_scale);
+    if (!perm_polys.empty()) {
+      std::vector<Buffer> z_cosets;
+      for (auto& p : perm_polys) z_cosets.push_back(E.coeff_to_extended(p));
+      std::vector<const Fr*> cosets;
+      for (auto& pc : cs.permutation) cosets.push_back(column(pc, pk.fixed_cosets, advice_cosets, inst_cosets));
+      U256 ew = root_of_unity(); for (uint32_t i = E.extended_k; i < 28; i++) ew = mulmod(ew, ew);
+      E.permutation_constraints(values, ext_n, rot_scale, -(int32_t)(bf + 1), chunk, ptrs(z_cosets), cosets, ptrs(pk.sigma_cosets), pk.l0, pk.l_last, pk.l_active, beta, gamma, y, fr_mont(ew));
+    }
+    for (size_t li = 0; li < lookups.size(); li++) {
+      L& l = lookups[li];
+      Buffer table_value = E.alloc(ext_n);
+      E.graph_evaluate(cs.lookup_value_program(li), ptrs(pk.fixed_cosets), ptrs(advice_cosets), ptrs(inst_cosets), beta, gamma, theta, zero4, table_value, ext_n, rot_scale);
+      Buffer pc = E.coeff_to_extended(l.product), ic = E.coeff_to_extended(l.permuted_input_poly), tc = E.coeff_to_extended(l.permuted_table_poly);
+      E.lookup_constraints(values, ext_n, rot_scale, pc, ic, tc, table_value, pk.l0, pk.l_last, pk.l_active, beta, gamma, y);
+    }
+    E.divide_by_vanishing(values);
+    h_coeff = E.extended_to_coeff(values, n * pieces_n);
+  }
+  std::vector<Buffer> h_pieces;
+  for (uint32_t i = 0; i < pieces_n; i++) h_pieces.push_back(Buffer::view(h_coeff, (size_t)i * n, (size_t)(i + 1) * n));
+  draw(pieces_n);
+  for (auto& pt : E.commit(SPB_BASIS_G, ptrs(h_pieces), n)) write_point(pt);
+
+  const U256 x = transcript.squeeze_challenge();
+  auto x_pow = [&](int32_t rot) { int64_t r = ((int64_t)rot % (int64_t)n + (int64_t)n) % (int64_t)n; return mulmod(x, powmod(w, (uint64_t)r)); };
+
+  // 8. evaluations in the verifier's read order; poly ids for the multi-open
+  std::vector<const Fr*> poly_ptr; std::map<std::string, int> ids;
+  auto id_of = [&](const std::string& name, const Fr* p) { auto it = ids.find(name); if (it != ids.end()) return it->second; ids[name] = (int)poly_ptr.size(); poly_ptr.push_back(p); return (int)poly_ptr.size() - 1; };
+  struct Ev { int poly; U256 point, eval; };
+  auto ev = [&](const std::string& name, const Fr* p, int32_t rot) { U256 pt = x_pow(rot); return Ev{id_of(name, p), pt, E.eval_polynomial(p, n, pt)}; };
+  std::vector<Ev> adv_e, fix_e, sig_e;
+  for (auto& q : cs.advice_queries) adv_e.push_back(ev("advice" + std::to_string(q.first), advice_polys[q.first].ptr(), q.second));
+  for (auto& q : cs.fixed_queries) fix_e.push_back(ev("fixed" + std::to_string(q.first), pk.fixed_polys[q.first].ptr(), q.second));
+  for (auto& e : adv_e) transcript.write_scalar(e.eval);
+  for (auto& e : fix_e) transcript.write_scalar(e.eval);
+  Buffer h_poly = E.alloc(n);
+  E.lincomb(ptrs(h_pieces), fr_mont(powmod(x, n)), h_poly, n);
+  Ev rnd_e = ev("random", random_poly.ptr(), 0);
+  transcript.write_scalar(rnd_e.eval);
+  for (size_t c = 0; c < pk.sigma_polys.size(); c++) sig_e.push_back(ev("sigma" + std::to_string(c), pk.sigma_polys[c].ptr(), 0));
+  for (auto& e : sig_e) transcript.write_scalar(e.eval);
+  struct PermEv { Ev e0, e1, el; bool has_last; };
+  std::vector<PermEv> perm_e;
+  for (size_t s = 0; s < perm_polys.size(); s++) {
+    const std::string name = "perm" + std::to_string(s);
+    PermEv pe{ev(name, perm_polys[s].ptr(), 0), ev(name, perm_polys[s].ptr(), 1), Ev{}, false};
+    transcript.write_scalar(pe.e0.eval); transcript.write_scalar(pe.e1.eval);
+    if (s + 1 < perm_polys.size()) { pe.el = ev(name, perm_polys[s].ptr(), -(int32_t)(bf + 1)); pe.has_last = true; transcript.write_scalar(pe.el.eval); }
+    perm_e.push_back(pe);
+  }
+  struct LookEv { Ev pe, pne, ie, iie, te; };
+  std::vector<LookEv> look_e;
+  for (size_t li = 0; li < lookups.size(); li++) {
+    L& l = lookups[li];
+    const std::string s = std::to_string(li);
+    LookEv le{ev("lk_z" + s, l.product.ptr(), 0), ev("lk_z" + s, l.product.ptr(), 1), ev("lk_a" + s, l.permuted_input_poly.ptr(), 0),
+              ev("lk_a" + s, l.permuted_input_poly.ptr(), -1), ev("lk_s" + s, l.permuted_table_poly.ptr(), 0)};
+    for (const Ev* e : {&le.pe, &le.pne, &le.ie, &le.iie, &le.te}) transcript.write_scalar(e->eval);
+    look_e.push_back(le);
+  }
+
+  // 9. multi-open queries in create_proof's order
+  std::vector<OpenQuery> q;
+  auto push = [&](const Ev& e) { q.push_back(OpenQuery{e.poly, e.point, e.eval}); };
+  for (auto& e : adv_e) push(e);
+  for (auto& pe : perm_e) { push(pe.e0); push(pe.e1); }
+  for (size_t s = perm_e.size(); s-- > 0;) if (perm_e[s].has_last) push(perm_e[s].el);
+  for (auto& le : look_e) { push(le.pe); push(le.ie); push(le.te); push(le.iie); push(le.pne); }
+  for (auto& e : fix_e) push(e);
+  for (auto& e : sig_e) push(e);
+  { int hid = id_of("h", h_poly.ptr()); q.push_back(OpenQuery{hid, x, E.eval_polynomial(h_poly.ptr(), n, x)}); }
+  push(rnd_e);
+
+  std::vector<Engine::OpenSet> sets;
+  for (auto& rs : rotation_sets(q)) {
+    Engine::OpenSet os;
+    for (auto& pt : rs.points) os.points.push_back(fr_mont(pt));
+    for (int pid : rs.polys) os.polys.push_back(poly_ptr[pid]);
+    for (auto& row : rs.evals) for (auto& e : row) os.evals.push_back(fr_mont(e));
+    sets.push_back(std::move(os));
+  }
+  const Fr y2 = fr_mont(transcript.squeeze_challenge());
+  const Fr v = fr_mont(transcript.squeeze_challenge());
+  spb_shplonk* handle = nullptr;
+  write_point(E.shplonk_begin(sets, y2, v, &handle));
+  const Fr u = fr_mont(transcript.squeeze_challenge());
+  write_point(E.shplonk_finish(handle, u));
+  return transcript.proof();
+}
+
+}  // namespace plonk
 
 }  // namespace halo2

@@ -82,3 +82,73 @@ def test_keccak_and_transcript(hooks):
     assert bytes(proof[:n]) == bytes(T.proof)
     assert [_i(c) for c in chal_a] == chal
     assert list(absorbed[:len(T.absorbed)]) == T.absorbed
+
+
+# ---- the whole driver: C++ keygen + create_proof over the test-only ABI shim vs the Python driver on the oracle engine ------
+def _build_shim_and_main():
+    from oracle import oracle as orc
+    orc.build()
+    shim_dir = os.path.join(ROOT, "tests", "abi_shim")
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    shim = os.path.join(shim_dir, "libspb_shim.so")
+    hdrs = [os.path.join(ROOT, "include", h) for h in ("spectre_b200.h", "spectre_b200_prover.hpp")]
+    src = os.path.join(shim_dir, "shim.cpp")
+    if not os.path.exists(shim) or os.path.getmtime(shim) < max(os.path.getmtime(p) for p in [src] + hdrs):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-o", shim, src, "-L" + ref_dir, "-lhalo2_oracle", "-Wl,-rpath," + ref_dir])
+    exe = os.path.join(ROOT, "tests", "cpp", "prover_main")
+    msrc = exe + ".cpp"
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(p) for p in [msrc, shim] + hdrs):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, msrc, "-L" + shim_dir, "-lspb_shim", "-Wl,-rpath," + shim_dir, "-L" + ref_dir, "-lhalo2_oracle",
+                               "-Wl,-rpath," + ref_dir])
+    return exe
+
+
+class _RecordingRng:
+    def __init__(self, inner):
+        self.inner, self.calls = inner, []
+
+    def __call__(self, count):
+        out = self.inner(count)
+        self.calls.append(np.ascontiguousarray(out, dtype=np.uint64).reshape(-1, 4))
+        return out
+
+
+@pytest.mark.parametrize("shape,k", [("aggregation", 7), ("halo2lib", 8)])
+def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k):
+    """include/spectre_b200_prover.hpp (keygen + create_proof in C++) over the test-only CPU shim of the C ABI produces the
+    same VK commitments and the same proof bytes as spectre_b200/plonk.py on the oracle engine, from the same columns, copies
+    and RNG stream."""
+    from spectre_b200 import circuits, plonk
+    from tests.plonk_oracle_engine import OracleEngine, SeededRng
+    exe = _build_shim_and_main()
+    instances = [7, 8, 9]
+    if shape == "aggregation":
+        cs = circuits.aggregation_shape()
+        fixed, adv, copies = circuits.aggregation_witness(cs, k, instances, lookup_bits=3, groups=20)
+        adv = [adv]; head = "shape aggregation"
+    else:
+        cs = circuits.halo2lib_shape(3, 2)
+        fixed, adv, copies = circuits.halo2lib_witness(cs, k, instances, lookup_bits=4, groups=20, num_gate_advice=3, num_lookup_advice=2)
+        head = "shape halo2lib 3 2"
+    digest = 0x1234567890abcdef1234
+    E = OracleEngine(k, cs.degree())
+    pk = plonk.keygen(E, cs, k, fixed, copies, vk_digest=digest)
+    rec = _RecordingRng(SeededRng(77))
+    proof = plonk.create_proof(E, pk, [instances], adv, rec, EvmTranscriptWrite(pk.vk_digest))
+    d = str(tmp_path)
+    with open(os.path.join(d, "meta.txt"), "w") as f:
+        f.write(head + "\nk %d\ndigest %x\ninstances %s\n" % (k, digest, " ".join("%x" % v for v in instances)))
+        for (c1, r1), (c2, r2) in copies:
+            f.write("copy %d %d %d %d\n" % (c1, r1, c2, r2))
+        f.write("rng " + " ".join(str(c.shape[0]) for c in rec.calls) + "\n")
+    np.concatenate(fixed).tofile(os.path.join(d, "fixed.bin"))
+    np.concatenate(adv).tofile(os.path.join(d, "advice.bin"))
+    np.concatenate([c for c in rec.calls if c.shape[0]] or [np.zeros((0, 4), np.uint64)]).tofile(os.path.join(d, "rng.bin"))
+    orc.srs_tau().tofile(os.path.join(d, "tau.bin"))
+    out = subprocess.run([exe, d], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    with open(os.path.join(d, "vk.txt")) as f:
+        vk = [(int(l[:64], 16), int(l[64:128], 16)) for l in f.read().split()]
+    assert vk == pk.fixed_commitments + pk.sigma_commitments
+    with open(os.path.join(d, "proof.bin"), "rb") as f:
+        assert f.read() == proof
