@@ -6,6 +6,9 @@
 #include <iostream>
 #include <sstream>
 
+#ifdef SPB_PROVER_WITH_CUDART
+#include <cuda_runtime.h>
+#endif
 #include "../../include/spectre_b200_prover.hpp"
 
 using namespace halo2;
@@ -80,7 +83,11 @@ int main(int argc, char** argv) {
     std::ifstream tf(dir + "/tau.bin", std::ios::binary); Fr tau; tf.read((char*)&tau, 32);
     spb_srs* srs = nullptr;
     if (spb_srs_setup(ctx, k, &tau, &srs) != 0) throw std::runtime_error(std::string("spb_srs_setup: ") + spb_last_error(ctx));
-    HostMemory mem;
+#ifdef SPB_PROVER_WITH_CUDART
+    CudaMemory mem;      // the real library: device buffers through the CUDA runtime
+#else
+    HostMemory mem;      // the CPU shim: "device" pointers are host pointers
+#endif
     {
       Engine E(ctx, mem, srs, k, (uint32_t)cs.degree());
       ProvingKey pk = keygen(E, cs, fixed, copies, &digest);

@@ -152,3 +152,49 @@ def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k):
     assert vk == pk.fixed_commitments + pk.sigma_commitments
     with open(os.path.join(d, "proof.bin"), "rb") as f:
         assert f.read() == proof
+
+
+def _build_main_against_the_real_library():
+    from spectre_b200 import build
+    lib = build.build()
+    libdir = os.path.dirname(lib)
+    exe = os.path.join(ROOT, "tests", "cpp", "prover_main_cuda")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-DSPB_PROVER_WITH_CUDART", "-I" + os.path.join(cuda, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "prover_main.cpp"), "-L" + libdir, "-lspectre_b200", "-Wl,-rpath," + libdir,
+                           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + os.path.join(cuda, "lib64")])
+    return exe
+
+
+def test_cpp_driver_links_against_the_real_library():
+    """the same main builds with CudaMemory against libspectre_b200.so + cudart (every ABI symbol the driver uses exists there)"""
+    assert os.path.exists(_build_main_against_the_real_library())
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("SPB_TEST_CPP_DRIVER", "0") == "0", reason="first GPU run of the compiled driver is opt-in until validated (DESIGN.md section 8)")
+def test_cpp_driver_on_the_gpu_reproduces_the_oracle_proof(orc, tmp_path):
+    from spectre_b200 import circuits, plonk
+    from tests.plonk_oracle_engine import OracleEngine, SeededRng
+    exe = _build_main_against_the_real_library()
+    k, instances = 8, [7, 8, 9]
+    cs = circuits.halo2lib_shape(3, 2)
+    fixed, adv, copies = circuits.halo2lib_witness(cs, k, instances, lookup_bits=4, groups=20, num_gate_advice=3, num_lookup_advice=2)
+    digest = 0x1234567890abcdef1234
+    E = OracleEngine(k, cs.degree())
+    pk = plonk.keygen(E, cs, k, fixed, copies, vk_digest=digest)
+    rec = _RecordingRng(SeededRng(77))
+    proof = plonk.create_proof(E, pk, [instances], adv, rec, EvmTranscriptWrite(pk.vk_digest))
+    d = str(tmp_path)
+    with open(os.path.join(d, "meta.txt"), "w") as f:
+        f.write("shape halo2lib 3 2\nk %d\ndigest %x\ninstances %s\n" % (k, digest, " ".join("%x" % v for v in instances)))
+        for (c1, r1), (c2, r2) in copies:
+            f.write("copy %d %d %d %d\n" % (c1, r1, c2, r2))
+        f.write("rng " + " ".join(str(c.shape[0]) for c in rec.calls) + "\n")
+    np.concatenate(fixed).tofile(os.path.join(d, "fixed.bin")); np.concatenate(adv).tofile(os.path.join(d, "advice.bin"))
+    np.concatenate([c for c in rec.calls if c.shape[0]]).tofile(os.path.join(d, "rng.bin"))
+    orc.srs_tau().tofile(os.path.join(d, "tau.bin"))
+    out = subprocess.run([exe, d], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    with open(os.path.join(d, "proof.bin"), "rb") as f:
+        assert f.read() == proof
