@@ -5,7 +5,7 @@ Commitments use the known-tau shortcut of the seed-0 SRS (commit(p) = p(tau) * G
 import numpy as np
 
 from oracle import oracle as orc
-from spectre_b200 import halo2, plonk
+from spectre_b200 import halo2
 
 
 class Buf:
@@ -86,7 +86,7 @@ class SeededRng:
     """Deterministic stand-in for the `rng: R` argument of create_proof: ChaCha20 Fr draws (the oracle's generator),
     consumed strictly in order so both engines see the same values at the same protocol positions."""
 
-    def __init__(self, seed, chunk=1 << 12):
+    def __init__(self, seed):
         self.seed, self.counter = seed, 0
 
     def __call__(self, count):
