@@ -60,6 +60,15 @@ def test_product_never_imports_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     text = f.read()
                 assert "halo2_oracle" not in text and "from oracle" not in text and "import oracle" not in text, fn
+                assert "abi_shim" not in text and "spb_shim" not in text, fn      # the test-only CPU stand-in of the ABI
+
+
+def test_product_library_has_no_cpu_stand_in(libpath):
+    """libspectre_b200.so neither links nor embeds the oracle or the test-only ABI shim"""
+    needed = subprocess.check_output(["readelf", "-d", libpath], text=True)
+    assert "halo2_oracle" not in needed and "spb_shim" not in needed
+    syms = subprocess.check_output(["nm", "-D", libpath], text=True)
+    assert " orc_" not in syms
 
 
 def _build_cpp_mirror(libpath):
