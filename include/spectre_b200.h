@@ -14,6 +14,16 @@
  *   spb_g1          : Jacobian {x, y, z}, 96 bytes, affine = (x/z^2, y/z^3), identity z = 0
  * Pointers are HOST pointers unless a function name ends in `_dev`; the library never keeps a caller pointer
  * after returning and never frees caller memory. All functions are thread-safe (one lock per context).
+ *
+ * Stream contract of the `_dev` entry points: the library enqueues its work on the context's own non-blocking stream
+ * of that device (spb_stream) -- MSMs on lane streams that first wait for it -- and returns only after that work has
+ * completed, so results are visible to any stream on return. Inputs are the caller's side of the contract: a device
+ * buffer passed to a `_dev` call must either have been produced on spb_stream(ctx, i) (enqueue your memsets / copies /
+ * kernels there, as include/spectre_b200_prover.hpp's CudaMemory and the Python DeviceEngine do: no synchronisation is
+ * needed then) or be complete, i.e. the producing stream synchronised, before the call. The legacy default stream does
+ * NOT order against spb_stream (it is created with cudaStreamNonBlocking).
+ * Concurrency (Spectre's RPC `--concurrency N`, prover/src/prover.rs:114): one context serialises its calls; open one
+ * context per concurrent proof on the same device(s) -- they share nothing but the GPU and may share one spb_srs.
  * Return value: 0 = ok, negative = error (spb_last_error gives the text); nothing aborts or throws.
  * There is no CPU fallback inside the library: without a usable CUDA device spb_init fails.
  */
@@ -51,8 +61,8 @@ typedef struct spb_domain spb_domain; /* EvaluationDomain<Fr> constants */
 
 /* ---- context -------------------------------------------------------------------------------------------- */
 /* One context drives n_dev devices of this process (device_ids == NULL: devices 0..n_dev-1). With n_dev > 1
- * an MSM is sharded by point range over the devices and the partial sums are folded on the host; NTTs run
- * on the first device. Multi-process use (one context per rank, torch.distributed / NCCL between ranks) is
+ * an MSM is sharded by point range over the devices and the partial sums are folded on the host; host-buffer NTTs of
+ * 2^16 points and more run six-step across all devices (one NVLink all-to-all), `_dev` NTTs on the first device. Multi-process use (one context per rank, torch.distributed / NCCL between ranks) is
  * what bench.py does. Returns NULL on failure (no CUDA device, bad id). */
 spb_ctx* spb_init(const int* device_ids, int n_dev);
 void spb_shutdown(spb_ctx* ctx);
@@ -62,6 +72,9 @@ const char* spb_last_error(spb_ctx* ctx);
 uint64_t spb_kernel_launches(spb_ctx* ctx);
 float spb_last_device_ms(spb_ctx* ctx);
 int spb_device_count(void);
+/* The CUDA stream (a cudaStream_t) every `_dev` call of device `dev_index` of this context is ordered on; NULL on a bad
+ * index. See "Stream contract" above. */
+void* spb_stream(spb_ctx* ctx, int dev_index);
 /* pin / unpin a caller buffer so host<->device copies run at full PCIe rate (optional) */
 int spb_host_register(spb_ctx* ctx, void* ptr, size_t bytes);
 int spb_host_unregister(spb_ctx* ctx, void* ptr);
@@ -259,8 +272,8 @@ int spb_g1_fixed_base_mul(spb_ctx* ctx, const spb_fr* scalars, size_t n, spb_g1_
 /* Elementwise device arithmetic exposed for parity tests of the field/curve layer: op 0 mul, 1 add, 2 sub;
  * field 0 = Fr, 1 = Fq. */
 int spb_test_field_op(spb_ctx* ctx, int field, int op, const spb_fr* a, const spb_fr* b, spb_fr* out, size_t n);
-/* modular-multiply throughput microbenchmark: `iters` dependent products per thread over `threads` threads;
- * returns device milliseconds in *ms. */
+/* modular-multiply throughput microbenchmark: `iters` dependent products per thread over `threads` threads, `ilp`
+ * independent chains each (1, 2 or 4; ilp | 0x100 = two chains of squarings); returns device milliseconds in *ms. */
 int spb_bench_modmul(spb_ctx* ctx, int field, uint32_t threads, uint32_t iters, int ilp, float* ms);
 /* raw issue-rate probe of one pipe (8 independent chains per thread, `iters` x 8 instructions each):
  * kind 0 IMAD.WIDE, 1 IMAD, 2 DFMA, 3 IMAD.WIDE+DFMA interleaved, 4 IADD, 5 IMAD.WIDE+IADD interleaved. */

@@ -322,23 +322,26 @@ struct ConstraintSystem {
     }
     fixed_queries = q.fixed; advice_queries = q.advice; instance_queries = q.instance;
   }
+  int minimum_degree = 0;                                   // ConstraintSystem::set_minimum_degree
+  // ConstraintSystem::degree: permutation::Argument::required_degree() = 3 enters with or without equality columns; a lookup
+  // needs max(4, 2 + input_degree + table_degree) with both degrees floored at 1; then the gates and minimum_degree
   int degree() const {
-    int d = permutation.empty() ? 1 : 3;
+    int d = 3;
     for (auto& l : lookups) {
-      int di = 0, dt = 0;
+      int di = 1, dt = 1;
       for (auto& e : l.inputs) di = std::max(di, plonk::degree(e));
       for (auto& e : l.tables) dt = std::max(dt, plonk::degree(e));
       d = std::max(d, std::max(4, 2 + di + dt));
     }
     for (auto& g : gates) d = std::max(d, plonk::degree(g));
-    return d;
+    return std::max(d, minimum_degree);
   }
   uint32_t blinding_factors() const {
     uint32_t mx = num_advice ? 0 : 1;
     for (uint32_t c = 0; c < num_advice; c++) { uint32_t cnt = 0; for (auto& q : advice_queries) if (q.first == c) cnt++; mx = std::max(mx, cnt); }
     return std::max<uint32_t>(3, mx) + 2;
   }
-  uint32_t chunk_len() const { return (uint32_t)std::max(1, degree() - 2); }
+  uint32_t chunk_len() const { return (uint32_t)(degree() - 2); }
   Graph gates_program() const { Program p; p.horner({K_PREV, 0}, {K_Y, 0}, gates); return p.finish(); }
   Graph lookup_compress_program(const std::vector<ExprP>& exprs) const { Program p; p.horner(p.constant(u256(0)), {K_THETA, 0}, exprs); return p.finish(); }
   Graph lookup_value_program(size_t li) const {
@@ -368,13 +371,25 @@ struct HostMemory : DeviceMemory {                           // "device" = host:
   void copy(Fr* d, const Fr* s, size_t rows) override { memcpy(d, s, rows * sizeof(Fr)); }
 };
 #ifdef SPB_PROVER_WITH_CUDART
+// Device memory for the real library. Every memset / copy is enqueued on the context's own stream (spb_stream), which is
+// the stream every `_dev` entry point is ordered on: a buffer is therefore ready for the library call that follows without
+// any synchronisation (stream contract in spectre_b200.h; the legacy default stream would NOT order against that stream).
 struct CudaMemory : DeviceMemory {
+  explicit CudaMemory(spb_ctx* ctx) : stream_((cudaStream_t)spb_stream(ctx, 0)) { if (!stream_) throw std::runtime_error("CudaMemory: spb_stream returned no stream"); }
   static void ck(cudaError_t e) { if (e != cudaSuccess) throw std::runtime_error(std::string("cuda: ") + cudaGetErrorString(e)); }
-  Fr* alloc(size_t rows) override { void* p; ck(cudaMalloc(&p, (rows ? rows : 1) * sizeof(Fr))); ck(cudaMemset(p, 0, (rows ? rows : 1) * sizeof(Fr))); return (Fr*)p; }
-  void free(Fr* p) override { cudaFree(p); }
-  void upload(Fr* d, const Fr* s, size_t rows) override { ck(cudaMemcpy(d, s, rows * sizeof(Fr), cudaMemcpyHostToDevice)); }
-  void download(Fr* d, const Fr* s, size_t rows) override { ck(cudaMemcpy(d, s, rows * sizeof(Fr), cudaMemcpyDeviceToHost)); }
-  void copy(Fr* d, const Fr* s, size_t rows) override { ck(cudaMemcpy(d, s, rows * sizeof(Fr), cudaMemcpyDeviceToDevice)); }
+  Fr* alloc(size_t rows) override {
+    void* p; ck(cudaMalloc(&p, (rows ? rows : 1) * sizeof(Fr))); ck(cudaMemsetAsync(p, 0, (rows ? rows : 1) * sizeof(Fr), stream_)); return (Fr*)p;
+  }
+  void free(Fr* p) override { cudaFree(p); }                 // synchronises the device: nothing in flight can still use p
+  void upload(Fr* d, const Fr* s, size_t rows) override {    // s may be a temporary: it must be consumed before returning
+    ck(cudaMemcpyAsync(d, s, rows * sizeof(Fr), cudaMemcpyHostToDevice, stream_)); ck(cudaStreamSynchronize(stream_));
+  }
+  void download(Fr* d, const Fr* s, size_t rows) override {
+    ck(cudaMemcpyAsync(d, s, rows * sizeof(Fr), cudaMemcpyDeviceToHost, stream_)); ck(cudaStreamSynchronize(stream_));
+  }
+  void copy(Fr* d, const Fr* s, size_t rows) override { ck(cudaMemcpyAsync(d, s, rows * sizeof(Fr), cudaMemcpyDeviceToDevice, stream_)); }
+ private:
+  cudaStream_t stream_;
 };
 #endif
 
@@ -481,6 +496,7 @@ class Engine {
     check(spb_shplonk_begin_dev(ctx_, srs_, n, raw.data(), (uint32_t)raw.size(), &y, &v, &h, handle), "spb_shplonk_begin_dev");
     return to_affine(h);
   }
+  void shplonk_abort(spb_shplonk* handle) { spb_shplonk_abort(ctx_, handle); }
   Point shplonk_finish(spb_shplonk* handle, const Fr& u) {
     spb_g1 c;
     check(spb_shplonk_finish_dev(ctx_, handle, &u, &c), "spb_shplonk_finish_dev");
@@ -496,7 +512,7 @@ class Engine {
 // ---- keygen ---------------------------------------------------------------------------------------------------------------
 using Cell = std::pair<uint32_t, uint64_t>;                  // (index in cs.permutation, row)
 struct ProvingKey {
-  const ConstraintSystem* cs = nullptr;
+  ConstraintSystem cs;                                      // held by value (expression nodes are shared_ptr): a cached key never dangles
   uint32_t k = 0; size_t n = 0; uint32_t blinding_factors = 0; size_t usable_rows = 0;
   std::vector<Buffer> fixed_values, fixed_polys, fixed_cosets, sigma_values, sigma_polys, sigma_cosets;
   Buffer l0, l_last, l_active;
@@ -548,7 +564,7 @@ inline U256 default_vk_digest(const ProvingKey& pk) {
 inline ProvingKey keygen(Engine& E, const ConstraintSystem& cs, const std::vector<const Fr*>& fixed_columns, const std::vector<std::pair<Cell, Cell>>& copies,
                          const U256* vk_digest = nullptr) {
   ProvingKey pk;
-  pk.cs = &cs; pk.k = E.k; pk.n = E.n;
+  pk.cs = cs; pk.k = E.k; pk.n = E.n;
   pk.blinding_factors = cs.blinding_factors(); pk.usable_rows = E.n - (pk.blinding_factors + 1);
   for (auto* c : fixed_columns) pk.fixed_values.push_back(E.upload(c, E.n));
   pk.sigma_values = build_sigma(E, cs, copies);
@@ -605,7 +621,7 @@ inline std::vector<RotationSet> rotation_sets(const std::vector<OpenQuery>& quer
 using Rng = std::function<void(size_t, Fr*)>;
 inline std::vector<uint8_t> create_proof(Engine& E, const ProvingKey& pk, const std::vector<std::vector<U256>>& instances, const std::vector<const Fr*>& advice_columns,
                                          const Rng& rng, EvmTranscriptWrite& transcript) {
-  const ConstraintSystem& cs = *pk.cs;
+  const ConstraintSystem& cs = pk.cs;
   const size_t n = pk.n, usable = pk.usable_rows;
   const uint32_t bf = pk.blinding_factors;
   const uint64_t ext_n = (uint64_t)1 << E.extended_k; const int32_t rot_scale = 1 << (E.extended_k - pk.k);
@@ -800,9 +816,13 @@ inline std::vector<uint8_t> create_proof(Engine& E, const ProvingKey& pk, const 
   }
   const Fr y2 = fr_mont(transcript.squeeze_challenge());
   const Fr v = fr_mont(transcript.squeeze_challenge());
-  spb_shplonk* handle = nullptr;
-  write_point(E.shplonk_begin(sets, y2, v, &handle));
+  struct OpenGuard {                                         // releases the library's SHPLONK workspace if anything throws in between
+    Engine& E; spb_shplonk* h = nullptr;
+    ~OpenGuard() { if (h) E.shplonk_abort(h); }
+  } open{E};
+  write_point(E.shplonk_begin(sets, y2, v, &open.h));
   const Fr u = fr_mont(transcript.squeeze_challenge());
+  spb_shplonk* handle = open.h; open.h = nullptr;            // spb_shplonk_finish_dev consumes the handle, also on error
   write_point(E.shplonk_finish(handle, u));
   return transcript.proof();
 }

@@ -11,8 +11,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libspectre_b200.so")
-OBJDIR = os.path.join(HERE, "_obj")
+# A/B experiments: SPB_BUILD_VARIANT=name SPB_BUILD_FLAGS="-DX ..." builds libspectre_b200_name.so next to the product
+# library (select it at run time with SPB_LIB_PATH); the product is always the plain name with no extra flags.
+VARIANT = os.environ.get("SPB_BUILD_VARIANT", "")
+EXTRA_FLAGS = os.environ.get("SPB_BUILD_FLAGS", "").split() if VARIANT else []
+OUT = os.path.join(HERE, "libspectre_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
+OBJDIR = os.path.join(HERE, "_obj" + ("_" + VARIANT if VARIANT else ""))
 SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "poly.cu", "quotient.cu", "lookup.cu", "plonk.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -32,7 +36,7 @@ def needs_build():
 
 def _compile(src, verbose):
     obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + FLAGS + EXTRA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -54,7 +54,7 @@ __global__ void field_op_kernel(int op, const Fp<P>* a, const Fp<P>* b, Fp<P>* o
 }
 
 // ILP independent multiply chains per thread; result folded and written so nothing is optimised away
-template <class P, int ILP>
+template <class P, int ILP, bool SQR = false>
 __global__ void modmul_bench_kernel(Fp<P>* out, uint32_t iters) {
   Fp<P> x[ILP], y;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,7 +63,7 @@ __global__ void modmul_bench_kernel(Fp<P>* out, uint32_t iters) {
   y = x[0]; y.l[1] ^= 0x9e3779b9u;
   for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
-    for (int j = 0; j < ILP; j++) x[j] = fp_mul(x[j], y);
+    for (int j = 0; j < ILP; j++) x[j] = SQR ? fp_sqr(x[j]) : fp_mul(x[j], y);
   }
   Fp<P> acc = x[0];
 #pragma unroll
@@ -120,6 +120,7 @@ spb_ctx* spb_init(const int* device_ids, int n_dev) {
     d.sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     cudaEventCreate(&d.ev0); cudaEventCreate(&d.ev1);
+    cudaEventCreateWithFlags(&d.dep_ev, cudaEventDisableTiming);
     for (int e = 0; e < 8; e++) cudaEventCreate(&d.stage_ev[e]);
     d.pinned_cap = 1 << 20;
     if (cudaMallocHost(&d.pinned, d.pinned_cap) != cudaSuccess) { delete ctx; return nullptr; }
@@ -151,7 +152,7 @@ void spb_shutdown(spb_ctx* ctx) {
     for (auto& kv : d.slots) if (kv.second.ptr) cudaFree(kv.second.ptr);
     for (auto& t : d.ntt_tables) { cudaFree(t.tw_lo); cudaFree(t.tw_hi); if (t.tw_full) cudaFree(t.tw_full); }
     if (d.pinned) cudaFreeHost(d.pinned);
-    cudaEventDestroy(d.ev0); cudaEventDestroy(d.ev1);
+    cudaEventDestroy(d.ev0); cudaEventDestroy(d.ev1); cudaEventDestroy(d.dep_ev);
     for (int e = 0; e < 8; e++) cudaEventDestroy(d.stage_ev[e]);
     cudaStreamDestroy(d.stream);
   }
@@ -161,6 +162,11 @@ void spb_shutdown(spb_ctx* ctx) {
 const char* spb_last_error(spb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 uint64_t spb_kernel_launches(spb_ctx* ctx) { return ctx ? ctx->n_kernel_launches : 0; }
 float spb_last_device_ms(spb_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
+
+void* spb_stream(spb_ctx* ctx, int dev_index) {
+  if (!ctx || dev_index < 0 || (size_t)dev_index >= ctx->dev.size()) return nullptr;
+  return (void*)ctx->dev[dev_index].stream;
+}
 
 int spb_host_register(spb_ctx* ctx, void* ptr, size_t bytes) {
   SPB_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
@@ -431,7 +437,10 @@ int spb_bench_modmul(spb_ctx* ctx, int field, uint32_t threads, uint32_t iters, 
   if (!buf) return SPB_ERR_OOM;
   SPB_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
   unsigned blocks = threads / 256;
-  if (field == 0) {
+  if (ilp & 0x100) {  // squaring chains (two independent ones per thread)
+    if (field == 0) modmul_bench_kernel<FrParams, 2, true><<<blocks, 256, 0, d.stream>>>((Fr*)buf, iters);
+    else modmul_bench_kernel<FqParams, 2, true><<<blocks, 256, 0, d.stream>>>((Fq*)buf, iters);
+  } else if (field == 0) {
     if (ilp == 1) modmul_bench_kernel<FrParams, 1><<<blocks, 256, 0, d.stream>>>((Fr*)buf, iters);
     else if (ilp == 2) modmul_bench_kernel<FrParams, 2><<<blocks, 256, 0, d.stream>>>((Fr*)buf, iters);
     else modmul_bench_kernel<FrParams, 4><<<blocks, 256, 0, d.stream>>>((Fr*)buf, iters);

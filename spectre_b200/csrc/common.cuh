@@ -32,6 +32,7 @@ struct DeviceState {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t dep_ev = nullptr;  // recorded on `stream` when other streams (MSM lanes, peer devices) must wait for it
   cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // MSM stage boundaries
   std::map<std::string, DevBuf> slots;
   std::vector<NttTables> ntt_tables;

@@ -42,7 +42,7 @@ SPB_HD G1Xyzz xyzz_dbl_affine(const G1Affine& p) {
   Fq m = fp_add(fp_dbl(xx), xx);
   G1Xyzz r;
   r.x = fp_sub(fp_sqr(m), fp_dbl(s));
-  r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
+  r.y = fp_mul_sub_mul(m, fp_sub(s, r.x), w, p.y);
   r.zz = v;
   r.zzz = w;
   return r;  // y = 0 cannot occur on a prime-order curve, so zz != 0
@@ -59,7 +59,7 @@ SPB_HD G1Xyzz xyzz_dbl(const G1Xyzz& p) {
   Fq m = fp_add(fp_dbl(xx), xx);
   G1Xyzz r;
   r.x = fp_sub(fp_sqr(m), fp_dbl(s));
-  r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
+  r.y = fp_mul_sub_mul(m, fp_sub(s, r.x), w, p.y);
   r.zz = fp_mul(v, p.zz);
   r.zzz = fp_mul(w, p.zzz);
   return r;
@@ -82,7 +82,7 @@ SPB_HD void xyzz_add_mixed(G1Xyzz& acc, const G1Affine& q) {
   Fq ppp = fp_mul(p, pp);
   Fq qq = fp_mul(acc.x, pp);
   Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
-  Fq y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(acc.y, ppp));
+  Fq y3 = fp_mul_sub_mul(r, fp_sub(qq, x3), acc.y, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fp_mul(acc.zz, pp);
@@ -108,7 +108,7 @@ SPB_HD void xyzz_add(G1Xyzz& acc, const G1Xyzz& q) {
   Fq ppp = fp_mul(p, pp);
   Fq qq = fp_mul(u1, pp);
   Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
-  Fq y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(s1, ppp));
+  Fq y3 = fp_mul_sub_mul(r, fp_sub(qq, x3), s1, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fp_mul(fp_mul(acc.zz, q.zz), pp);

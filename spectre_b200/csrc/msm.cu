@@ -187,6 +187,12 @@ static int job_enqueue(spb_ctx* ctx, int lane, std::vector<MsmPart>& parts) {
     Lane* ln; SPB_TRY(get_lane(ctx, p.dev_index, lane, &ln));
     p.g.L = choose_chunk(d, p.n * p.g.W);
     const Fr* ds = p.d_scalars;
+    // stream contract (spectre_b200.h): scalars produced on the context stream of the device they live on are ready for the lane
+    DeviceState& src = p.peer_src_device >= 0 ? ctx->dev[0] : d;
+    if (&src != &d) SPB_CUDA(ctx, cudaSetDevice(src.device));
+    SPB_CUDA(ctx, cudaEventRecord(src.dep_ev, src.stream));
+    if (&src != &d) SPB_CUDA(ctx, cudaSetDevice(d.device));
+    SPB_CUDA(ctx, cudaStreamWaitEvent(ln->stream, src.dep_ev, 0));
     SPB_CUDA(ctx, cudaEventRecord(ln->ev[8], ln->stream));
     if (p.h_scalars || p.peer_src_device >= 0) {
       Fr* buf = (Fr*)lane_slot(ctx, d, lane, "msm_scalars", p.n * sizeof(Fr));

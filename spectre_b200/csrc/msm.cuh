@@ -316,7 +316,10 @@ __global__ void msm_scatter_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uin
     }
   }
 }
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* total, MsmGeom g, const MsmEntry* ent,
+#ifndef SPB_ACC_MINBLOCKS
+#define SPB_ACC_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, SPB_ACC_MINBLOCKS) msm_accumulate_kernel(const uint32_t* total, MsmGeom g, const MsmEntry* ent,
                                                              const G1Affine* bases, G1Xyzz* buckets, uint32_t* head_key, G1Xyzz* head,
                                                              uint32_t* tail_key, G1Xyzz* tail) {
   msm_accumulate_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, *total, g, ent, bases, buckets, head_key, head, tail_key, tail);

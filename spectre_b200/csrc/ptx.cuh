@@ -36,10 +36,12 @@ SPB_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc
 SPB_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 SPB_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 SPB_D uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// (hi:lo) << 1, upper word: one SHF.L.W on the ALU pipe (the doubling step of a squaring)
+SPB_D uint32_t shl1_hi(uint32_t lo, uint32_t hi) { uint32_t r; asm("shf.l.clamp.b32 %0, %1, %2, 1;" : "=r"(r) : "r"(lo), "r"(hi)); return r; }
 
 // (lo,hi) = a*b
 SPB_D void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
-  asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+  asm("{ .reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
 // (lo,hi) = (clo,chi) + a*b, carry-out set, no carry-in
 SPB_D void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
@@ -67,6 +69,7 @@ inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; g
 inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - g_cf; g_cf = (uint32_t)(t >> 63); return (uint32_t)t; }
 inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - g_cf; }
 inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t shl1_hi(uint32_t lo, uint32_t hi) { return (hi << 1) | (lo >> 31); }
 inline void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a * b; lo = (uint32_t)t; hi = (uint32_t)(t >> 32); }
 inline void wide_acc_(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi, uint32_t cin, bool set) {
   unsigned __int128 t = (unsigned __int128)a * b + (((uint64_t)chi << 32) | clo) + cin;

@@ -24,7 +24,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspectre_b200.so")
+LIB_PATH = os.environ.get("SPB_LIB_PATH") or os.path.join(_HERE, "libspectre_b200.so")   # SPB_LIB_PATH: A/B builds (tools/), never the product default
 
 BASIS_G = 0
 BASIS_G_LAGRANGE = 1
@@ -106,6 +106,15 @@ class Backend:
     def check(self, rc, what):
         if rc != 0:
             raise BackendError("%s failed (%d): %s" % (what, rc, self.lib.spb_last_error(self.ctx).decode()))
+
+    def stream(self, dev_index=0):
+        """cudaStream_t (int) every `_dev` call of that device is ordered on: enqueue the producers of device buffers there."""
+        self.lib.spb_stream.restype = ctypes.c_void_p
+        self.lib.spb_stream.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        s = self.lib.spb_stream(self.ctx, dev_index)
+        if not s:
+            raise BackendError("spb_stream: no stream for device index %d" % dev_index)
+        return int(s)
 
     @property
     def kernel_launches(self):
@@ -323,7 +332,7 @@ class Backend:
         ms = ctypes.c_float(0)
         self.check(self.lib.spb_bench_modmul(self.ctx, {"fr": 0, "fq": 1}[field], ctypes.c_uint32(threads), ctypes.c_uint32(iters), ilp, ctypes.byref(ms)), "spb_bench_modmul")
         threads = (threads + 255) // 256 * 256
-        return ms.value, threads * iters * ilp / (ms.value * 1e-3)
+        return ms.value, threads * iters * (2 if ilp & 0x100 else ilp) / (ms.value * 1e-3)
 
 
     def bench_pipe(self, kind, threads=148 * 2048, iters=4000):

@@ -132,8 +132,9 @@ class Program:
 class ConstraintSystem:
     """What halo2's ConstraintSystem records at configure time, for the parts create_proof reads."""
 
-    def __init__(self, num_fixed, num_advice, num_instance, gates, lookups, permutation, fixed_queries=None, advice_queries=None):
+    def __init__(self, num_fixed, num_advice, num_instance, gates, lookups, permutation, fixed_queries=None, advice_queries=None, minimum_degree=None):
         self.num_fixed, self.num_advice, self.num_instance = num_fixed, num_advice, num_instance
+        self.minimum_degree = minimum_degree                               # ConstraintSystem::set_minimum_degree
         self.gates, self.lookups, self.permutation = list(gates), [(list(i), list(t)) for i, t in lookups], list(permutation)
         q = {"fixed": list(fixed_queries or []), "advice": list(advice_queries or []), "instance": []}
         for g in self.gates:
@@ -147,12 +148,15 @@ class ConstraintSystem:
         self.fixed_queries, self.advice_queries, self.instance_queries = q["fixed"], q["advice"], q["instance"]
 
     def degree(self):
-        d = 3 if self.permutation else 1                                    # permutation::Argument::required_degree
+        """ConstraintSystem::degree ([UPSTREAM] halo2_proofs/src/plonk/circuit.rs): the permutation argument's
+        required_degree() = 3 always enters, equality columns or not; a lookup needs max(4, 2 + input_degree + table_degree)
+        with both degrees floored at 1; then the gates; finally `minimum_degree` if the circuit set one."""
+        d = 3                                                               # permutation::Argument::required_degree
         for ins, tbs in self.lookups:                                      # lookup::Argument::required_degree
-            d = max(d, max(4, 2 + max(degree(e) for e in ins) + max(degree(e) for e in tbs)))
+            d = max(d, max(4, 2 + max([1] + [degree(e) for e in ins]) + max([1] + [degree(e) for e in tbs])))
         for g in self.gates:
             d = max(d, degree(g))
-        return d
+        return max(d, self.minimum_degree or 0)
 
     def blinding_factors(self):
         per_col = [sum(1 for c, _ in self.advice_queries if c == col) for col in range(self.num_advice)]
@@ -199,7 +203,12 @@ def uniform_residues(torch, rows, device, generator=None):
 
 # ---- the engine bound to libspectre_b200.so -----------------------------------------------------------------------
 class DeviceEngine:
-    """Buffers are torch int64 tensors of shape (rows, 4) on the context's first device (PyTorch = device memory only)."""
+    """Buffers are torch int64 tensors of shape (rows, 4) on the context's first device (PyTorch = device memory only).
+
+    Stream contract (include/spectre_b200.h): every `_dev` entry point is ordered on the context's own stream and has
+    completed when it returns. Every method below that makes torch allocate, zero, copy or assign runs with that stream
+    (spb_stream) as torch's current stream, so the driver's memory traffic is in order with the library's kernels:
+    no torch.cuda.synchronize() anywhere on the proof path (sync() exists for wall-clock laps)."""
 
     def __init__(self, backend, params, k, j):
         import torch
@@ -207,75 +216,85 @@ class DeviceEngine:
         self.dom = halo2.EvaluationDomain(backend, j, k)
         self.extended_k = self.dom.extended_k
         self.dev = torch.device("cuda", backend.devices[0])
+        self.stream = torch.cuda.ExternalStream(backend.stream(0), device=self.dev)
+        torch.cuda.synchronize(self.dev)                      # whatever the caller queued on other streams is complete
 
-    # memory
-    def alloc(self, rows): return self.torch.zeros((rows, 4), dtype=self.torch.int64, device=self.dev)
-    def upload(self, a): return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).to(self.dev)
-    def download(self, b): return b.cpu().numpy().view(np.uint64)
-    def clone(self, b): return b.clone()
+    # memory (all torch work on the context's stream)
+    def alloc(self, rows):
+        with self.torch.cuda.stream(self.stream):
+            return self.torch.zeros((rows, 4), dtype=self.torch.int64, device=self.dev)
+    def upload(self, a):
+        """host column -> device. A pinned torch tensor (witness buffers registered once by the caller) goes up as one
+        asynchronous DMA; numpy arrays take the pageable path."""
+        with self.torch.cuda.stream(self.stream):
+            if isinstance(a, self.torch.Tensor):
+                return a.view(self.torch.int64).reshape(-1, 4).to(self.dev, non_blocking=True)
+            return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).to(self.dev)
+    def download(self, b):
+        with self.torch.cuda.stream(self.stream):
+            return b.cpu().numpy().view(np.uint64)
+    def clone(self, b):
+        with self.torch.cuda.stream(self.stream):
+            return b.clone()
     def view(self, b, lo, hi): return b[lo:hi]
     def write_rows(self, b, start, rows):
         rows = np.ascontiguousarray(rows, dtype=np.uint64).reshape(-1, 4)
         if rows.shape[0]:
-            b[start:start + rows.shape[0]] = self.upload(rows)
+            with self.torch.cuda.stream(self.stream):
+                b[start:start + rows.shape[0]] = self.upload(rows)
     def read_rows(self, b, start, count): return self.download(b[start:start + count])
-    def random_rows(self, rows, generator=None): return uniform_residues(self.torch, rows, self.dev, generator)
-    def sync(self): self.torch.cuda.synchronize()
+    def random_rows(self, rows, generator=None):
+        with self.torch.cuda.stream(self.stream):
+            return uniform_residues(self.torch, rows, self.dev, generator)
+    def sync(self): self.stream.synchronize()
 
     # commitments -> affine integer pairs
     def commit(self, basis, bufs, n):
-        self.sync()
         jac = self.params.commit_batch_dev(basis, [b.data_ptr() for b in bufs], n)
         return [halo2.jacobian_to_affine_ints(p) for p in jac]
 
     # domain
-    def lagrange_to_coeff(self, b): self.sync(); self.dom.lagrange_to_coeff_dev(b.data_ptr())
+    def lagrange_to_coeff(self, b): self.dom.lagrange_to_coeff_dev(b.data_ptr())
     def coeff_to_lagrange(self, b):
-        self.sync()
         self.be.best_fft_dev(b.data_ptr(), fr_mont(omega_of(self.k)).reshape(1, 4), self.k)
     def coeff_to_extended(self, b):
-        out = self.alloc(1 << self.extended_k); self.sync()
+        out = self.alloc(1 << self.extended_k)
         self.dom.coeff_to_extended_dev(b.data_ptr(), out.data_ptr())
         return out
     def extended_to_coeff(self, e, rows):
-        out = self.alloc(rows); self.sync()
+        out = self.alloc(rows)
         self.dom.extended_to_coeff_dev(e.data_ptr(), out.data_ptr())
         return out
-    def divide_by_vanishing(self, e): self.sync(); self.dom.divide_by_vanishing_poly_dev(e.data_ptr())
+    def divide_by_vanishing(self, e): self.dom.divide_by_vanishing_poly_dev(e.data_ptr())
 
     # quotient numerator
     def graph_evaluate(self, p, fixed, advice, instance, beta, gamma, theta, y, values, size, rot_scale):
-        self.sync()
         ptr = lambda bs: [b.data_ptr() for b in bs]
         self.be.graph_evaluate_dev(p["prog"], p["ncalc"], p["ncalc"], p["constants"], p["rotations"], ptr(fixed), ptr(advice), ptr(instance),
                                    np.zeros((1, 4), np.uint64), beta, gamma, theta, y, values.data_ptr(), size, rot_scale)
     def permutation_constraints(self, values, size, rot_scale, last_rotation, chunk_len, z, cols, sigma, l0, l_last, l_active, beta, gamma, y, ext_omega):
-        self.sync()
         ptr = lambda bs: [b.data_ptr() for b in bs]
         self.be.permutation_constraints_dev(values.data_ptr(), size, rot_scale, last_rotation, chunk_len, ptr(z), ptr(cols), ptr(sigma), l0.data_ptr(),
                                             l_last.data_ptr(), l_active.data_ptr(), beta, gamma, y, ext_omega)
     def lookup_constraints(self, values, size, rot_scale, product, pin, ptab, table_value, l0, l_last, l_active, beta, gamma, y):
-        self.sync()
         self.be.lookup_constraints_dev(values.data_ptr(), size, rot_scale, product.data_ptr(), pin.data_ptr(), ptab.data_ptr(), table_value.data_ptr(),
                                        l0.data_ptr(), l_last.data_ptr(), l_active.data_ptr(), beta, gamma, y)
 
     # argument provers
     def permute_expression_pair(self, a, s, usable, out_a, out_s):
-        self.sync(); self.be.permute_expression_pair_dev(a.data_ptr(), s.data_ptr(), usable, out_a.data_ptr(), out_s.data_ptr())
+        self.be.permute_expression_pair_dev(a.data_ptr(), s.data_ptr(), usable, out_a.data_ptr(), out_s.data_ptr())
     def permutation_product(self, values, sigma, first_col, beta, gamma, blinds, last_z, z):
-        self.sync()
         return self.be.permutation_product_dev(self.k, [b.data_ptr() for b in values], [b.data_ptr() for b in sigma], first_col, beta, gamma, blinds, last_z, z.data_ptr())
     def lookup_product(self, ci, ct, pi, pt, beta, gamma, blinds, z):
-        self.sync(); self.be.lookup_product_dev(self.n, ci.data_ptr(), ct.data_ptr(), pi.data_ptr(), pt.data_ptr(), beta, gamma, blinds, z.data_ptr())
+        self.be.lookup_product_dev(self.n, ci.data_ptr(), ct.data_ptr(), pi.data_ptr(), pt.data_ptr(), beta, gamma, blinds, z.data_ptr())
 
     # batch ops
-    def eval_polynomial(self, b, n, point): self.sync(); return self.be.eval_polynomial_dev(b.data_ptr(), n, point)
-    def lincomb(self, bufs, y, out, n): self.sync(); self.be.lincomb_dev([b.data_ptr() for b in bufs], y, out.data_ptr(), n)
-    def vec_scale(self, b, alpha, n): self.sync(); self.be.vec_scale_dev(b.data_ptr(), alpha, n)
+    def eval_polynomial(self, b, n, point): return self.be.eval_polynomial_dev(b.data_ptr(), n, point)
+    def lincomb(self, bufs, y, out, n): self.be.lincomb_dev([b.data_ptr() for b in bufs], y, out.data_ptr(), n)
+    def vec_scale(self, b, alpha, n): self.be.vec_scale_dev(b.data_ptr(), alpha, n)
 
     # multi-open
     def shplonk_begin(self, sets, y, v):
-        self.sync()
         c, h = self.be.shplonk_begin_dev(self.params, self.n, [(pts, [b.data_ptr() for b in polys], ev) for pts, polys, ev in sets], y, v)
         return halo2.jacobian_to_affine_ints(c), h
     def shplonk_finish(self, state, u):
@@ -466,7 +485,7 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
 
     # 4. permutation grand products, one per chunk of columns
     col_values = [{"fixed": pk.fixed_values, "advice": advice_values, "instance": inst_values}[kind][c] for kind, c in cs.permutation]
-    chunk = max(1, cs.chunk_len())                           # without permutation columns the degree can be below 3
+    chunk = cs.chunk_len()                                   # degree() >= 3, so >= 1
     perm_z, last_z = [], fr_mont(1)
     for lo in range(0, len(col_values), chunk):
         hi = min(lo + chunk, len(col_values))

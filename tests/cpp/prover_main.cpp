@@ -2,6 +2,7 @@
 // keygen + create_proof through whatever implements the C ABI at link time (the test links tests/abi_shim) and writes the
 // proof bytes. usage: prover_main <dir>
 #include <cstdio>
+#include <chrono>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -84,20 +85,34 @@ int main(int argc, char** argv) {
     spb_srs* srs = nullptr;
     if (spb_srs_setup(ctx, k, &tau, &srs) != 0) throw std::runtime_error(std::string("spb_srs_setup: ") + spb_last_error(ctx));
 #ifdef SPB_PROVER_WITH_CUDART
-    CudaMemory mem;      // the real library: device buffers through the CUDA runtime
+    if (getenv("SPB_MAIN_TABLES") && spb_srs_precompute(ctx, srs) != 0) throw std::runtime_error(std::string("spb_srs_precompute: ") + spb_last_error(ctx));
+    CudaMemory mem(ctx); // the real library: device buffers through the CUDA runtime, on the context's stream
 #else
     HostMemory mem;      // the CPU shim: "device" pointers are host pointers
 #endif
     {
       Engine E(ctx, mem, srs, k, (uint32_t)cs.degree());
+      auto t_k0 = std::chrono::steady_clock::now();
       ProvingKey pk = keygen(E, cs, fixed, copies, &digest);
+      auto t_k1 = std::chrono::steady_clock::now();
       size_t call = 0, pos = 0;
       Rng rng = [&](size_t count, Fr* out) {
         if (call >= rng_counts.size() || rng_counts[call] != count) throw std::runtime_error("rng stream out of step at call " + std::to_string(call));
         memcpy(out, rng_raw.data() + pos * 32, count * 32); pos += count; call++;
       };
-      EvmTranscriptWrite T(pk.vk_digest);
-      std::vector<uint8_t> proof = create_proof(E, pk, {inst}, advice, rng, T);
+      // SPB_MAIN_REPEAT=r: prove r times from the same RNG stream (identical bytes each time); the last pass is the warm one
+      const int repeat = getenv("SPB_MAIN_REPEAT") ? std::max(1, atoi(getenv("SPB_MAIN_REPEAT"))) : 1;
+      std::vector<uint8_t> proof;
+      std::printf("keygen_ms %.3f\n", std::chrono::duration<double, std::milli>(t_k1 - t_k0).count());
+      for (int rep = 0; rep < repeat; rep++) {
+        call = 0; pos = 0;
+        EvmTranscriptWrite T(pk.vk_digest);
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<uint8_t> pr = create_proof(E, pk, {inst}, advice, rng, T);
+        std::printf("create_proof_ms %.3f\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        if (rep && pr != proof) throw std::runtime_error("repeated proof differs");
+        proof = pr;
+      }
       std::ofstream out(dir + "/proof.bin", std::ios::binary);
       out.write((const char*)proof.data(), proof.size());
       std::ofstream vk(dir + "/vk.txt");

@@ -6,6 +6,9 @@
 using namespace spb;
 extern "C" {
 void he_fr_mul(Fr* o, const Fr* a, const Fr* b, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fp_mul(a[i], b[i]); }
+void he_fr_sqr(Fr* o, const Fr* a, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fp_sqr(a[i]); }
+void he_fq_sqr(Fq* o, const Fq* a, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fp_sqr(a[i]); }
+void he_fq_mul_sub_mul(Fq* o, const Fq* a, const Fq* b, const Fq* c, const Fq* d, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fp_mul_sub_mul(a[i], b[i], c[i], d[i]); }
 void he_fr_add(Fr* o, const Fr* a, const Fr* b, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fp_add(a[i], b[i]); }
 void he_fr_sub(Fr* o, const Fr* a, const Fr* b, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fp_sub(a[i], b[i]); }
 void he_fr_neg(Fr* o, const Fr* a, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fp_neg(a[i]); }

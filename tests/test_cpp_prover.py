@@ -171,9 +171,23 @@ def test_cpp_driver_links_against_the_real_library():
     assert os.path.exists(_build_main_against_the_real_library())
 
 
+def _dump_case(d, head, k, digest, instances, copies, counts_or_calls, fixed, adv, rng_rows, tau):
+    with open(os.path.join(d, "meta.txt"), "w") as f:
+        f.write(head + "\nk %d\ndigest %x\ninstances %s\n" % (k, digest, " ".join("%x" % v for v in instances)))
+        for (c1, r1), (c2, r2) in copies:
+            f.write("copy %d %d %d %d\n" % (c1, r1, c2, r2))
+        f.write("rng " + " ".join(str(c) for c in counts_or_calls) + "\n")
+    np.concatenate(fixed).tofile(os.path.join(d, "fixed.bin")); np.concatenate(adv).tofile(os.path.join(d, "advice.bin"))
+    with open(os.path.join(d, "rng.bin"), "wb") as f:
+        for rows in rng_rows:
+            f.write(np.ascontiguousarray(rows, dtype=np.uint64).tobytes())
+    tau.tofile(os.path.join(d, "tau.bin"))
+
+
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("SPB_TEST_CPP_DRIVER", "0") == "0", reason="first GPU run of the compiled driver is opt-in until validated (DESIGN.md section 8)")
 def test_cpp_driver_on_the_gpu_reproduces_the_oracle_proof(orc, tmp_path):
+    """The compiled driver (include/spectre_b200_prover.hpp, CudaMemory on the context's stream) against libspectre_b200.so:
+    the same proof bytes as the Python driver on the CPU oracle, proved twice in the same process."""
     from spectre_b200 import circuits, plonk
     from tests.plonk_oracle_engine import OracleEngine, SeededRng
     exe = _build_main_against_the_real_library()
@@ -186,15 +200,40 @@ def test_cpp_driver_on_the_gpu_reproduces_the_oracle_proof(orc, tmp_path):
     rec = _RecordingRng(SeededRng(77))
     proof = plonk.create_proof(E, pk, [instances], adv, rec, EvmTranscriptWrite(pk.vk_digest))
     d = str(tmp_path)
-    with open(os.path.join(d, "meta.txt"), "w") as f:
-        f.write("shape halo2lib 3 2\nk %d\ndigest %x\ninstances %s\n" % (k, digest, " ".join("%x" % v for v in instances)))
-        for (c1, r1), (c2, r2) in copies:
-            f.write("copy %d %d %d %d\n" % (c1, r1, c2, r2))
-        f.write("rng " + " ".join(str(c.shape[0]) for c in rec.calls) + "\n")
-    np.concatenate(fixed).tofile(os.path.join(d, "fixed.bin")); np.concatenate(adv).tofile(os.path.join(d, "advice.bin"))
-    np.concatenate([c for c in rec.calls if c.shape[0]]).tofile(os.path.join(d, "rng.bin"))
-    orc.srs_tau().tofile(os.path.join(d, "tau.bin"))
-    out = subprocess.run([exe, d], capture_output=True, text=True)
+    _dump_case(d, "shape halo2lib 3 2", k, digest, instances, copies, [c.shape[0] for c in rec.calls], fixed, adv, [c for c in rec.calls if c.shape[0]], orc.srs_tau())
+    out = subprocess.run([exe, d], capture_output=True, text=True, env=dict(os.environ, SPB_MAIN_REPEAT="2"))
     assert out.returncode == 0, out.stdout + out.stderr
     with open(os.path.join(d, "proof.bin"), "rb") as f:
         assert f.read() == proof
+
+
+@pytest.mark.gpu
+def test_cpp_driver_on_the_gpu_reproduces_the_contract_accepted_k23_fixture(orc, tmp_path):
+    """K = 23: the compiled driver regenerates tests/golden/aggregation_k23_proof.json -- the bytes the reference's
+    sync_step verifier contract accepted -- through the real library, with window tables, and reports its wall time
+    (gpurun_out/cpp_k23_timings.json; bench.py times the same binary)."""
+    import json
+    from spectre_b200 import circuits
+    from tests.plonk_oracle_engine import SeededRng
+    exe = _build_main_against_the_real_library()
+    with open(os.path.join(ROOT, "tests", "golden", "aggregation_k23_proof.json")) as f:
+        fx = json.load(f)
+    k, n = fx["k"], 1 << fx["k"]
+    instances = [int(v, 16) for v in fx["instances"]]
+    cs = circuits.aggregation_shape()
+    fixed, adv, copies = circuits.aggregation_witness(cs, k, instances, fx["lookup_bits"], fx["groups"], seed=fx["seed"])
+    bf = cs.blinding_factors()
+    counts = [bf + 1, 1, bf + 1, bf + 1, 2, bf, 1, bf, 1, n, 1, cs.degree() - 1]     # create_proof's draw sizes for this shape, in order
+    rng = SeededRng(fx["seed"])
+    d = str(tmp_path)
+    _dump_case(d, "shape aggregation", k, int(fx["vk_digest"]), instances, copies, counts, fixed, [adv], [rng(c) for c in counts], orc.srs_tau())
+    del fixed, adv
+    out = subprocess.run([exe, d], capture_output=True, text=True, env=dict(os.environ, SPB_MAIN_REPEAT="2", SPB_MAIN_TABLES="1"))
+    assert out.returncode == 0, out.stdout + out.stderr
+    with open(os.path.join(d, "proof.bin"), "rb") as f:
+        assert f.read().hex() == fx["proof"]
+    ms = [float(l.split()[1]) for l in out.stdout.splitlines() if l.startswith("create_proof_ms")]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "cpp_k23_timings.json"), "w") as f:
+        json.dump({"k": k, "create_proof_ms": ms, "stdout": out.stdout}, f)
+    print("compiled driver K=23 create_proof ms:", ms)

@@ -47,6 +47,49 @@ def _edge_and_random(mod, n, rng):
 
 
 @pytest.mark.parametrize("field", ["fr", "fq"])
+def test_mul_and_sqr_carry_patterns(he, orc, field):
+    """The Karatsuba multiplier / squarer (field.cuh fp_mul_wide, fp_sqr_wide) on operands built to drive every carry:
+    half sums that overflow 2^128, all-ones limbs, equal halves, single-limb values, and 20000 random pairs."""
+    mod = pyref.R_MOD if field == "fr" else pyref.P_MOD
+    rng = random.Random(99)
+    F = (1 << 128) - 1
+    special = [0, 1, mod - 1, mod - 2, F, F << 96, (F << 126) % mod, ((1 << 126) - 1) << 128 | F, (mod >> 128) << 128, mod & F, 0xFFFFFFFF << 96,
+               (0xFFFFFFFF << 224) % mod, ((1 << 253) - 1) % mod, (1 << 253) % mod, F | (F >> 3) << 128, 0xFFFFFFFF00000000FFFFFFFF00000000FFFFFFFF00000000FFFFFFFF % mod]
+    special += [(((1 << 32) - 1) << (32 * i)) % mod for i in range(8)] + [(1 << (32 * i)) % mod for i in range(8)]
+    a = [x for x in special for _ in special] + [rng.randrange(mod) for _ in range(20000)]
+    b = [y for _ in special for y in special] + [rng.randrange(mod) for _ in range(20000)]
+    rinv = pow(1 << 256, -1, mod)
+    A = orc.to_mont(a, mod); B = orc.to_mont(b, mod)
+    out = np.empty_like(A)
+    n = ctypes.c_size_t(len(a))
+    getattr(he, f"he_{field}_mul")(_p(out), _p(A), _p(B), n)
+    assert orc.from_mont(out, mod) == [x * y % mod for x, y in zip(a, b)]
+    getattr(he, f"he_{field}_sqr")(_p(out), _p(A), n)
+    assert orc.from_mont(out, mod) == [x * x % mod for x in a]
+    # raw (non-Montgomery) operands exercise other limb patterns: result = a * b * 2^-256
+    raw_a = np.array([[(v >> (64 * j)) & (2**64 - 1) for j in range(4)] for v in a], dtype=np.uint64)
+    raw_b = np.array([[(v >> (64 * j)) & (2**64 - 1) for j in range(4)] for v in b], dtype=np.uint64)
+    getattr(he, f"he_{field}_mul")(_p(out), _p(raw_a), _p(raw_b), n)
+    got = [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in out]
+    assert got == [x * y * rinv % mod for x, y in zip(a, b)]
+    getattr(he, f"he_{field}_sqr")(_p(out), _p(raw_a), n)
+    got = [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in out]
+    assert got == [x * x * rinv % mod for x in a]
+
+
+def test_mul_sub_mul_single_reduction(he, orc):
+    """a*b - c*d through one Montgomery reduction (the y-coordinate of the XYZZ formulas), both signs of the difference."""
+    mod = pyref.P_MOD
+    rng = random.Random(5)
+    edge = [0, 1, mod - 1, mod - 2, (1 << 253) % mod, (1 << 128) - 1]
+    quads = [(a, b, c, d) for a in edge for b in edge for c in edge for d in edge] + [tuple(rng.randrange(mod) for _ in range(4)) for _ in range(5000)]
+    cols = [orc.to_mont([q[i] for q in quads], mod) for i in range(4)]
+    out = np.empty_like(cols[0])
+    he.he_fq_mul_sub_mul(_p(out), _p(cols[0]), _p(cols[1]), _p(cols[2]), _p(cols[3]), ctypes.c_size_t(len(quads)))
+    assert orc.from_mont(out, mod) == [(a * b - c * d) % mod for a, b, c, d in quads]
+
+
+@pytest.mark.parametrize("field", ["fr", "fq"])
 def test_field_ops_match_bigint(he, orc, field):
     mod = pyref.R_MOD if field == "fr" else pyref.P_MOD
     rng = random.Random(1234)

@@ -30,6 +30,14 @@ def main():
                     be.bench_modmul(field, 148 * tpsm, 200, ilp)
                     ms, rate = be.bench_modmul(field, 148 * tpsm, 2000, ilp)
                     print(json.dumps({"bench": "modmul", "field": field, "ilp": ilp, "threads_per_sm": tpsm, "ms": round(ms, 3), "gmul_per_s": round(rate / 1e9, 2)}), flush=True)
+    if "modmul_quick" in what:
+        for field in ("fq",):
+            for ilp, nm in ((2, "mul"), (0x102, "sqr")):
+                for tpsm in (384, 512, 1024):
+                    be.bench_modmul(field, 148 * tpsm, 200, ilp)
+                    ms, rate = be.bench_modmul(field, 148 * tpsm, 2000, ilp)
+                    print(json.dumps({"bench": "modmul", "op": nm, "field": field, "threads_per_sm": tpsm, "ms": round(ms, 3), "gop_per_s": round(rate / 1e9, 2),
+                                      "lib": os.path.basename(halo2.LIB_PATH)}), flush=True)
     if "pipe" in what:
         names = {0: "IMAD.WIDE.U32", 1: "IMAD", 2: "DFMA", 3: "IMAD.WIDE+DFMA (pairs)", 4: "IADD", 5: "IMAD.WIDE+IADD (pairs)"}
         for kind in range(6):
