@@ -121,7 +121,8 @@ int spb_srs_precompute(spb_ctx* ctx, spb_srs* srs);
 uint64_t spb_last_msm_adds(spb_ctx* ctx);
 /* device milliseconds of the last MSM's stages on the context's first device, from CUDA events on the stream the
  * kernels ran on: [0] digit histogram, [1] bucket-offset scan, [2] scatter, [3] bucket accumulation (the dominant
- * kernel), [4] chain stitch, [5] row/column tree sums of the buckets, [6] weighted partial sums. */
+ * kernel), [4] chain stitch, [5] bucket groups (running sums over 8 buckets per thread), [6] row/column tree sums of the
+ * group sums + weighted partial sums. */
 void spb_last_msm_stage_ms(spb_ctx* ctx, float out[7]);
 /* window width c and window count the library uses for an n-pair MSM (tables: with spb_srs_precompute) */
 void spb_msm_geometry(size_t n, int tables, uint32_t* c, uint32_t* windows);
@@ -129,6 +130,8 @@ void spb_msm_geometry(size_t n, int tables, uint32_t* c, uint32_t* windows);
 /* Sum of n Jacobian points on the host (folding the per-rank / per-device partial results of a sharded MSM after
  * the all-gather; EC addition is not an NCCL reduction). Result normalised to z = 1. No context needed. */
 int spb_g1_sum(const spb_g1* pts, size_t n, spb_g1* out);
+/* the same for a batch: pts is [groups][count] (one row per rank, as an all-gather delivers it), out[i] = sum over the groups */
+int spb_g1_sum_batch(const spb_g1* pts, size_t groups, size_t count, spb_g1* out);
 
 /* ---- NTT -------------------------------------------------------------------------------------------------- */
 /* best_fft(a, omega, log_n) ([UPSTREAM] halo2_proofs/src/arithmetic.rs): in place, natural order,
@@ -158,6 +161,11 @@ int spb_lagrange_to_coeff_dev(spb_ctx* ctx, const spb_domain* d, spb_fr* d_a);
 int spb_coeff_to_extended_dev(spb_ctx* ctx, const spb_domain* d, const spb_fr* d_in, spb_fr* d_out);
 int spb_extended_to_coeff_dev(spb_ctx* ctx, const spb_domain* d, const spb_fr* d_in, spb_fr* d_out);
 int spb_divide_by_vanishing_dev(spb_ctx* ctx, const spb_domain* d, spb_fr* d_a);
+/* `count` polynomials at once (create_proof converts its advice / permutation / lookup columns back to back): on a
+ * context with several devices polynomial i runs on device i mod n_dev, reading and writing the caller's buffers on the
+ * first device through NVLink peer access (NTTs sharded by polynomial). HOST arrays of device pointers. */
+int spb_lagrange_to_coeff_batch_dev(spb_ctx* ctx, const spb_domain* d, spb_fr* const* d_a, size_t count);
+int spb_coeff_to_extended_batch_dev(spb_ctx* ctx, const spb_domain* d, const spb_fr* const* d_in, spb_fr* const* d_out, size_t count);
 
 /* ---- batch polynomial arithmetic ([UPSTREAM] halo2_proofs/src/arithmetic.rs, ff::BatchInvert) ---------- */
 /* a[i] <- a[i]^-1, zeros stay zero (BatchInvert semantics) */

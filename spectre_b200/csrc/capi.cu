@@ -187,6 +187,18 @@ int spb_g1_sum(const spb_g1* pts, size_t n, spb_g1* out) {
   return 0;
 }
 
+// out[i] = sum_g pts[g * count + i]: the fold of a whole batch of sharded MSMs after ONE all-gather (groups = ranks)
+int spb_g1_sum_batch(const spb_g1* pts, size_t groups, size_t count, spb_g1* out) {
+  if (!out || (groups && count && !pts)) return SPB_ERR_ARG;
+  for (size_t i = 0; i < count; i++) {
+    G1Xyzz acc = xyzz_identity();
+    for (size_t g = 0; g < groups; g++) { G1Jac j; memcpy(&j, &pts[g * count + i], sizeof j); xyzz_add(acc, xyzz_from_jac(j)); }
+    G1Jac r = jac_from_affine(xyzz_to_affine(acc));
+    memcpy(&out[i], &r, sizeof r);
+  }
+  return 0;
+}
+
 // ---- NTT ---------------------------------------------------------------------------------------------------
 static int ntt_timed(spb_ctx* ctx, DeviceState& d, const Fr* src, Fr* dst, uint32_t k, const Fr& omega, const NttOpts& o) {
   SPB_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
@@ -371,6 +383,46 @@ int spb_extended_to_coeff_dev(spb_ctx* ctx, const spb_domain* dm, const spb_fr* 
   DeviceState& d = ctx->dev[0]; SPB_CUDA(ctx, cudaSetDevice(d.device));
   Fr post[3]; NttOpts o; e2c_opts(dm, post, o);
   return ntt_timed(ctx, d, (const Fr*)d_in, (Fr*)d_out, dm->extended_k, dm->extended_omega_inv, o);
+}
+// `count` transforms with the same options, polynomial i on device i mod D of the context ("shard by polynomial
+// for the NTTs"): the buffers stay on the first device; the other devices read the first pass's input and write the last
+// pass's output through NVLink peer access, intermediate passes run in their own HBM.
+static int ntt_batch_devices(spb_ctx* ctx, const spb_fr* const* d_in, spb_fr* const* d_out, size_t count, uint32_t k, const Fr& omega, const NttOpts& o) {
+  DeviceState& d0 = ctx->dev[0];
+  const size_t D = (ctx->peer_access && ctx->dev.size() > 1 && k >= 16) ? ctx->dev.size() : 1;
+  SPB_CUDA(ctx, cudaSetDevice(d0.device));
+  SPB_CUDA(ctx, cudaEventRecord(d0.ev0, d0.stream));
+  if (D > 1) SPB_CUDA(ctx, cudaEventRecord(d0.dep_ev, d0.stream));
+  for (size_t i = 0; i < count; i++) {
+    if (!d_in[i] || !d_out[i]) return SPB_ERR_ARG;
+    DeviceState& d = ctx->dev[i % D];
+    SPB_CUDA(ctx, cudaSetDevice(d.device));
+    if (i < D && i > 0) SPB_CUDA(ctx, cudaStreamWaitEvent(d.stream, d0.dep_ev, 0));
+    SPB_TRY(ntt_device(ctx, d, (const Fr*)d_in[i], (Fr*)d_out[i], k, omega, o));
+  }
+  for (size_t i = 1; i < D && i < count; i++) {
+    DeviceState& d = ctx->dev[i];
+    SPB_CUDA(ctx, cudaSetDevice(d.device));
+    SPB_CUDA(ctx, cudaEventRecord(d.dep_ev, d.stream));
+    SPB_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d.dep_ev, 0));
+  }
+  SPB_CUDA(ctx, cudaSetDevice(d0.device));
+  SPB_CUDA(ctx, cudaEventRecord(d0.ev1, d0.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+  SPB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, d0.ev0, d0.ev1));
+  return 0;
+}
+int spb_lagrange_to_coeff_batch_dev(spb_ctx* ctx, const spb_domain* dm, spb_fr* const* d_a, size_t count) {
+  if (!ctx || !dm || (count && !d_a)) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Fr post[3]; NttOpts o; l2c_opts(dm, post, o);
+  return ntt_batch_devices(ctx, (const spb_fr* const*)d_a, d_a, count, dm->k, dm->omega_inv, o);
+}
+int spb_coeff_to_extended_batch_dev(spb_ctx* ctx, const spb_domain* dm, const spb_fr* const* d_in, spb_fr* const* d_out, size_t count) {
+  if (!ctx || !dm || (count && (!d_in || !d_out))) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Fr pre[3]; NttOpts o; c2e_opts(dm, pre, o);
+  return ntt_batch_devices(ctx, d_in, d_out, count, dm->extended_k, dm->extended_omega, o);
 }
 int spb_divide_by_vanishing_dev(spb_ctx* ctx, const spb_domain* dm, spb_fr* d_a) {
   if (!ctx || !dm || !d_a) return SPB_ERR_ARG;

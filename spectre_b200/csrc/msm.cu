@@ -108,18 +108,22 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   G1Xyzz* huge_part = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_huge_part", max_huge * kHugeBlocks * sizeof(G1Xyzz));
   const MsmTail tl = msm_tail_shape(g.c);
   const uint32_t R = 1u << tl.r_log, C = 1u << tl.c_log, per = msm_tail_partials(tl);
-  G1Xyzz* seg_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_rowcol", (uint64_t)g.BW * (R + C) * sizeof(G1Xyzz));
+  const uint32_t T1 = g.B >> tl.m_log;                       // group sums per bucket set
+  const uint64_t ngroups = (uint64_t)g.BW * T1;
+  G1Xyzz* grp = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_groups", 2 * ngroups * sizeof(G1Xyzz));   // S1 | W1
+  G1Xyzz* seg_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_rowcol", (uint64_t)g.BW * (2 * R + C) * sizeof(G1Xyzz));   // rows | columns | W rows
   G1Xyzz* win_out = (G1Xyzz*)lane_slot(ctx, d, lane, "msm_partials", (uint64_t)g.BW * per * sizeof(G1Xyzz));
   size_t scan_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, offsets, (int)(nb + 1), ln.stream);
   void* scan_tmp = lane_slot(ctx, d, lane, "msm_scan_tmp", scan_bytes ? scan_bytes : 16);
-  if (!counts || !offsets || !ent || !buckets || !head_key || !tail_key || !head || !tail || !giant || !huge || !huge_part || !seg_out || !win_out || !scan_tmp)
+  if (!counts || !offsets || !ent || !buckets || !head_key || !tail_key || !head || !tail || !giant || !huge || !huge_part || !grp || !seg_out || !win_out || !scan_tmp)
     return SPB_ERR_OOM;
   if ((size_t)g.BW * per * sizeof(G1Xyzz) + 16 > kLanePinnedBytes) return set_error(ctx, SPB_ERR_STATE, "msm: %u window partials exceed the pinned staging area", g.BW * per);
 
   cudaStream_t st = ln.stream;
   SPB_CUDA(ctx, cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
-  SPB_CUDA(ctx, cudaMemsetAsync(buckets, 0, nb * sizeof(G1Xyzz), st));
+  // the bucket array is NOT cleared: every non-empty bucket is written exactly once (accumulate / stitch / giant paths) and
+  // the reduction reads a bucket only where the sort's offsets say it has entries
   SPB_CUDA(ctx, cudaMemsetAsync(giant, 0, 4, st));
   SPB_CUDA(ctx, cudaMemsetAsync(huge, 0, 4, st));
   const unsigned tb = 256;
@@ -140,12 +144,14 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   msm_huge_kernel<<<kHugeBlocks, 128, 0, st>>>(huge, huge + 2, head, huge_part);
   msm_huge_finish_kernel<<<8, 128, 0, st>>>(huge, huge + 2, kHugeBlocks, huge_part, tail_key, tail, buckets);
   cudaEventRecord(ln.ev[5], st);
-  msm_rowcol_kernel<<<g.BW * (R + C), 64, 0, st>>>(g, tl, buckets, seg_out, seg_out + (uint64_t)g.BW * R);
+  G1Xyzz *rows = seg_out, *cols = seg_out + (uint64_t)g.BW * R, *wrows = seg_out + (uint64_t)g.BW * (R + C);
+  msm_group_kernel<<<(unsigned)((ngroups + 127) / 128), 128, 0, st>>>(ngroups, tl.m_log, offsets, buckets, grp, grp + ngroups);
   cudaEventRecord(ln.ev[6], st);
-  msm_weighted_kernel<<<g.BW * (tl.nbr + tl.nbc), 128, 0, st>>>(g, tl, seg_out, seg_out + (uint64_t)g.BW * R, win_out);
+  msm_rowcol_kernel<<<g.BW * (2 * R + C), 64, 0, st>>>(T1, tl, grp, grp + ngroups, rows, cols, wrows);
+  msm_weighted_kernel<<<g.BW * (2 * tl.nbr + tl.nbc), 128, 0, st>>>(tl, rows, cols, wrows, win_out);
   cudaEventRecord(ln.ev[7], st);
   SPB_CUDA(ctx, cudaGetLastError());
-  ctx->n_kernel_launches += 9;
+  ctx->n_kernel_launches += 10;
   SPB_CUDA(ctx, cudaMemcpyAsync(ln.pinned, win_out, (size_t)g.BW * per * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
   SPB_CUDA(ctx, cudaMemcpyAsync((char*)ln.pinned + (size_t)g.BW * per * sizeof(G1Xyzz), total, 4, cudaMemcpyDeviceToHost, st));
   return 0;

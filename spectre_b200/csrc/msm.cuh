@@ -21,8 +21,9 @@
 //                 a chunk ("tail") and the run that enters one ("head") are stored as chunk pieces.
 //   5. stitch   : one thread per tail piece walks the following head pieces of the same key and stores the
 //                 bucket; chains longer than a cap (giant buckets) go to a block-wide tree reduction.
-//   6. reduce   : per bucket set S = sum_b (b+1) * bucket[b] with the buckets viewed as an R x C matrix:
-//                 S = C * sum_r r*Row_r + sum_r Row_r + sum_c c*Col_c -- tree sums and scalar multiples < 2^10 only.
+//   6. reduce   : per bucket set S = sum_b (b+1) * bucket[b]: groups of 8 buckets by a running sum per thread, then the group
+//                 sums viewed as an R x C matrix: sum_t t*S1_t = C * sum_r r*Row_r + sum_c c*Col_c -- tree sums and local
+//                 weights < 2^7 only.
 //   7. host     : fold the few partial sums per bucket set, Horner over the sets (none with tables), one inversion.
 //
 // Roofline: algorithmic bytes = 96 B per pair. The kernel that dominates (step 4) executes
@@ -199,38 +200,68 @@ SPB_HD void msm_stitch_thread(uint64_t tid, uint64_t T, uint32_t cap, const uint
 }
 
 // ---- step 6: weighted bucket sum  S_w = sum_b (b+1) * bucket[w][b] ---------------------------------------------
-// The B buckets of a window are viewed as an R x C matrix (b = r*C + c). Then
-//   S_w = C * sum_r r*Row_r + sum_r Row_r + sum_c c*Col_c,   Row_r = sum_c X[r][c],  Col_c = sum_r X[r][c]
-// so the whole reduction is tree sums (log depth, fully parallel) plus scalar multiples by weights < 2^10 --
-// no running sum over tens of buckets and no 19-bit scalar multiple on the critical path.
+// Two levels, both free of scalar multiples and of long running sums:
+//  (a) groups: thread t takes the m = 2^m_log consecutive buckets b = t*m + j and forms, with one running sum from the top,
+//      S1_t = sum_j B_{t*m+j} and W1_t = sum_j j * B_{t*m+j} (2m - 1 additions, no synchronisation, every thread busy).
+//      Empty buckets are recognised from the bucket offsets of the counting sort, so the bucket array is never cleared
+//      and never read where nothing was written. Then S_w = sum_t W1_t + sum_t S1_t + m * sum_t t * S1_t.
+//  (b) the T = B / m group sums S1 are viewed as an R x C matrix (t = r*C + c):
+//      sum_t t*S1_t = C * sum_r r*Row_r + sum_c c*Col_c,   Row_r = sum_c S1[r][c],  Col_c = sum_r S1[r][c]
+//      -- tree sums (log depth) and, per block of 128 rows / columns, one suffix scan: weights < 2^7 only. The W1 are
+//      summed by rows next to it.
 struct MsmTail {
-  uint32_t r_log, c_log;  // R = 2^r_log rows, C = 2^c_log columns, R*C = B
+  uint32_t m_log;         // buckets per group = 2^m_log
+  uint32_t r_log, c_log;  // R = 2^r_log rows, C = 2^c_log columns, R*C = T = B >> m_log group sums
   uint32_t nbr, nbc;      // blocks (of 128 items) covering the rows / the columns in the weighted pass
 };
 inline MsmTail msm_tail_shape(uint32_t c) {
   MsmTail t; uint32_t bits = c - 1;
+  t.m_log = bits < 3 ? bits : 3;
+  bits -= t.m_log;
   t.c_log = bits / 2; t.r_log = bits - t.c_log;
   t.nbr = ((1u << t.r_log) + 127) / 128; t.nbc = ((1u << t.c_log) + 127) / 128;
   return t;
 }
-// Partial layout per bucket set: [A(nbr) | S(nbr) | D(nbc) | T(nbc)], each over a block of 128 rows / columns with
+// Partial layout per bucket set: [A(nbr) | S(nbr) | D(nbc) | T(nbc) | V(nbr)], each over a block of 128 rows / columns with
 // LOCAL weights: A[j] = sum_i i * Row_{128j+i}, S[j] = sum_i Row_{128j+i}, D[j] = sum_i i * Col_{128j+i}, T[j] = sum_i
-// Col_{128j+i}. The host adds the 128*j offsets (msm_tail_finish).
-SPB_HD uint32_t msm_tail_partials(const MsmTail& t) { return 2 * t.nbr + 2 * t.nbc; }
-// host-side reference of the two kernels below (tests/hostemu)
-inline void msm_tail_host(const MsmGeom& g, const G1Xyzz* buckets, G1Xyzz* partials) {
+// Col_{128j+i}, V[j] = sum_i WRow_{128j+i} (WRow_r = sum_c W1[r][c]). The host adds the 128*j offsets (msm_tail_finish).
+SPB_HD uint32_t msm_tail_partials(const MsmTail& t) { return 3 * t.nbr + 2 * t.nbc; }
+
+// (a): one group of buckets. `offsets` is the exclusive scan of the bucket counters (offsets[b+1] - offsets[b] entries in b).
+SPB_HD void msm_group_thread(uint64_t tid, uint64_t ngroups, uint32_t m_log, const uint32_t* offsets, const G1Xyzz* buckets, G1Xyzz* s1, G1Xyzz* w1) {
+  if (tid >= ngroups) return;
+  const uint64_t b0 = tid << m_log;
+  G1Xyzz run = xyzz_identity(), acc = xyzz_identity();
+  uint32_t hi = offsets[b0 + (1u << m_log)];
+  for (int j = (int)(1u << m_log) - 1; j >= 0; j--) {
+    const uint32_t lo = offsets[b0 + (uint64_t)j];
+    if (hi != lo) xyzz_add(run, buckets[b0 + (uint64_t)j]);
+    hi = lo;
+    if (j >= 1) xyzz_add(acc, run);   // after the loop: acc = sum_{j>=1} (sum_{i>=j} B_i) = sum_i i * B_i
+  }
+  s1[tid] = run;
+  w1[tid] = acc;
+}
+// host-side reference of the kernels below (tests/hostemu): buckets -> partials
+inline void msm_tail_host(const MsmGeom& g, const uint32_t* offsets, const G1Xyzz* buckets, G1Xyzz* partials) {
   MsmTail t = msm_tail_shape(g.c);
   uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = msm_tail_partials(t);
+  const uint64_t T = (uint64_t)g.B >> t.m_log;
+  G1Xyzz* s1 = (G1Xyzz*)malloc(sizeof(G1Xyzz) * T * g.BW);
+  G1Xyzz* w1 = (G1Xyzz*)malloc(sizeof(G1Xyzz) * T * g.BW);
+  for (uint64_t tid = 0; tid < T * g.BW; tid++) msm_group_thread(tid, T * g.BW, t.m_log, offsets, buckets, s1, w1);
   for (uint32_t w = 0; w < g.BW; w++) {
-    const G1Xyzz* X = buckets + (uint64_t)w * g.B;
+    const G1Xyzz* X = s1 + (uint64_t)w * T;
+    const G1Xyzz* V = w1 + (uint64_t)w * T;
     G1Xyzz* out = partials + (uint64_t)w * per;
     for (uint32_t i = 0; i < per; i++) out[i] = xyzz_identity();
     for (uint32_t r = 0; r < R; r++) {
-      G1Xyzz row = xyzz_identity();
-      for (uint32_t c = 0; c < C; c++) xyzz_add(row, X[(uint64_t)r * C + c]);
+      G1Xyzz row = xyzz_identity(), wrow = xyzz_identity();
+      for (uint32_t c = 0; c < C; c++) { xyzz_add(row, X[(uint64_t)r * C + c]); xyzz_add(wrow, V[(uint64_t)r * C + c]); }
       G1Xyzz wr = xyzz_mul_u32(row, r % 128);
       xyzz_add(out[r / 128], wr);
       xyzz_add(out[t.nbr + r / 128], row);
+      xyzz_add(out[2 * t.nbr + 2 * t.nbc + r / 128], wrow);
     }
     for (uint32_t c = 0; c < C; c++) {
       G1Xyzz col = xyzz_identity();
@@ -240,6 +271,7 @@ inline void msm_tail_host(const MsmGeom& g, const G1Xyzz* buckets, G1Xyzz* parti
       xyzz_add(out[2 * t.nbr + t.nbc + c / 128], col);
     }
   }
+  free(s1); free(w1);
 }
 // host: window sum from its partials
 inline G1Xyzz msm_tail_finish(const MsmGeom& g, const G1Xyzz* part) {
@@ -257,10 +289,13 @@ inline G1Xyzz msm_tail_finish(const MsmGeom& g, const G1Xyzz* part) {
     return sx;
   };
   G1Xyzz S;
-  G1Xyzz A = fold(part, part + t.nbr, t.nbr, &S);
-  G1Xyzz D = fold(part + 2 * t.nbr, part + 2 * t.nbr + t.nbc, t.nbc, nullptr);
+  G1Xyzz A = fold(part, part + t.nbr, t.nbr, &S);                                   // sum_r r * Row_r ; S = sum_t S1_t
+  G1Xyzz D = fold(part + 2 * t.nbr, part + 2 * t.nbr + t.nbc, t.nbc, nullptr);      // sum_c c * Col_c
   for (uint32_t i = 0; i < t.c_log; i++) A = xyzz_dbl(A);
-  xyzz_add(A, S); xyzz_add(A, D);
+  xyzz_add(A, D);                                                                   // sum_t t * S1_t
+  for (uint32_t i = 0; i < t.m_log; i++) A = xyzz_dbl(A);
+  xyzz_add(A, S);
+  for (uint32_t j = 0; j < t.nbr; j++) xyzz_add(A, part[2 * t.nbr + 2 * t.nbc + j]);  // sum_t W1_t
   return A;
 }
 
@@ -417,29 +452,49 @@ __global__ void __launch_bounds__(128) msm_huge_finish_kernel(const uint32_t* hu
   }
 }
 
-// block (w, idx): idx < R -> row sum, else column sum
+// (a) one thread per group of 2^m_log buckets
+__global__ void __launch_bounds__(128) msm_group_kernel(uint64_t ngroups, uint32_t m_log, const uint32_t* offsets, const G1Xyzz* buckets, G1Xyzz* s1, G1Xyzz* w1) {
+  msm_group_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, ngroups, m_log, offsets, buckets, s1, w1);
+}
+// (b) block (w, idx): idx < R -> row sum of S1, idx < R + C -> column sum of S1, else row sum of W1
 // 64 threads per vector: more serial additions per thread and a shorter tree keep more lanes busy than 128 would
-__global__ void __launch_bounds__(64) msm_rowcol_kernel(MsmGeom g, MsmTail t, const G1Xyzz* buckets, G1Xyzz* row_out, G1Xyzz* col_out) {
+__global__ void __launch_bounds__(64) msm_rowcol_kernel(uint32_t T, MsmTail t, const G1Xyzz* s1, const G1Xyzz* w1, G1Xyzz* row_out, G1Xyzz* col_out, G1Xyzz* wrow_out) {
   __shared__ G1Xyzz sh[32];
   const uint32_t R = 1u << t.r_log, C = 1u << t.c_log;
-  const uint32_t w = blockIdx.x / (R + C), idx = blockIdx.x % (R + C);
-  const G1Xyzz* X = buckets + (uint64_t)w * g.B;
+  const uint32_t w = blockIdx.x / (2 * R + C), idx = blockIdx.x % (2 * R + C);
+  const G1Xyzz* X = (idx < R + C ? s1 : w1) + (uint64_t)w * T;
   G1Xyzz acc = xyzz_identity();
   if (idx < R) { for (uint32_t c = threadIdx.x; c < C; c += 64) xyzz_add(acc, X[(uint64_t)idx * C + c]); }
-  else { const uint32_t col = idx - R; for (uint32_t r = threadIdx.x; r < R; r += 64) xyzz_add(acc, X[(uint64_t)r * C + col]); }
+  else if (idx < R + C) { const uint32_t col = idx - R; for (uint32_t r = threadIdx.x; r < R; r += 64) xyzz_add(acc, X[(uint64_t)r * C + col]); }
+  else { const uint32_t row = idx - R - C; for (uint32_t c = threadIdx.x; c < C; c += 64) xyzz_add(acc, X[(uint64_t)row * C + c]); }
   block_sum_xyzz<64>(acc, sh);
-  if (threadIdx.x == 0) { if (idx < R) row_out[(uint64_t)w * R + idx] = acc; else col_out[(uint64_t)w * C + (idx - R)] = acc; }
+  if (threadIdx.x == 0) {
+    if (idx < R) row_out[(uint64_t)w * R + idx] = acc;
+    else if (idx < R + C) col_out[(uint64_t)w * C + (idx - R)] = acc;
+    else wrow_out[(uint64_t)w * R + (idx - R - C)] = acc;
+  }
 }
-// block (w, j): j < nbr -> rows [128 j, 128 j + 128), else columns. Local weighted sum without any scalar multiple:
-// sum_i i * X_i = sum_{i >= 1} (suffix sum S_i), so one suffix scan (7 steps) and one tree sum (7 steps).
-__global__ void __launch_bounds__(128) msm_weighted_kernel(MsmGeom g, MsmTail t, const G1Xyzz* row_out, const G1Xyzz* col_out, G1Xyzz* partials) {
+// block (w, j): j < nbr -> rows [128 j, 128 j + 128), j < nbr + nbc -> columns, else the W1 row sums (plain sum only).
+// Local weighted sum without any scalar multiple: sum_i i * X_i = sum_{i >= 1} (suffix sum S_i), so one suffix scan
+// (7 steps) and one tree sum (7 steps).
+__global__ void __launch_bounds__(128) msm_weighted_kernel(MsmTail t, const G1Xyzz* row_out, const G1Xyzz* col_out, const G1Xyzz* wrow_out, G1Xyzz* partials) {
   __shared__ G1Xyzz sh[128];
+  __shared__ G1Xyzz sh2[64];
   const uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = msm_tail_partials(t);
-  const uint32_t w = blockIdx.x / (t.nbr + t.nbc), j = blockIdx.x % (t.nbr + t.nbc);
-  const bool rows = j < t.nbr;
-  const uint32_t jb = rows ? j : j - t.nbr, idx = jb * 128 + threadIdx.x, tid = threadIdx.x;
+  const uint32_t nblk = 2 * t.nbr + t.nbc;
+  const uint32_t w = blockIdx.x / nblk, j = blockIdx.x % nblk;
+  const int kind = j < t.nbr ? 0 : (j < t.nbr + t.nbc ? 1 : 2);
+  const uint32_t jb = kind == 0 ? j : (kind == 1 ? j - t.nbr : j - t.nbr - t.nbc), idx = jb * 128 + threadIdx.x, tid = threadIdx.x;
   G1Xyzz* out = partials + (uint64_t)w * per;
-  G1Xyzz x = rows ? (idx < R ? row_out[(uint64_t)w * R + idx] : xyzz_identity()) : (idx < C ? col_out[(uint64_t)w * C + idx] : xyzz_identity());
+  G1Xyzz x = xyzz_identity();
+  if (kind == 0) { if (idx < R) x = row_out[(uint64_t)w * R + idx]; }
+  else if (kind == 1) { if (idx < C) x = col_out[(uint64_t)w * C + idx]; }
+  else { if (idx < R) x = wrow_out[(uint64_t)w * R + idx]; }
+  if (kind == 2) {   // plain sum
+    block_sum_xyzz<128>(x, sh2);
+    if (tid == 0) out[2 * t.nbr + 2 * t.nbc + jb] = x;
+    return;
+  }
   // inclusive suffix scan: x <- sum_{t >= tid} X_t
   for (uint32_t off = 1; off < 128; off <<= 1) {
     sh[tid] = x;
@@ -449,10 +504,9 @@ __global__ void __launch_bounds__(128) msm_weighted_kernel(MsmGeom g, MsmTail t,
   }
   G1Xyzz total = x;                       // thread 0 holds the plain block sum
   if (tid == 0) x = xyzz_identity();      // weights start at 0: drop S_0 from the weighted sum
-  __shared__ G1Xyzz sh2[64];
   block_sum_xyzz<128>(x, sh2);
   if (tid == 0) {
-    if (rows) { out[jb] = x; out[t.nbr + jb] = total; }
+    if (kind == 0) { out[jb] = x; out[t.nbr + jb] = total; }
     else { out[2 * t.nbr + jb] = x; out[2 * t.nbr + t.nbc + jb] = total; }
   }
 }

@@ -12,6 +12,7 @@ struct GraphArgs {
   const Fr* const* fixed; const Fr* const* advice; const Fr* const* instance;
   const Fr* scalars;   // [beta, gamma, theta, y, challenges...]
   Fr* values; Fr* scratch; uint64_t size; int32_t rot_scale;
+  uint64_t row_lo, row_hi;   // this launch's extended rows [row_lo, row_hi): a row-range shard of a multi-device context
 };
 
 SPB_HD uint64_t rotation_idx(uint64_t idx, int32_t rot, int32_t rot_scale, uint64_t size) {
@@ -66,12 +67,15 @@ SPB_HD void graph_evaluate_row(const GraphArgs& a, uint64_t row, uint32_t slot, 
 
 struct PermArgs {
   Fr* values; uint64_t size; int32_t rot_scale, last_rotation; uint32_t n_sets, chunk_len, n_cols;
+  uint64_t row_lo, row_hi;   // row-range shard
+  const Fr* omega_pow;       // extended_omega^j, j < 256 (device table): omega^idx = omega^(idx & ~255) * omega_pow[idx & 255]
   const Fr* const* z; const Fr* const* col_values; const Fr* const* sigma;
   const Fr* l0; const Fr* l_last; const Fr* l_active;
   Fr beta, gamma, y, delta_start, delta, extended_omega;
 };
 
-SPB_HD void permutation_constraints_row(const PermArgs& a, uint64_t idx) {
+// omega_idx = extended_omega^idx (the kernel derives it from one power per block and the 256-entry table)
+SPB_HD void permutation_constraints_row(const PermArgs& a, uint64_t idx, const Fr& omega_idx) {
   const uint64_t r_next = rotation_idx(idx, 1, a.rot_scale, a.size), r_last = rotation_idx(idx, a.last_rotation, a.rot_scale, a.size);
   const Fr one = fp_one<FrParams>();
   Fr v = ntt_ld_stream(a.values + idx);
@@ -80,7 +84,7 @@ SPB_HD void permutation_constraints_row(const PermArgs& a, uint64_t idx) {
   { Fr zl = ntt_ldg(a.z[a.n_sets - 1] + idx); v = fp_add(fp_mul(v, a.y), fp_mul(fp_sub(fp_sqr(zl), zl), l_last)); }
   for (uint32_t s = 1; s < a.n_sets; s++)
     v = fp_add(fp_mul(v, a.y), fp_mul(fp_sub(ntt_ldg(a.z[s] + idx), ntt_ldg(a.z[s - 1] + r_last)), l0));
-  Fr current_delta = fp_mul(a.delta_start, fp_pow_u64(a.extended_omega, idx));
+  Fr current_delta = fp_mul(a.delta_start, omega_idx);
   for (uint32_t s = 0; s < a.n_sets; s++) {
     const uint32_t lo = s * a.chunk_len, hi = lo + a.chunk_len < a.n_cols ? lo + a.chunk_len : a.n_cols;
     Fr left = ntt_ldg(a.z[s] + r_next), right = ntt_ldg(a.z[s] + idx);
@@ -97,6 +101,7 @@ SPB_HD void permutation_constraints_row(const PermArgs& a, uint64_t idx) {
 
 struct LookupArgs {
   Fr* values; uint64_t size; int32_t rot_scale;
+  uint64_t row_lo, row_hi;   // row-range shard
   const Fr* product; const Fr* permuted_input; const Fr* permuted_table; const Fr* table_value;
   const Fr* l0; const Fr* l_last; const Fr* l_active;
   Fr beta, gamma, y;

@@ -132,7 +132,7 @@ class Backend:
     def last_msm_stage_ms(self):
         out = (ctypes.c_float * 7)()
         self.lib.spb_last_msm_stage_ms(self.ctx, out)
-        return dict(zip(("count", "scan", "scatter", "accumulate", "stitch", "rowcol", "weighted"), [float(v) for v in out]))
+        return dict(zip(("count", "scan", "scatter", "accumulate", "stitch", "groups", "rowcol_weighted"), [float(v) for v in out]))
 
     def msm_geometry(self, n, tables=False):
         c = ctypes.c_uint32(); w = ctypes.c_uint32()
@@ -401,6 +401,14 @@ class EvaluationDomain:
     def lagrange_to_coeff_dev(self, d_a):
         self.be.check(self.be.lib.spb_lagrange_to_coeff_dev(self.be.ctx, self.h, _p(d_a)), "spb_lagrange_to_coeff_dev")
 
+    def lagrange_to_coeff_batch_dev(self, d_ptrs):
+        ptrs = (ctypes.c_void_p * max(1, len(d_ptrs)))(*d_ptrs)
+        self.be.check(self.be.lib.spb_lagrange_to_coeff_batch_dev(self.be.ctx, self.h, ptrs, ctypes.c_size_t(len(d_ptrs))), "spb_lagrange_to_coeff_batch_dev")
+
+    def coeff_to_extended_batch_dev(self, d_in, d_out):
+        pi = (ctypes.c_void_p * max(1, len(d_in)))(*d_in); po = (ctypes.c_void_p * max(1, len(d_out)))(*d_out)
+        self.be.check(self.be.lib.spb_coeff_to_extended_batch_dev(self.be.ctx, self.h, pi, po, ctypes.c_size_t(len(d_in))), "spb_coeff_to_extended_batch_dev")
+
     def coeff_to_extended_dev(self, d_in, d_out):
         self.be.check(self.be.lib.spb_coeff_to_extended_dev(self.be.ctx, self.h, _p(d_in), _p(d_out)), "spb_coeff_to_extended_dev")
 
@@ -525,6 +533,17 @@ def g1_sum(points):
     rc = load_library().spb_g1_sum(_p(pts), ctypes.c_size_t(pts.shape[0]), _p(out))
     if rc != 0:
         raise BackendError("spb_g1_sum failed (%d)" % rc)
+    return out
+
+
+def g1_sum_batch(points):
+    """points: (groups, count, 12) Jacobian partial sums (row g = rank g's batch) -> (count, 12): one C call per batch."""
+    pts = np.ascontiguousarray(points, dtype=np.uint64)
+    groups, count = pts.shape[0], pts.shape[1]
+    out = np.empty((count, 12), dtype=np.uint64)
+    rc = load_library().spb_g1_sum_batch(_p(pts), ctypes.c_size_t(groups), ctypes.c_size_t(count), _p(out))
+    if rc != 0:
+        raise BackendError("spb_g1_sum_batch failed (%d)" % rc)
     return out
 
 

@@ -223,6 +223,10 @@ class DeviceEngine:
     def alloc(self, rows):
         with self.torch.cuda.stream(self.stream):
             return self.torch.zeros((rows, 4), dtype=self.torch.int64, device=self.dev)
+    def alloc_uninit(self, rows):
+        """a buffer every element of which the next library call overwrites (extended cosets): no memset pass"""
+        with self.torch.cuda.stream(self.stream):
+            return self.torch.empty((rows, 4), dtype=self.torch.int64, device=self.dev)
     def upload(self, a):
         """host column -> device. A pinned torch tensor (witness buffers registered once by the caller) goes up as one
         asynchronous DMA; numpy arrays take the pageable path."""
@@ -255,14 +259,23 @@ class DeviceEngine:
 
     # domain
     def lagrange_to_coeff(self, b): self.dom.lagrange_to_coeff_dev(b.data_ptr())
+    def lagrange_to_coeff_many(self, bufs):
+        """in place; on a context with several devices the polynomials are spread over them (NTTs sharded by polynomial)"""
+        if bufs:
+            self.dom.lagrange_to_coeff_batch_dev([b.data_ptr() for b in bufs])
+    def coeff_to_extended_many(self, bufs):
+        outs = [self.alloc_uninit(1 << self.extended_k) for _ in bufs]
+        if bufs:
+            self.dom.coeff_to_extended_batch_dev([b.data_ptr() for b in bufs], [o.data_ptr() for o in outs])
+        return outs
     def coeff_to_lagrange(self, b):
         self.be.best_fft_dev(b.data_ptr(), fr_mont(omega_of(self.k)).reshape(1, 4), self.k)
     def coeff_to_extended(self, b):
-        out = self.alloc(1 << self.extended_k)
+        out = self.alloc_uninit(1 << self.extended_k)
         self.dom.coeff_to_extended_dev(b.data_ptr(), out.data_ptr())
         return out
     def extended_to_coeff(self, e, rows):
-        out = self.alloc(rows)
+        out = self.alloc_uninit(rows)
         self.dom.extended_to_coeff_dev(e.data_ptr(), out.data_ptr())
         return out
     def divide_by_vanishing(self, e): self.dom.divide_by_vanishing_poly_dev(e.data_ptr())
@@ -299,6 +312,21 @@ class DeviceEngine:
         return halo2.jacobian_to_affine_ints(c), h
     def shplonk_finish(self, state, u):
         return halo2.jacobian_to_affine_ints(self.be.shplonk_finish_dev(state, u))
+
+
+def lagrange_to_coeff_many(E, bufs):
+    """in place for every buffer; engines that can spread the transforms over several devices take the whole list"""
+    if hasattr(E, "lagrange_to_coeff_many"):
+        E.lagrange_to_coeff_many(list(bufs))
+    else:
+        for b in bufs:
+            E.lagrange_to_coeff(b)
+
+
+def coeff_to_extended_many(E, bufs):
+    if hasattr(E, "coeff_to_extended_many"):
+        return E.coeff_to_extended_many(list(bufs))
+    return [E.coeff_to_extended(b) for b in bufs]
 
 
 # ---- keygen -------------------------------------------------------------------------------------------------------
@@ -356,18 +384,19 @@ def keygen(E, cs, k, fixed_columns, copies, vk_digest=None):
     pk.fixed_commitments = E.commit(G_LAG, pk.fixed_values, n) if pk.fixed_values else []
     pk.sigma_commitments = E.commit(G_LAG, pk.sigma_values, n) if pk.sigma_values else []
 
-    def poly_and_coset(values):
-        p = E.clone(values); E.lagrange_to_coeff(p)
-        return p, E.coeff_to_extended(p)
-    pk.fixed_polys, pk.fixed_cosets = map(list, zip(*[poly_and_coset(v) for v in pk.fixed_values])) if pk.fixed_values else ([], [])
-    pk.sigma_polys, pk.sigma_cosets = map(list, zip(*[poly_and_coset(v) for v in pk.sigma_values])) if pk.sigma_values else ([], [])
+    def polys_and_cosets(values):
+        ps = [E.clone(v) for v in values]
+        lagrange_to_coeff_many(E, ps)
+        return ps, coeff_to_extended_many(E, ps)
+    pk.fixed_polys, pk.fixed_cosets = polys_and_cosets(pk.fixed_values)
+    pk.sigma_polys, pk.sigma_cosets = polys_and_cosets(pk.sigma_values)
     one = fr_mont(1).reshape(1, 4)
     l0 = E.alloc(n); E.write_rows(l0, 0, one)
     l_last = E.alloc(n); E.write_rows(l_last, pk.usable_rows, one)
     # l_active = 1 - l_last - l_blind on the evaluation rows: ones on rows [0, usable_rows)
     l_active = E.alloc(n)
     E.write_rows(l_active, 0, np.broadcast_to(one, (pk.usable_rows, 4)))
-    pk.l0, pk.l_last, pk.l_active = (poly_and_coset(b)[1] for b in (l0, l_last, l_active))
+    pk.l0, pk.l_last, pk.l_active = polys_and_cosets([l0, l_last, l_active])[1]
     pk.vk_digest = vk_digest if vk_digest is not None else default_vk_digest(pk)
     return pk
 
@@ -439,8 +468,7 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
             raise ValueError("create_proof: an instance column has more than %d values (upstream: Error::InstanceTooLarge)" % usable)
         b = E.alloc(n); E.write_rows(b, 0, fr_mont_rows(col)); inst_values.append(b)
     inst_polys = [E.clone(b) for b in inst_values]
-    for p in inst_polys:
-        E.lagrange_to_coeff(p)
+    lagrange_to_coeff_many(E, inst_polys)
     lap("instances")
 
     # 2. advice: blind the unusable rows, commit, to coefficient form
@@ -453,8 +481,7 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
     for pt in E.commit(GL, advice_values, n):
         transcript.write_ec_point(pt)
     advice_polys = [E.clone(b) for b in advice_values]
-    for p in advice_polys:
-        E.lagrange_to_coeff(p)
+    lagrange_to_coeff_many(E, advice_polys)
     lap("advice")
 
     theta = fr_mont(transcript.squeeze_challenge())
@@ -476,7 +503,7 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
         for pt in E.commit(GL, [L.permuted_input, L.permuted_table], n):
             transcript.write_ec_point(pt)
         L.permuted_input_poly, L.permuted_table_poly = E.clone(L.permuted_input), E.clone(L.permuted_table)
-        E.lagrange_to_coeff(L.permuted_input_poly); E.lagrange_to_coeff(L.permuted_table_poly)
+        lagrange_to_coeff_many(E, [L.permuted_input_poly, L.permuted_table_poly])
         lookups.append(L)
     lap("lookup_permuted")
 
@@ -497,8 +524,7 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
         for pt in E.commit(GL, perm_z, n):
             transcript.write_ec_point(pt)
     perm_polys = perm_z                                      # converted in place: the Lagrange form is not needed again
-    for p in perm_polys:
-        E.lagrange_to_coeff(p)
+    lagrange_to_coeff_many(E, perm_polys)
     lap("permutation_product")
 
     # 5. lookup grand products
@@ -509,9 +535,9 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
     if lookups:
         for pt in E.commit(GL, [L.product for L in lookups], n):
             transcript.write_ec_point(pt)
+    lagrange_to_coeff_many(E, [L.product for L in lookups])
     for L in lookups:
         L.product_poly = L.product
-        E.lagrange_to_coeff(L.product_poly)
         L.compressed_input = L.compressed_table = L.permuted_input = L.permuted_table = None
     lap("lookup_product")
 
@@ -525,14 +551,15 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
     y = fr_mont(transcript.squeeze_challenge())
 
     # 7. quotient: extended cosets, evaluate_h, divide by the vanishing polynomial, split, commit
-    advice_cosets = [E.coeff_to_extended(p) for p in advice_polys]
-    inst_cosets = [E.coeff_to_extended(p) for p in inst_polys]
+    both = coeff_to_extended_many(E, advice_polys + inst_polys)
+    advice_cosets, inst_cosets = both[:len(advice_polys)], both[len(advice_polys):]
+    del both
     lap("coeff_to_extended")
     values = E.alloc(ext_n)
     if cs.gates:
         E.graph_evaluate(cs.gates_program(), pk.fixed_cosets, advice_cosets, inst_cosets, beta, gamma, theta, y, values, ext_n, rot_scale)
     if perm_polys:
-        z_cosets = [E.coeff_to_extended(p) for p in perm_polys]
+        z_cosets = coeff_to_extended_many(E, perm_polys)
         cosets = [{"fixed": pk.fixed_cosets, "advice": advice_cosets, "instance": inst_cosets}[kind][c] for kind, c in cs.permutation]
         ext_omega = fr_mont(pow(ROOT_OF_UNITY, 1 << (28 - E.extended_k), R_MOD))
         E.permutation_constraints(values, ext_n, rot_scale, -(bf + 1), chunk, z_cosets, cosets, pk.sigma_cosets, pk.l0, pk.l_last, pk.l_active, beta, gamma, y, ext_omega)
@@ -540,7 +567,7 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
     for li, L in enumerate(lookups):
         table_value = E.alloc(ext_n)
         E.graph_evaluate(cs.lookup_value_program(li), pk.fixed_cosets, advice_cosets, inst_cosets, beta, gamma, theta, zero4, table_value, ext_n, rot_scale)
-        pc, ic, tc = (E.coeff_to_extended(p) for p in (L.product_poly, L.permuted_input_poly, L.permuted_table_poly))
+        pc, ic, tc = coeff_to_extended_many(E, [L.product_poly, L.permuted_input_poly, L.permuted_table_poly])
         E.lookup_constraints(values, ext_n, rot_scale, pc, ic, tc, table_value, pk.l0, pk.l_last, pk.l_active, beta, gamma, y)
         del table_value, pc, ic, tc
     del advice_cosets, inst_cosets

@@ -64,7 +64,7 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
   std::vector<MsmEntry> ent(M + 1);
   for (uint64_t t = 0; t < n; t++) msm_scatter_thread(t, n, scalars, g, cursor.data(), ent.data());
   std::vector<G1Xyzz> buckets(nb);
-  memset(buckets.data(), 0, nb * sizeof(G1Xyzz));
+  memset(buckets.data(), 0xAB, nb * sizeof(G1Xyzz));   // never cleared on the device either: only written buckets may be read
   uint64_t T = (M + g.L - 1) / g.L;
   std::vector<uint32_t> hk(T + 1, 0x12345678u), tk(T + 1, 0x12345678u), glist(T + 2);
   std::vector<G1Xyzz> head(T + 1), tail(T + 1);
@@ -82,7 +82,7 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
   MsmTail tl = msm_tail_shape(g.c);
   uint32_t per = msm_tail_partials(tl);
   std::vector<G1Xyzz> partials((uint64_t)g.BW * per), win(g.BW);
-  msm_tail_host(g, buckets.data(), partials.data());
+  msm_tail_host(g, offsets.data(), buckets.data(), partials.data());
   for (uint32_t w = 0; w < g.BW; w++) win[w] = msm_tail_finish(g, partials.data() + (uint64_t)w * per);
   *out = xyzz_to_affine(msm_combine_windows(win.data(), g.BW, g.c));
   return M;
@@ -191,7 +191,7 @@ void he_permutation_constraints(Fr* values, uint64_t size, int32_t rot_scale, in
   a.beta = *beta; a.gamma = *gamma; a.y = *y; a.extended_omega = *extended_omega;
   constexpr uint32_t zeta[8] = SPB_FR_ZETA_MONT; constexpr uint32_t delta[8] = SPB_FR_DELTA_MONT;
   a.delta = fr_macro(delta); a.delta_start = fp_mul(a.beta, fr_macro(zeta));
-  for (uint64_t idx = 0; idx < size; idx++) permutation_constraints_row(a, idx);
+  for (uint64_t idx = 0; idx < size; idx++) permutation_constraints_row(a, idx, fp_pow_u64(a.extended_omega, idx));
 }
 void he_lookup_constraints(Fr* values, uint64_t size, int32_t rot_scale, const Fr* product, const Fr* permuted_input, const Fr* permuted_table, const Fr* table_value,
                            const Fr* l0, const Fr* l_last, const Fr* l_active, const Fr* beta, const Fr* gamma, const Fr* y) {

@@ -180,7 +180,10 @@ def test_driver_edge_shapes(orc, variant):
         for i in range(1, rows):
             f[i + 1] = (a[i] - 3 * a[i - 1]) % R
         q = [1 if 1 <= i < rows else 0 for i in range(n)]
-        cs = ConstraintSystem(2, 1, 0, [Prod(Fixed(0), Sum(Sum(Advice(0), Neg(Scaled(Advice(0, -1), 3))), Neg(Fixed(1, 1))))], [], [])
+        # (times a(X): cs.degree() is 3 even without a permutation -- upstream always counts permutation::Argument::required_degree() --
+        # so the quotient is split into two pieces, and a degree-2 gate would leave the second one zero: a commitment to the point
+        # at infinity, which the EVM transcript refuses upstream as well; see test_degree_floor_matches_upstream)
+        cs = ConstraintSystem(2, 1, 0, [Prod(Prod(Fixed(0), Advice(0)), Sum(Sum(Advice(0), Neg(Scaled(Advice(0, -1), 3))), Neg(Fixed(1, 1))))], [], [])
         fixed, advice, copies, instances = [q, f], [a + [0] * (n - rows)], [], []
     elif variant == "no_lookup":
         # a * a = b with b copied from the instance column; permutation over (advice 0, advice 1, instance)
@@ -217,6 +220,25 @@ def test_driver_edge_shapes(orc, variant):
     proof = plonk.create_proof(E, pk, instances, [to_m(c) for c in advice], SeededRng(7), T)
     tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
     assert plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, instances, proof, tau)
+
+
+def test_degree_floor_matches_upstream(orc):
+    """ConstraintSystem::degree: 3 from the permutation argument even with no equality column, lookup input / table degrees
+    floored at 1, minimum_degree honoured. A permutation-free degree-2 circuit therefore still has TWO quotient
+    pieces; its second piece is the zero polynomial and the EVM transcript rejects the point at infinity, as upstream does."""
+    from spectre_b200.plonk import Advice, Const, ConstraintSystem, Fixed, Neg, Prod, Sum
+    assert ConstraintSystem(1, 1, 0, [Prod(Fixed(0), Advice(0))], [], []).degree() == 3
+    assert ConstraintSystem(1, 1, 0, [], [([Const(5)], [Fixed(0)])], []).degree() == 4                       # 2 + max(1, 0) + 1
+    assert ConstraintSystem(1, 2, 0, [], [([Const(5)], [Prod(Fixed(0), Prod(Advice(0), Advice(1)))])], []).degree() == 6   # 2 + 1 + 3
+    assert ConstraintSystem(1, 1, 0, [Prod(Fixed(0), Advice(0))], [], [], minimum_degree=7).degree() == 7
+    k = 5; n = 1 << k
+    cs = ConstraintSystem(1, 1, 0, [Prod(Fixed(0), Sum(Advice(0), Neg(Advice(0))))], [], [])
+    assert (cs.degree(), cs.chunk_len()) == (3, 1)
+    E = OracleEngine(k, cs.degree())
+    col = np.stack([plonk.fr_mont(i) for i in range(n)])
+    pk = plonk.keygen(E, cs, k, [col], [])
+    with pytest.raises(ValueError, match="infinity"):
+        plonk.create_proof(E, pk, [], [col], SeededRng(3), EvmTranscriptWrite(pk.vk_digest))
 
 
 def test_create_proof_argument_errors(orc):

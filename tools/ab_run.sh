@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of library build variants on one GPU box: tools/ab_run.sh <tag> <variant> [<variant> ...]   ("" = product build)
+# A/B of library build variants on one GPU box: tools/ab_run.sh <tag> <variant> [<variant> ...]   ("base" = product build)
 tag=$1; shift
 mkdir -p gpurun_out
 for v in "$@"; do
