@@ -91,6 +91,10 @@ int spb_srs_setup(spb_ctx* ctx, uint32_t k, const spb_fr* s, spb_srs** out);
 /* copy a range of a resident basis back to the host (ParamsKZG::get_g / write) */
 int spb_srs_download(spb_ctx* ctx, const spb_srs* srs, int basis, size_t start, size_t count, spb_g1_affine* out);
 void spb_srs_free(spb_ctx* ctx, spb_srs* srs);
+/* ParamsKZG::downsize(k), k <= the handle's k: g truncated to 2^k points and g_lagrange recomputed for the smaller domain
+ * (g_to_lagrange: the inverse DFT over the group, on the device; no knowledge of the secret needed). The reference keeps
+ * a degree -> params map for exactly this (prover/src/prover.rs:34). Returns a NEW handle without window tables. */
+int spb_srs_downsize(spb_ctx* ctx, const spb_srs* srs, uint32_t k, spb_srs** out);
 /* ParamsKZG::read / ::write, SerdeFormat::RawBytes: k (u32 LE) | g[2^k] | g_lagrange[2^k] | g2 | s_g2 with every
  * coordinate as its in-memory Montgomery limbs -- the `params/kzg_bn254_{k}.srs` file halo2-base's gen_srs caches
  * (reference: prover/src/cli.rs:48, .gitignore:36). Read streams the points straight into device memory. */

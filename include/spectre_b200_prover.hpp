@@ -374,13 +374,31 @@ struct HostMemory : DeviceMemory {                           // "device" = host:
 // Device memory for the real library. Every memset / copy is enqueued on the context's own stream (spb_stream), which is
 // the stream every `_dev` entry point is ordered on: a buffer is therefore ready for the library call that follows without
 // any synchronisation (stream contract in spectre_b200.h; the legacy default stream would NOT order against that stream).
+// Allocation is a size-keyed cache: create_proof allocates and drops the same few buffer sizes (n, 2^extended_k) dozens of
+// times per proof, and cudaMalloc / cudaFree cost milliseconds and a device-wide synchronisation each. A freed block goes
+// back on its size's free list and is handed out again for the next request of that size -- safe without events because
+// every consumer of the old contents was enqueued on the same stream before the new owner's memset. trim() or the
+// destructor return the memory to the driver.
 struct CudaMemory : DeviceMemory {
   explicit CudaMemory(spb_ctx* ctx) : stream_((cudaStream_t)spb_stream(ctx, 0)) { if (!stream_) throw std::runtime_error("CudaMemory: spb_stream returned no stream"); }
+  ~CudaMemory() override { trim(); }
   static void ck(cudaError_t e) { if (e != cudaSuccess) throw std::runtime_error(std::string("cuda: ") + cudaGetErrorString(e)); }
   Fr* alloc(size_t rows) override {
-    void* p; ck(cudaMalloc(&p, (rows ? rows : 1) * sizeof(Fr))); ck(cudaMemsetAsync(p, 0, (rows ? rows : 1) * sizeof(Fr), stream_)); return (Fr*)p;
+    const size_t bytes = (rows ? rows : 1) * sizeof(Fr);
+    void* p = nullptr;
+    auto it = free_.find(bytes);
+    if (it != free_.end() && !it->second.empty()) { p = it->second.back(); it->second.pop_back(); }
+    else {
+      cudaError_t e = cudaMalloc(&p, bytes);
+      if (e != cudaSuccess) { cudaGetLastError(); trim(); e = cudaMalloc(&p, bytes); }   // out of memory: give the cache back first
+      ck(e);
+    }
+    size_[p] = bytes;
+    ck(cudaMemsetAsync(p, 0, bytes, stream_));
+    return (Fr*)p;
   }
-  void free(Fr* p) override { cudaFree(p); }                 // synchronises the device: nothing in flight can still use p
+  void free(Fr* p) override { if (!p) return; auto it = size_.find(p); if (it == size_.end()) { cudaFree(p); return; } free_[it->second].push_back(p); size_.erase(it); }
+  void trim() { cudaStreamSynchronize(stream_); for (auto& kv : free_) for (void* p : kv.second) cudaFree(p); free_.clear(); }
   void upload(Fr* d, const Fr* s, size_t rows) override {    // s may be a temporary: it must be consumed before returning
     ck(cudaMemcpyAsync(d, s, rows * sizeof(Fr), cudaMemcpyHostToDevice, stream_)); ck(cudaStreamSynchronize(stream_));
   }
@@ -390,6 +408,8 @@ struct CudaMemory : DeviceMemory {
   void copy(Fr* d, const Fr* s, size_t rows) override { ck(cudaMemcpyAsync(d, s, rows * sizeof(Fr), cudaMemcpyDeviceToDevice, stream_)); }
  private:
   cudaStream_t stream_;
+  std::map<size_t, std::vector<void*>> free_;
+  std::map<void*, size_t> size_;
 };
 #endif
 

@@ -1089,3 +1089,10 @@ void orc_vec_fold(const fe* const* polys, size_t count, const fe* y, fe* out, si
     out[i] = acc;
   }
 }
+/* compute_inner_product(a, b) = sum_i a_i * b_i ([UPSTREAM] halo2_proofs/src/arithmetic.rs). Used by
+ * bench.py's parity flags: for bases h_i * G1 with known h_i, MSM(s, bases) = compute_inner_product(s, h) * G1. */
+void orc_compute_inner_product(fe* out, const fe* a, const fe* b, size_t n) {
+  fe acc; memset(&acc, 0, sizeof acc);
+  for (size_t i = 0; i < n; i++) acc = f_add(&FR, acc, f_mul(&FR, a[i], b[i]));
+  *out = acc;
+}

@@ -408,3 +408,12 @@ def vec_fold(polys, y):
     out = np.empty_like(keep[0])
     lib().orc_vec_fold(pp, ctypes.c_size_t(len(polys)), _p(_c(y)), _p(out), ctypes.c_size_t(out.shape[0]))
     return out
+
+
+def compute_inner_product(a, b):
+    """arithmetic::compute_inner_product: sum_i a_i * b_i (Montgomery in, Montgomery out)"""
+    a = _c(a); b = _c(b)
+    assert a.shape == b.shape
+    out = np.empty(4, dtype=np.uint64)
+    lib().orc_compute_inner_product(_p(out), _p(a), _p(b), ctypes.c_size_t(a.shape[0]))
+    return out

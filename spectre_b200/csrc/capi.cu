@@ -4,6 +4,7 @@
 #include "ntt.cuh"
 #include "../../include/spectre_b200.h"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 using namespace spb;
@@ -389,7 +390,9 @@ int spb_extended_to_coeff_dev(spb_ctx* ctx, const spb_domain* dm, const spb_fr* 
 // pass's output through NVLink peer access, intermediate passes run in their own HBM.
 static int ntt_batch_devices(spb_ctx* ctx, const spb_fr* const* d_in, spb_fr* const* d_out, size_t count, uint32_t k, const Fr& omega, const NttOpts& o) {
   DeviceState& d0 = ctx->dev[0];
-  const size_t D = (ctx->peer_access && ctx->dev.size() > 1 && k >= 16) ? ctx->dev.size() : 1;
+  uint32_t min_k = 16;   // smaller transforms are launch-bound: first device only (tests lower it: SPB_SHARD_MIN_LOGN)
+  if (const char* e = getenv("SPB_SHARD_MIN_LOGN")) { int v = atoi(e); if (v >= 1) min_k = (uint32_t)v; }
+  const size_t D = (ctx->peer_access && ctx->dev.size() > 1 && k >= min_k) ? ctx->dev.size() : 1;
   SPB_CUDA(ctx, cudaSetDevice(d0.device));
   SPB_CUDA(ctx, cudaEventRecord(d0.ev0, d0.stream));
   if (D > 1) SPB_CUDA(ctx, cudaEventRecord(d0.dep_ev, d0.stream));

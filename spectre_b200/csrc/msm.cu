@@ -333,6 +333,70 @@ fail:
   return SPB_ERR_CUDA;
 }
 
+// ParamsKZG::downsize(k) ([UPSTREAM] halo2_proofs/src/poly/kzg/commitment.rs; the reference keeps a degree -> params map "for
+// params downsize", prover/src/prover.rs:34): g truncated to 2^k points, g_lagrange recomputed for the smaller domain as
+// g_to_lagrange(g) = the inverse DFT over the group (log2 n stages of n/2 butterflies, each one point addition, one
+// subtraction and one 254-bit scalar multiple by a power of omega^-1; then 1/n and affine normalisation). Works for any SRS
+// (no knowledge of the secret). Returns a NEW handle (no window tables); the caller frees the old one when it is done with it.
+static int srs_downsize_locked(spb_ctx* ctx, const spb_srs* srs, uint32_t k, spb_srs** made) {
+  const uint64_t n = 1ull << k;
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  G1Affine* g0 = (G1Affine*)slot(ctx, d, "ds_g", n * sizeof(G1Affine));          // the first n points of g, gathered on device 0
+  G1Xyzz* pts = (G1Xyzz*)slot(ctx, d, "ds_pts", n * sizeof(G1Xyzz));
+  G1Affine* lag = (G1Affine*)slot(ctx, d, "ds_lag", n * sizeof(G1Affine));
+  Fr* tw = (Fr*)slot(ctx, d, "ds_tw", (n / 2 ? n / 2 : 1) * sizeof(Fr));
+  if (!g0 || !pts || !lag || !tw) return SPB_ERR_OOM;
+  for (auto& sh : srs->shards) {
+    if (sh.start >= n || !sh.count) continue;
+    if (!sh.g) return set_error(ctx, SPB_ERR_STATE, "spb_srs_downsize: basis g not resident");
+    const size_t cnt = (n - sh.start) < sh.count ? (n - sh.start) : sh.count;
+    SPB_CUDA(ctx, cudaMemcpyPeerAsync(g0 + sh.start, d.device, sh.g, ctx->dev[sh.dev_index].device, cnt * sizeof(G1Affine), d.stream));
+  }
+  Fr w; { constexpr uint32_t v[8] = SPB_FR_ROOT_OF_UNITY_MONT; for (int i = 0; i < 8; i++) w.l[i] = v[i]; }
+  for (uint32_t i = k; i < 28; i++) w = fp_sqr(w);
+  const Fr w_inv = fp_inv(w), n_inv = fp_inv(fr_from_u64(n));
+  const unsigned tb = 128;
+  ec_lift_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, d.stream>>>(n, g0, pts);
+  if (n >= 2) {
+    fr_powers_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, d.stream>>>(tw, w_inv, n / 2);
+    for (uint64_t half = n / 2; half >= 1; half >>= 1) ec_ntt_stage_kernel<<<(unsigned)((n / 2 + tb - 1) / tb), tb, 0, d.stream>>>(n, half, tw, pts);
+  }
+  ec_ntt_finish_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, d.stream>>>(n, k, n_inv, pts, lag);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches += 3 + k;
+  spb_srs* s = srs_alloc(ctx, k);
+  *made = s;
+  memcpy(s->g2, srs->g2, 128); memcpy(s->s_g2, srs->s_g2, 128);
+  cudaError_t e = cudaSuccess;
+  for (auto& sh : s->shards) {
+    if (!sh.count) continue;
+    DeviceState& dd = ctx->dev[sh.dev_index];
+    e = cudaSetDevice(dd.device);
+    if (e == cudaSuccess) e = cudaMalloc(&sh.g, sh.count * sizeof(G1Affine));
+    if (e == cudaSuccess) e = cudaMalloc(&sh.g_lagrange, sh.count * sizeof(G1Affine));
+    if (e != cudaSuccess) break;
+    cudaSetDevice(d.device);
+    e = cudaMemcpyPeerAsync(sh.g, dd.device, g0 + sh.start, d.device, sh.count * sizeof(G1Affine), d.stream);
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(sh.g_lagrange, dd.device, lag + sh.start, d.device, sh.count * sizeof(G1Affine), d.stream);
+    if (e != cudaSuccess) break;
+  }
+  cudaSetDevice(d.device);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+  if (e != cudaSuccess) return set_error(ctx, SPB_ERR_CUDA, "spb_srs_downsize: %s", cudaGetErrorString(e));
+  return 0;
+}
+int spb_srs_downsize(spb_ctx* ctx, const spb_srs* srs, uint32_t k, spb_srs** out) {
+  if (!ctx || !srs || !out || k > srs->k) return SPB_ERR_ARG;
+  if (srs->table_c) return set_error(ctx, SPB_ERR_STATE, "spb_srs_downsize: call before spb_srs_precompute (the table rows replaced the plain basis layout)");
+  spb_srs* made = nullptr;
+  int rc;
+  { std::lock_guard<std::mutex> lk(ctx->mu); rc = srs_downsize_locked(ctx, srs, k, &made); }
+  if (rc != 0) { if (made) spb_srs_free(ctx, made); return rc; }
+  *out = made;
+  return 0;
+}
+
 // ParamsKZG::read / write in SerdeFormat::RawBytes: k (u32 LE) | g[n] | g_lagrange[n] | g2 | s_g2, every coordinate as
 // its in-memory Montgomery limbs -- the file halo2-base's gen_srs caches as params/kzg_bn254_{k}.srs
 // ([UPSTREAM] halo2_proofs/src/poly/kzg/commitment.rs; reference .gitignore:36 `params/`). Streamed through a pinned

@@ -535,6 +535,53 @@ __global__ void srs_scalars_kernel(int mode, Fr s, Fr w, Fr coef, uint64_t start
 }
 #endif
 
+// ---- ParamsKZG::downsize: g_to_lagrange = inverse DFT over the group ------------------------------------------------------
+// k * P for a canonical (non-Montgomery) 254-bit scalar: MSB-first double-and-add
+SPB_HD G1Xyzz xyzz_mul_scalar(const G1Xyzz& p, const Fr& k) {
+  int top = 255;
+  while (top >= 0 && !((k.l[top >> 5] >> (top & 31)) & 1)) top--;
+  G1Xyzz r = xyzz_identity();
+  for (int i = top; i >= 0; i--) {
+    r = xyzz_dbl(r);
+    if ((k.l[i >> 5] >> (i & 31)) & 1) xyzz_add(r, p);
+  }
+  return r;
+}
+// one decimation-in-frequency stage of the group DFT, butterfly `tid` of n/2: (a, b) <- (a + b, (a - b) * w^(j * stride)) with
+// j = tid mod half. tw[i] = w^i (Montgomery), i < n/2. After log2 n stages the result sits in bit-reversed order.
+SPB_HD void ec_ntt_stage_thread(uint64_t tid, uint64_t n, uint64_t half, const Fr* tw, G1Xyzz* p) {
+  if (tid >= n / 2) return;
+  const uint64_t j = tid & (half - 1), base = ((tid - j) << 1) + j, stride = (n / 2) / half;
+  G1Xyzz a = p[base], b = p[base + half];
+  G1Xyzz sum = a; xyzz_add(sum, b);
+  G1Xyzz diff = a; xyzz_add(diff, xyzz_neg(b));
+  p[base] = sum;
+  p[base + half] = j == 0 ? diff : xyzz_mul_scalar(diff, fp_from_mont(tw[j * stride]));
+}
+// out[i] = scale * p[bitrev_k(i)] as an affine point (scale = 1/n, Montgomery)
+SPB_HD void ec_ntt_finish_thread(uint64_t tid, uint64_t n, uint32_t k, const Fr& scale, const G1Xyzz* p, G1Affine* out) {
+  if (tid >= n) return;
+  uint64_t r = 0;
+  for (uint32_t b = 0; b < k; b++) r |= ((tid >> b) & 1ull) << (k - 1 - b);
+  out[tid] = xyzz_to_affine(xyzz_mul_scalar(p[r], fp_from_mont(scale)));
+}
+#if defined(__CUDACC__) && defined(SPB_MSM_KERNELS)
+__global__ void __launch_bounds__(128) ec_lift_kernel(uint64_t n, const G1Affine* in, G1Xyzz* out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = xyzz_from_affine(in[i]);
+}
+__global__ void __launch_bounds__(128) ec_ntt_stage_kernel(uint64_t n, uint64_t half, const Fr* tw, G1Xyzz* p) {
+  ec_ntt_stage_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, n, half, tw, p);
+}
+__global__ void __launch_bounds__(128) ec_ntt_finish_kernel(uint64_t n, uint32_t k, Fr scale, const G1Xyzz* p, G1Affine* out) {
+  ec_ntt_finish_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, n, k, scale, p, out);
+}
+__global__ void fr_powers_kernel(Fr* out, Fr base, uint64_t count) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < count) out[i] = fp_pow_u64(base, i);
+}
+#endif
+
 // ---- step 7 (host): Horner over the bucket windows ------------------------------------------------------
 inline G1Xyzz msm_combine_windows(const G1Xyzz* S, uint32_t BW, uint32_t c) {
   G1Xyzz acc = xyzz_identity();

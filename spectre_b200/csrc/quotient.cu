@@ -13,6 +13,7 @@
 // not pinned by any reference-owned vector (none exists for this row).
 #include "common.cuh"
 #include "quotient.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 using namespace spb;
@@ -48,7 +49,9 @@ struct RowShard { int dev_index; uint64_t lo, hi; };
 std::vector<RowShard> row_shards(spb_ctx* ctx, uint64_t size) {
   std::vector<RowShard> v;
   const size_t D = ctx->dev.size();
-  if (D > 1 && ctx->peer_access && size >= ((uint64_t)1 << 16)) {
+  uint64_t min_rows = (uint64_t)1 << 16;   // below this a pass is launch-bound: one device (tests lower it: SPB_SHARD_MIN_ROWS)
+  if (const char* e = getenv("SPB_SHARD_MIN_ROWS")) { long long v = atoll(e); if (v >= 256) min_rows = (uint64_t)v; }
+  if (D > 1 && ctx->peer_access && size >= min_rows) {
     const uint64_t per = ((size + D - 1) / D + 255) / 256 * 256;
     for (size_t i = 0; i < D; i++) {
       uint64_t lo = per * i, hi = lo + per < size ? lo + per : size;

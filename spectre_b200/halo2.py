@@ -460,6 +460,13 @@ class ParamsKZG:
         backend.lib.spb_srs_k.argtypes = [ctypes.c_void_p]
         return cls(backend, int(backend.lib.spb_srs_k(h)), h)
 
+    def downsize(self, k):
+        """ParamsKZG::downsize(k): a new handle with g truncated to 2^k points and g_lagrange = g_to_lagrange(g) recomputed on the
+        device (upstream mutates in place; here the old handle stays valid until dropped)."""
+        h = ctypes.c_void_p()
+        self.be.check(self.be.lib.spb_srs_downsize(self.be.ctx, self.h, ctypes.c_uint32(k), ctypes.byref(h)), "spb_srs_downsize")
+        return ParamsKZG(self.be, k, h)
+
     def write(self, path):
         self.be.check(self.be.lib.spb_srs_write_file(self.be.ctx, self.h, path.encode()), "spb_srs_write_file")
 

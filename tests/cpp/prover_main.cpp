@@ -87,6 +87,10 @@ int main(int argc, char** argv) {
 #ifdef SPB_PROVER_WITH_CUDART
     if (getenv("SPB_MAIN_TABLES") && spb_srs_precompute(ctx, srs) != 0) throw std::runtime_error(std::string("spb_srs_precompute: ") + spb_last_error(ctx));
     CudaMemory mem(ctx); // the real library: device buffers through the CUDA runtime, on the context's stream
+    // a prover keeps its synthesis buffers pinned: register the column / rng files once so uploads are plain DMA
+    spb_host_register(ctx, fixed_raw.data(), fixed_raw.size());
+    spb_host_register(ctx, advice_raw.data(), advice_raw.size());
+    if (!rng_raw.empty()) spb_host_register(ctx, rng_raw.data(), rng_raw.size());
 #else
     HostMemory mem;      // the CPU shim: "device" pointers are host pointers
 #endif

@@ -87,6 +87,16 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
   *out = xyzz_to_affine(msm_combine_windows(win.data(), g.BW, g.c));
   return M;
 }
+// ParamsKZG::downsize's g_to_lagrange: the per-thread bodies of the EC inverse-DFT kernels, run serially
+void he_g_to_lagrange(G1Affine* out, const G1Affine* g, uint32_t k, const Fr* omega_inv, const Fr* n_inv) {
+  const uint64_t n = 1ull << k;
+  std::vector<G1Xyzz> p(n);
+  for (uint64_t i = 0; i < n; i++) p[i] = xyzz_from_affine(g[i]);
+  std::vector<Fr> tw(n / 2 ? n / 2 : 1);
+  for (uint64_t i = 0; i < n / 2; i++) tw[i] = fp_pow_u64(*omega_inv, i);
+  for (uint64_t half = n / 2; half >= 1; half >>= 1) for (uint64_t t = 0; t < n / 2; t++) ec_ntt_stage_thread(t, n, half, tw.data(), p.data());
+  for (uint64_t t = 0; t < n; t++) ec_ntt_finish_thread(t, n, k, *n_inv, p.data(), out);
+}
 void he_geometry(uint64_t n, int precomp, uint32_t* c, uint32_t* W) { MsmGeom g = msm_make_geometry(msm_choose_c(n, precomp != 0), precomp != 0, 0); *c = g.c; *W = g.W; }
 }
 

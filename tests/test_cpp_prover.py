@@ -155,15 +155,8 @@ def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k):
 
 
 def _build_main_against_the_real_library():
-    from spectre_b200 import build
-    lib = build.build()
-    libdir = os.path.dirname(lib)
-    exe = os.path.join(ROOT, "tests", "cpp", "prover_main_cuda")
-    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-DSPB_PROVER_WITH_CUDART", "-I" + os.path.join(cuda, "include"), "-o", exe,
-                           os.path.join(ROOT, "tests", "cpp", "prover_main.cpp"), "-L" + libdir, "-lspectre_b200", "-Wl,-rpath," + libdir,
-                           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + os.path.join(cuda, "lib64")])
-    return exe
+    from tools import cpp_driver
+    return cpp_driver.build_main_against_the_real_library()
 
 
 def test_cpp_driver_links_against_the_real_library():
@@ -171,17 +164,9 @@ def test_cpp_driver_links_against_the_real_library():
     assert os.path.exists(_build_main_against_the_real_library())
 
 
-def _dump_case(d, head, k, digest, instances, copies, counts_or_calls, fixed, adv, rng_rows, tau):
-    with open(os.path.join(d, "meta.txt"), "w") as f:
-        f.write(head + "\nk %d\ndigest %x\ninstances %s\n" % (k, digest, " ".join("%x" % v for v in instances)))
-        for (c1, r1), (c2, r2) in copies:
-            f.write("copy %d %d %d %d\n" % (c1, r1, c2, r2))
-        f.write("rng " + " ".join(str(c) for c in counts_or_calls) + "\n")
-    np.concatenate(fixed).tofile(os.path.join(d, "fixed.bin")); np.concatenate(adv).tofile(os.path.join(d, "advice.bin"))
-    with open(os.path.join(d, "rng.bin"), "wb") as f:
-        for rows in rng_rows:
-            f.write(np.ascontiguousarray(rows, dtype=np.uint64).tobytes())
-    tau.tofile(os.path.join(d, "tau.bin"))
+def _dump_case(*args):
+    from tools import cpp_driver
+    cpp_driver.dump_case(*args)
 
 
 @pytest.mark.gpu

@@ -134,6 +134,58 @@ def test_params_kzg_setup_and_commit_seed0(be, orc):
     assert np.array_equal(affine_of(orc, params.commit(short)), orc.commit_known_tau(short))
 
 
+@pytest.mark.parametrize("k,k2", [(10, 7), (12, 12), (9, 0)])
+def test_params_kzg_downsize(be, orc, k, k2):
+    """ParamsKZG::downsize(k2): g truncated, g_lagrange recomputed by the group inverse DFT on the device -- must equal the
+    seed-0 SRS of the smaller domain (the derivation pinned by the verifier contracts), and commitments through it the
+    known-tau values. The original handle is untouched."""
+    from spectre_b200.halo2 import ParamsKZG, BASIS_G, BASIS_G_LAGRANGE
+    params = ParamsKZG.setup(be, k, orc.srs_tau())
+    small = params.downsize(k2)
+    n2 = 1 << k2
+    assert np.array_equal(small.get_g(basis=BASIS_G), orc.srs_g(k2, 0, n2))
+    assert np.array_equal(small.get_g(basis=BASIS_G_LAGRANGE), orc.srs_g_lagrange(k2, 0, n2))
+    poly = orc.fr_random_chacha(n2, 77)
+    assert np.array_equal(affine_of(orc, small.commit_lagrange(poly)), orc.commit_lagrange_known_tau(k2, poly))
+    assert np.array_equal(params.get_g(basis=BASIS_G_LAGRANGE), orc.srs_g_lagrange(k, 0, 1 << k))
+    with pytest.raises(Exception):
+        params.downsize(k + 1)
+
+
+def test_two_contexts_prove_concurrently_on_one_device(orc):
+    """Spectre's RPC `--concurrency N` (prover/src/prover.rs:114): one context per concurrent proof on the same GPU, sharing
+    nothing but the device. Two threads prove at the same time; both proofs are byte-identical to the sequential ones."""
+    import threading
+    from spectre_b200 import circuits, halo2, plonk
+    from spectre_b200.transcript import EvmTranscriptWrite
+    from tests.plonk_oracle_engine import SeededRng
+    k, instances = 11, [3, 1, 4]
+    cs = circuits.halo2lib_shape(4, 1)
+    fixed, adv, copies = circuits.halo2lib_witness(cs, k, instances, lookup_bits=5, groups=100, num_gate_advice=4, num_lookup_advice=1)
+    ctxs = [halo2.Backend([0]) for _ in range(2)]
+    try:
+        engines, keys = [], []
+        for b in ctxs:
+            E = plonk.DeviceEngine(b, halo2.ParamsKZG.setup(b, k, orc.srs_tau()), k, cs.degree())
+            engines.append(E); keys.append(plonk.keygen(E, cs, k, fixed, copies, vk_digest=99))
+        want = [plonk.create_proof(E, pk, [instances], adv, SeededRng(5 + i), EvmTranscriptWrite(pk.vk_digest)) for i, (E, pk) in enumerate(zip(engines, keys))]
+        got, errs = [None, None], []
+
+        def work(i):
+            try:
+                for _ in range(3):
+                    got[i] = plonk.create_proof(engines[i], keys[i], [instances], adv, SeededRng(5 + i), EvmTranscriptWrite(keys[i].vk_digest))
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        assert not errs, errs
+        assert got == want
+    finally:
+        for b in ctxs:
+            b.close()
+
+
 def test_reference_kat_range_table_k23(be, orc, kats):
     """The reference's own pinned number: commit_lagrange(range table 0..2^19) under the seed-0 SRS at K=23 equals
     the fixed-column commitment in contracts/snark-verifiers/sync_step_verifier.sol:1048-1049. Only the first 2^19

@@ -232,19 +232,23 @@ def test_k23_proof_equals_the_contract_accepted_fixture(be, orc, kats, path):
         json.dump({"k": k, "keygen_s": t1 - t0, "create_proof_s": t2 - t1, "stages": timings}, f)
 
 
-def test_proof_with_msm_sharded_over_two_devices_if_available(orc):
-    """One context driving two GPUs: every commitment of create_proof is an MSM sharded by point range (scalar ranges
-    peer-copied over NVLink), the polynomial arithmetic stays on the first device; the proof bytes do not change."""
+def test_proof_with_msm_sharded_over_two_devices_if_available(orc, monkeypatch):
+    """One context driving several GPUs: every commitment of create_proof is an MSM sharded by point range (scalar ranges
+    peer-copied over NVLink), the quotient kernels run on row ranges and the NTTs on whole polynomials spread over the
+    devices (all through peer access to the first device's buffers; thresholds lowered so that this small circuit is
+    actually sharded); the proof bytes do not change."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    monkeypatch.setenv("SPB_SHARD_MIN_ROWS", "256")
+    monkeypatch.setenv("SPB_SHARD_MIN_LOGN", "8")
     from spectre_b200 import circuits, halo2, plonk
     from spectre_b200.transcript import EvmTranscriptWrite
     from tests.plonk_oracle_engine import OracleEngine, SeededRng
     k, instances = 12, [3, 1, 4]
     cs = circuits.halo2lib_shape(4, 1)
     fixed, adv, copies = circuits.halo2lib_witness(cs, k, instances, lookup_bits=5, groups=200, num_gate_advice=4, num_lookup_advice=1)
-    be2 = halo2.Backend([0, 1])
+    be2 = halo2.Backend(list(range(min(torch.cuda.device_count(), 8))))
     try:
         proofs = []
         for E in (plonk.DeviceEngine(be2, halo2.ParamsKZG.setup(be2, k, orc.srs_tau()).precompute(), k, cs.degree()), OracleEngine(k, cs.degree())):

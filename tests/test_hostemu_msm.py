@@ -102,3 +102,17 @@ def test_geometry_choice(he):
         he.he_geometry(ctypes.c_uint64(n), ctypes.c_int(pre), ctypes.byref(c), ctypes.byref(W))
         # W*c >= 255 keeps one spare bit above the 254-bit scalar so the signed-digit carry never leaves the top window
         assert lo <= c.value <= hi and W.value * c.value >= 255 and (W.value - 1) * c.value < 255
+
+
+def test_g_to_lagrange_of_the_seed0_srs(he, orc):
+    """ParamsKZG::downsize recomputes g_lagrange = g_to_lagrange(g) (inverse DFT over the group). For the seed-0 SRS that must
+    reproduce the Lagrange basis the oracle derives from the known secret -- the derivation the verifier contracts pin."""
+    from tests import pyref
+    for k in (0, 1, 3, 5):
+        n = 1 << k
+        g = orc.srs_g(k, 0, n)
+        w = pow(pow(7, (pyref.R_MOD - 1) >> 28, pyref.R_MOD), 1 << (28 - k), pyref.R_MOD)
+        w_inv = orc.fr([pow(w, -1, pyref.R_MOD)]); n_inv = orc.fr([pow(n, -1, pyref.R_MOD)])
+        out = np.empty((n, 8), dtype=np.uint64)
+        he.he_g_to_lagrange(_p(out), _p(np.ascontiguousarray(g)), ctypes.c_uint32(k), _p(w_inv), _p(n_inv))
+        assert np.array_equal(out, orc.srs_g_lagrange(k, 0, n)), k
