@@ -31,6 +31,27 @@ def test_every_declared_symbol_is_exported(libpath):
     assert not missing, "declared in include/spectre_b200.h but not exported: %s" % missing
 
 
+def test_rust_shim_binds_only_declared_and_exported_symbols(libpath):
+    """shim/halo2_proofs_b200/src/b200.rs (the Rust `extern "C"` block a maintainer compiles on a cargo host) names only entry
+    points the header declares and the library exports, with the argument count of the C declaration."""
+    with open(os.path.join(ROOT, "shim", "halo2_proofs_b200", "src", "b200.rs")) as f:
+        rust = f.read()
+    block = rust[rust.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    rust_fns = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (spb_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->[^;]*)?;", block, flags=re.S)}
+    assert len(rust_fns) >= 45
+    with open(os.path.join(ROOT, "include", "spectre_b200.h")) as f:
+        header = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    lib = ctypes.CDLL(libpath)
+    for name, args in rust_fns.items():
+        assert hasattr(lib, name), "%s is bound by the Rust shim but not exported" % name
+        m = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, header, flags=re.S)
+        assert m, "%s is bound by the Rust shim but not declared in the header" % name
+        c_args = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
+        r_args = [a for a in args.split(",") if a.strip()]
+        assert len(c_args) == len(r_args), "%s: %d C parameters, %d in the Rust declaration" % (name, len(c_args), len(r_args))
+
+
 def test_only_abi_symbols_are_exported(libpath):
     out = subprocess.check_output(["nm", "-D", "--defined-only", libpath], text=True)
     exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
