@@ -75,6 +75,12 @@ int spb_device_count(void);
 /* The CUDA stream (a cudaStream_t) every `_dev` call of device `dev_index` of this context is ordered on; NULL on a bad
  * index. See "Stream contract" above. */
 void* spb_stream(spb_ctx* ctx, int dev_index);
+/* File <-> device streaming for the prover's large artefacts (params/kzg_bn254_{k}.srs, *.pkey; reference: .gitignore:34-43,
+ * lightclient-circuits/src/util/circuit.rs:104-115,273-280): `bytes` bytes at `offset` of the file go straight to / come from
+ * a device buffer of the first device through two pinned staging buffers, the file read of one chunk overlapping the DMA of
+ * the previous one. spb_write_file_dev truncates the file unless `append`. */
+int spb_read_file_dev(spb_ctx* ctx, const char* path, uint64_t offset, void* d_dst, size_t bytes);
+int spb_write_file_dev(spb_ctx* ctx, const char* path, int append, const void* d_src, size_t bytes);
 /* pin / unpin a caller buffer so host<->device copies run at full PCIe rate (optional) */
 int spb_host_register(spb_ctx* ctx, void* ptr, size_t bytes);
 int spb_host_unregister(spb_ctx* ctx, void* ptr);

@@ -398,7 +398,15 @@ struct CudaMemory : DeviceMemory {
     return (Fr*)p;
   }
   void free(Fr* p) override { if (!p) return; auto it = size_.find(p); if (it == size_.end()) { cudaFree(p); return; } free_[it->second].push_back(p); size_.erase(it); }
-  void trim() { cudaStreamSynchronize(stream_); for (auto& kv : free_) for (void* p : kv.second) cudaFree(p); free_.clear(); }
+  // call before spb_shutdown (the stream belongs to the context); a no-op when nothing is cached
+  void trim() {
+    bool any = false;
+    for (auto& kv : free_) any = any || !kv.second.empty();
+    if (!any) return;
+    cudaStreamSynchronize(stream_);
+    for (auto& kv : free_) for (void* p : kv.second) cudaFree(p);
+    free_.clear();
+  }
   void upload(Fr* d, const Fr* s, size_t rows) override {    // s may be a temporary: it must be consumed before returning
     ck(cudaMemcpyAsync(d, s, rows * sizeof(Fr), cudaMemcpyHostToDevice, stream_)); ck(cudaStreamSynchronize(stream_));
   }

@@ -4,6 +4,8 @@
 #include "ntt.cuh"
 #include "../../include/spectre_b200.h"
 #include <stdarg.h>
+#include <stdio.h>
+#include <sys/types.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -31,6 +33,58 @@ void* slot(spb_ctx* ctx, DeviceState& d, const char* name, size_t bytes) {
   if (e != cudaSuccess) { set_error(ctx, SPB_ERR_OOM, "cudaMalloc(%zu) for slot %s: %s", want, name, cudaGetErrorString(e)); b.ptr = nullptr; return nullptr; }
   b.cap = want;
   return b.ptr;
+}
+
+// Double-buffered staging: two pinned 16 MiB buffers per device (slot-like, allocated once). While the DMA of one buffer is
+// in flight (cudaMemcpyAsync + an event), the host fills / drains the other, so the file system and the PCIe copy overlap
+// instead of alternating as a synchronous cudaMemcpy loop does. (cuFile / GDS would remove the bounce buffer altogether; the
+// pool's boxes expose no nvidia-fs, where cuFile itself falls back to exactly this scheme.)
+static const size_t kStageBytes = (size_t)16 << 20;
+static int stage_buffers(spb_ctx* ctx, DeviceState& d, char** a, char** b, cudaEvent_t* ea, cudaEvent_t* eb) {
+  if (!d.stage[0]) {
+    SPB_CUDA(ctx, cudaMallocHost(&d.stage[0], kStageBytes));
+    SPB_CUDA(ctx, cudaMallocHost(&d.stage[1], kStageBytes));
+    SPB_CUDA(ctx, cudaEventCreateWithFlags(&d.stage_done[0], cudaEventDisableTiming));
+    SPB_CUDA(ctx, cudaEventCreateWithFlags(&d.stage_done[1], cudaEventDisableTiming));
+  }
+  *a = (char*)d.stage[0]; *b = (char*)d.stage[1]; *ea = d.stage_done[0]; *eb = d.stage_done[1];
+  return 0;
+}
+int stream_file_to_device(spb_ctx* ctx, DeviceState& d, FILE* f, void* d_dst, size_t bytes, const char* what) {
+  char* buf[2]; cudaEvent_t ev[2];
+  SPB_TRY(stage_buffers(ctx, d, &buf[0], &buf[1], &ev[0], &ev[1]));
+  bool busy[2] = {false, false};
+  int cur = 0;
+  for (size_t off = 0; off < bytes; off += kStageBytes, cur ^= 1) {
+    const size_t cnt = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+    if (busy[cur]) SPB_CUDA(ctx, cudaEventSynchronize(ev[cur]));          // the DMA that last used this buffer has drained it
+    if (fread(buf[cur], 1, cnt, f) != cnt) return set_error(ctx, SPB_ERR_ARG, "%s: file is truncated", what);
+    SPB_CUDA(ctx, cudaMemcpyAsync((char*)d_dst + off, buf[cur], cnt, cudaMemcpyHostToDevice, d.stream));
+    SPB_CUDA(ctx, cudaEventRecord(ev[cur], d.stream));
+    busy[cur] = true;
+  }
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return 0;
+}
+int stream_device_to_file(spb_ctx* ctx, DeviceState& d, FILE* f, const void* d_src, size_t bytes, const char* what) {
+  char* buf[2]; cudaEvent_t ev[2];
+  SPB_TRY(stage_buffers(ctx, d, &buf[0], &buf[1], &ev[0], &ev[1]));
+  size_t pending_cnt[2] = {0, 0};
+  int cur = 0;
+  for (size_t off = 0; off < bytes || pending_cnt[0] || pending_cnt[1]; cur ^= 1) {
+    if (pending_cnt[cur]) {                                               // drain the buffer whose D2H was issued two steps ago
+      SPB_CUDA(ctx, cudaEventSynchronize(ev[cur]));
+      if (fwrite(buf[cur], 1, pending_cnt[cur], f) != pending_cnt[cur]) return set_error(ctx, SPB_ERR_ARG, "%s: short write", what);
+      pending_cnt[cur] = 0;
+    }
+    if (off < bytes) {
+      const size_t cnt = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+      SPB_CUDA(ctx, cudaMemcpyAsync(buf[cur], (const char*)d_src + off, cnt, cudaMemcpyDeviceToHost, d.stream));
+      SPB_CUDA(ctx, cudaEventRecord(ev[cur], d.stream));
+      pending_cnt[cur] = cnt; off += cnt;
+    }
+  }
+  return 0;
 }
 
 }  // namespace spb
@@ -153,6 +207,7 @@ void spb_shutdown(spb_ctx* ctx) {
     for (auto& kv : d.slots) if (kv.second.ptr) cudaFree(kv.second.ptr);
     for (auto& t : d.ntt_tables) { cudaFree(t.tw_lo); cudaFree(t.tw_hi); if (t.tw_full) cudaFree(t.tw_full); }
     if (d.pinned) cudaFreeHost(d.pinned);
+    for (int i = 0; i < 2; i++) { if (d.stage[i]) cudaFreeHost(d.stage[i]); if (d.stage_done[i]) cudaEventDestroy(d.stage_done[i]); }
     cudaEventDestroy(d.ev0); cudaEventDestroy(d.ev1); cudaEventDestroy(d.dep_ev);
     for (int e = 0; e < 8; e++) cudaEventDestroy(d.stage_ev[e]);
     cudaStreamDestroy(d.stream);
@@ -167,6 +222,30 @@ float spb_last_device_ms(spb_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.f;
 void* spb_stream(spb_ctx* ctx, int dev_index) {
   if (!ctx || dev_index < 0 || (size_t)dev_index >= ctx->dev.size()) return nullptr;
   return (void*)ctx->dev[dev_index].stream;
+}
+
+// ---- file <-> device (params / proving-key files: SURVEY.md 8f rank 4) -----------------------------------------------------
+int spb_read_file_dev(spb_ctx* ctx, const char* path, uint64_t offset, void* d_dst, size_t bytes) {
+  if (!ctx || !path || (bytes && !d_dst)) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  FILE* f = fopen(path, "rb");
+  if (!f) return set_error(ctx, SPB_ERR_ARG, "spb_read_file_dev: cannot open %s", path);
+  int rc = fseeko(f, (off_t)offset, SEEK_SET) == 0 ? stream_file_to_device(ctx, d, f, d_dst, bytes, "spb_read_file_dev") : set_error(ctx, SPB_ERR_ARG, "spb_read_file_dev: seek failed");
+  fclose(f);
+  return rc;
+}
+int spb_write_file_dev(spb_ctx* ctx, const char* path, int append, const void* d_src, size_t bytes) {
+  if (!ctx || !path || (bytes && !d_src)) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  FILE* f = fopen(path, append ? "ab" : "wb");
+  if (!f) return set_error(ctx, SPB_ERR_ARG, "spb_write_file_dev: cannot open %s", path);
+  int rc = stream_device_to_file(ctx, d, f, d_src, bytes, "spb_write_file_dev");
+  if (fclose(f) != 0 && rc == 0) rc = set_error(ctx, SPB_ERR_ARG, "spb_write_file_dev: close failed");
+  return rc;
 }
 
 int spb_host_register(spb_ctx* ctx, void* ptr, size_t bytes) {

@@ -38,6 +38,8 @@ struct DeviceState {
   std::vector<NttTables> ntt_tables;
   void* pinned = nullptr;  // small pinned staging area for results
   size_t pinned_cap = 0;
+  void* stage[2] = {nullptr, nullptr};              // two pinned 16 MiB buffers for file <-> device streaming (lazily allocated)
+  cudaEvent_t stage_done[2] = {nullptr, nullptr};
 };
 
 }  // namespace spb
@@ -71,6 +73,10 @@ void* slot(spb_ctx* ctx, DeviceState& d, const char* name, size_t bytes);
     int rc_ = (expr);            \
     if (rc_ != 0) return rc_;    \
   } while (0)
+
+// ---- capi.cu: file <-> device streaming through two pinned staging buffers (read of chunk i+1 overlaps the DMA of chunk i) ----
+int stream_file_to_device(spb_ctx* ctx, DeviceState& d, FILE* f, void* d_dst, size_t bytes, const char* what);
+int stream_device_to_file(spb_ctx* ctx, DeviceState& d, FILE* f, const void* d_src, size_t bytes, const char* what);
 
 // ---- msm.cu ----
 void msm_release_ctx(spb_ctx* ctx);

@@ -5,17 +5,119 @@
 //   permuted_input  = the input values sorted by canonical integer (halo2curves' Ord for Fr),
 //   permuted_table  = at the first row of each distinct input value that value; the remaining table elements
 //                     (ascending) handed to the repeated rows from the LAST repeated row backwards.
-// Built from data-parallel primitives: Montgomery -> canonical, LSD radix sort over the four 64-bit limbs
-// (cub::DeviceRadixSort::SortPairs carrying row indices; four stable passes), adjacent-difference flags, a binary
-// search of every distinct input value in the sorted table, two exclusive scans and a scatter.
+// Built from data-parallel primitives: Montgomery -> canonical, a stable LSD radix sort over the four 64-bit limbs carrying row
+// indices (this file's own counting-sort passes; only the exclusive scans are cub::DeviceScan), adjacent-difference flags, a
+// binary search of every distinct input value in the sorted table, two exclusive scans and a scatter.
 // Algorithmic bytes: 4 x 32 B per row (two columns in, two out).
 #include "common.cuh"
 #include "ntt.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <string.h>
 
 using namespace spb;
+
+// ---- stable LSD radix sort of (64-bit key, 32-bit row index) pairs: the sort that IS permute_expression_pair -------------
+// Eight 8-bit digits per limb. One histogram kernel counts all eight digit positions at once; a digit on which every key
+// agrees (range-check columns are < 2^20: five of their eight bytes, and three whole limbs, are zero) is skipped without a
+// pass. A pass is a counting sort: per-tile digit histograms, one exclusive scan over (digit, tile), and a scatter that
+// ranks keys inside a tile in their original order (warp match + per-warp digit counters), which is what makes it stable.
+namespace {
+const int kRsThreads = 256, kRsItems = 8, kRsTile = kRsThreads * kRsItems;   // keys per tile
+
+__global__ void __launch_bounds__(kRsThreads) rs_hist_all_kernel(const unsigned long long* keys, uint64_t n, uint32_t* hist /* 8 x 256 */) {
+  __shared__ uint32_t sh[8 * 256];
+  for (int i = threadIdx.x; i < 8 * 256; i += kRsThreads) sh[i] = 0;
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)kRsThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kRsThreads) {
+    const unsigned long long k = keys[i];
+#pragma unroll
+    for (int d = 0; d < 8; d++) atomicAdd(&sh[d * 256 + (uint32_t)((k >> (8 * d)) & 0xff)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 256; i += kRsThreads) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// tile_hist[digit * ntiles + tile] = keys of that tile with that digit
+__global__ void __launch_bounds__(kRsThreads) rs_tile_hist_kernel(const unsigned long long* keys, uint64_t n, uint32_t shift, uint32_t ntiles, uint32_t* tile_hist) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * kRsTile;
+#pragma unroll
+  for (int r = 0; r < kRsItems; r++) {
+    const uint64_t i = base + (uint64_t)r * kRsThreads + threadIdx.x;
+    if (i < n) atomicAdd(&sh[(uint32_t)((keys[i] >> shift) & 0xff)], 1u);
+  }
+  __syncthreads();
+  tile_hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = sh[threadIdx.x];
+}
+// offsets = exclusive scan of tile_hist; keys of one tile are taken in rounds of 256 (round-major = original order)
+__global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const unsigned long long* keys_in, const uint32_t* idx_in, unsigned long long* keys_out, uint32_t* idx_out,
+                                                                uint64_t n, uint32_t shift, uint32_t ntiles, const uint32_t* offsets) {
+  __shared__ uint32_t digit_base[256];          // next free output slot of each digit for this tile
+  __shared__ uint32_t warp_count[8][256];       // this round: keys of each digit per warp -> exclusive prefix over the warps
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  digit_base[threadIdx.x] = offsets[(uint64_t)threadIdx.x * ntiles + blockIdx.x];
+  const uint64_t base = (uint64_t)blockIdx.x * kRsTile;
+  for (int r = 0; r < kRsItems; r++) {
+    for (int w = 0; w < 8; w++) warp_count[w][threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t i = base + (uint64_t)r * kRsThreads + threadIdx.x;
+    const bool live = i < n;
+    unsigned long long k = 0; uint32_t v = 0, dgt = 0, rank = 0;
+    if (live) { k = keys_in[i]; v = idx_in[i]; dgt = (uint32_t)((k >> shift) & 0xff); }
+    const unsigned livemask = __ballot_sync(0xffffffffu, live);
+    if (live) {
+      const unsigned peers = __match_any_sync(livemask, dgt);
+      rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      if (rank == 0) warp_count[warp][dgt] = (uint32_t)__popc(peers);
+    }
+    __syncthreads();
+    {   // thread d: exclusive prefix of digit d's counts over the 8 warps, then advance the digit's base by the round total
+      uint32_t run = 0;
+      for (int w = 0; w < 8; w++) { const uint32_t c = warp_count[w][threadIdx.x]; warp_count[w][threadIdx.x] = run; run += c; }
+      const uint32_t b = digit_base[threadIdx.x];
+      __syncthreads();
+      if (live) { const uint32_t pos = digit_base[dgt] + warp_count[warp][dgt] + rank; keys_out[pos] = k; idx_out[pos] = v; }
+      __syncthreads();
+      digit_base[threadIdx.x] = b + run;
+    }
+    __syncthreads();
+  }
+}
+
+// sorts (keys_a, idx_a) by key, ascending, stable; the result ends up back in keys_a / idx_a. `hist` (8 x 256 u32) and `tile_hist`
+// (256 x ntiles + 1 u32, plus the scan's temp) are device scratch. One 8 KB D2H of the digit histograms per call.
+int radix_sort_pairs_u64(spb_ctx* ctx, DeviceState& d, unsigned long long* keys_a, unsigned long long* keys_b, uint32_t* idx_a, uint32_t* idx_b, uint64_t n,
+                         uint32_t* hist, uint32_t* tile_hist, void* scan_tmp, size_t scan_bytes) {
+  const uint32_t ntiles = (uint32_t)((n + kRsTile - 1) / kRsTile);
+  SPB_CUDA(ctx, cudaMemsetAsync(hist, 0, 8 * 256 * 4, d.stream));
+  unsigned hb = ntiles < (unsigned)d.sm_count * 4 ? ntiles : (unsigned)d.sm_count * 4;
+  rs_hist_all_kernel<<<hb ? hb : 1, kRsThreads, 0, d.stream>>>(keys_a, n, hist);
+  uint32_t h[8 * 256];
+  SPB_CUDA(ctx, cudaMemcpyAsync(h, hist, sizeof h, cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  ctx->n_kernel_launches++;
+  int passes = 0;
+  for (int dg = 0; dg < 8; dg++) {
+    bool trivial = false;
+    for (int b = 0; b < 256; b++) if (h[dg * 256 + b] == n) trivial = true;
+    if (trivial) continue;
+    rs_tile_hist_kernel<<<ntiles, kRsThreads, 0, d.stream>>>(keys_a, n, 8 * dg, ntiles, tile_hist);
+    SPB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, tile_hist, tile_hist, (int)(256 * ntiles), d.stream));
+    rs_scatter_kernel<<<ntiles, kRsThreads, 0, d.stream>>>(keys_a, idx_a, keys_b, idx_b, n, 8 * dg, ntiles, tile_hist);
+    SPB_CUDA(ctx, cudaGetLastError());
+    ctx->n_kernel_launches += 2;
+    unsigned long long* tk = keys_a; keys_a = keys_b; keys_b = tk;
+    uint32_t* ti = idx_a; idx_a = idx_b; idx_b = ti;
+    passes++;
+  }
+  if (passes & 1) {   // an odd number of passes left the result in the caller's b buffers
+    SPB_CUDA(ctx, cudaMemcpyAsync(keys_b, keys_a, n * 8, cudaMemcpyDeviceToDevice, d.stream));
+    SPB_CUDA(ctx, cudaMemcpyAsync(idx_b, idx_a, n * 4, cudaMemcpyDeviceToDevice, d.stream));
+  }
+  return 0;
+}
+}  // namespace
 
 __global__ void lk_canon_kernel(const Fr* in, Fr* out, uint32_t* idx, uint64_t n) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -77,14 +179,13 @@ inline unsigned nb(uint64_t n) { return (unsigned)((n + 255) / 256); }
 
 // sorted[i] = canonical values of src in ascending order (idx/keys/scratch are n-sized work arrays)
 int sort_canonical(spb_ctx* ctx, DeviceState& d, const Fr* src, Fr* canon, Fr* sorted, uint32_t* idx_a, uint32_t* idx_b, unsigned long long* keys_a,
-                   unsigned long long* keys_b, void* tmp, size_t tmp_bytes, uint64_t n) {
+                   unsigned long long* keys_b, uint32_t* hist, uint32_t* tile_hist, void* tmp, size_t tmp_bytes, uint64_t n) {
   lk_canon_kernel<<<nb(n), 256, 0, d.stream>>>(src, canon, idx_a, n);
   for (uint32_t limb = 0; limb < 4; limb++) {
     lk_gather_limb_kernel<<<nb(n), 256, 0, d.stream>>>(canon, idx_a, limb, keys_a, n);
-    SPB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, idx_a, idx_b, (int)n, 0, 64, d.stream));
-    uint32_t* t = idx_a; idx_a = idx_b; idx_b = t;
+    SPB_TRY(radix_sort_pairs_u64(ctx, d, keys_a, keys_b, idx_a, idx_b, n, hist, tile_hist, tmp, tmp_bytes));   // result back in keys_a / idx_a
   }
-  lk_gather_kernel<<<nb(n), 256, 0, d.stream>>>(canon, idx_a, sorted, n);   // after four swaps idx_a is the caller's idx_a again
+  lk_gather_kernel<<<nb(n), 256, 0, d.stream>>>(canon, idx_a, sorted, n);
   ctx->n_kernel_launches += 6;
   return 0;
 }
@@ -109,16 +210,19 @@ int spb_permute_expression_pair_dev(spb_ctx* ctx, const spb_fr* d_input, const s
   unsigned long long* keys_b = (unsigned long long*)slot(ctx, d, "lk_keys_b", n * 8);
   uint32_t* flags = (uint32_t*)slot(ctx, d, "lk_flags", (4 * n + 8) * 4);   // repeated_flag | rep_rank | used->left_flag | left_rank
   int* err = (int*)slot(ctx, d, "lk_err", 16);
-  size_t sort_bytes = 0, scan_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_a, keys_b, idx_a, idx_b, (int)n, 0, 64, d.stream);
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags, flags, (int)n + 1, d.stream);
-  size_t tmp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+  const uint32_t ntiles = (uint32_t)((n + kRsTile - 1) / kRsTile);
+  uint32_t* rs_hist = (uint32_t*)slot(ctx, d, "lk_rs_hist", 8 * 256 * 4);
+  uint32_t* rs_tile = (uint32_t*)slot(ctx, d, "lk_rs_tile", ((size_t)256 * ntiles + 1) * 4);
+  size_t scan_a = 0, scan_b = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_a, flags, flags, (int)n + 1, d.stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_b, rs_tile, rs_tile, (int)(256 * ntiles), d.stream);
+  size_t tmp_bytes = scan_a > scan_b ? scan_a : scan_b;
   void* tmp = slot(ctx, d, "lk_tmp", tmp_bytes ? tmp_bytes : 16);
-  if (!canon || !sin || !stb || !idx_a || !idx_b || !keys_a || !keys_b || !flags || !err || !tmp) return SPB_ERR_OOM;
+  if (!canon || !sin || !stb || !idx_a || !idx_b || !keys_a || !keys_b || !flags || !err || !tmp || !rs_hist || !rs_tile) return SPB_ERR_OOM;
   uint32_t* repeated_flag = flags, *rep_rank = flags + (n + 1), *used = flags + 2 * (n + 1), *left_rank = flags + 3 * (n + 1);
 
-  SPB_TRY(sort_canonical(ctx, d, (const Fr*)d_input, canon, sin, idx_a, idx_b, keys_a, keys_b, tmp, tmp_bytes, n));
-  SPB_TRY(sort_canonical(ctx, d, (const Fr*)d_table, canon, stb, idx_a, idx_b, keys_a, keys_b, tmp, tmp_bytes, n));
+  SPB_TRY(sort_canonical(ctx, d, (const Fr*)d_input, canon, sin, idx_a, idx_b, keys_a, keys_b, rs_hist, rs_tile, tmp, tmp_bytes, n));
+  SPB_TRY(sort_canonical(ctx, d, (const Fr*)d_table, canon, stb, idx_a, idx_b, keys_a, keys_b, rs_hist, rs_tile, tmp, tmp_bytes, n));
   SPB_CUDA(ctx, cudaMemsetAsync(flags, 0, (4 * n + 8) * 4, d.stream));
   SPB_CUDA(ctx, cudaMemsetAsync(err, 0, 4, d.stream));
   lk_match_kernel<<<nb(n), 256, 0, d.stream>>>(sin, stb, n, repeated_flag, used, err);

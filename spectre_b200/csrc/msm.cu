@@ -399,8 +399,8 @@ int spb_srs_downsize(spb_ctx* ctx, const spb_srs* srs, uint32_t k, spb_srs** out
 
 // ParamsKZG::read / write in SerdeFormat::RawBytes: k (u32 LE) | g[n] | g_lagrange[n] | g2 | s_g2, every coordinate as
 // its in-memory Montgomery limbs -- the file halo2-base's gen_srs caches as params/kzg_bn254_{k}.srs
-// ([UPSTREAM] halo2_proofs/src/poly/kzg/commitment.rs; reference .gitignore:36 `params/`). Streamed through a pinned
-// staging buffer straight into device memory (K = 24: 4 GiB).
+// ([UPSTREAM] halo2_proofs/src/poly/kzg/commitment.rs; reference .gitignore:36 `params/`). Streamed through two pinned
+// staging buffers straight into device memory, file read and DMA overlapped (K = 24: 4 GiB).
 int spb_srs_read_file(spb_ctx* ctx, const char* path, spb_srs** out) {
   if (!ctx || !path || !out) return SPB_ERR_ARG;
   FILE* f = fopen(path, "rb");
@@ -412,25 +412,17 @@ int spb_srs_read_file(spb_ctx* ctx, const char* path, spb_srs** out) {
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     s = srs_alloc(ctx, k);
-    const size_t chunk_pts = (size_t)1 << 18;  // 16 MiB staging
-    G1Affine* stage = nullptr;
-    if (cudaMallocHost(&stage, chunk_pts * sizeof(G1Affine)) != cudaSuccess) { fclose(f); delete s; return set_error(ctx, SPB_ERR_OOM, "spb_srs_read_file: pinned staging"); }
     for (int which = 0; which < 2 && rc == 0; which++) {
       for (auto& sh : s->shards) {
         DeviceState& d = ctx->dev[sh.dev_index];
         cudaSetDevice(d.device);
         G1Affine** dst = which == 0 ? &sh.g : &sh.g_lagrange;
         if (sh.count && cudaMalloc(dst, sh.count * sizeof(G1Affine)) != cudaSuccess) { rc = set_error(ctx, SPB_ERR_OOM, "spb_srs_read_file: cudaMalloc"); break; }
-        for (size_t off = 0; off < sh.count && rc == 0; off += chunk_pts) {
-          size_t cnt = sh.count - off < chunk_pts ? sh.count - off : chunk_pts;
-          if (fread(stage, sizeof(G1Affine), cnt, f) != cnt) { rc = set_error(ctx, SPB_ERR_ARG, "spb_srs_read_file: %s is truncated", path); break; }
-          if (cudaMemcpy(*dst + off, stage, cnt * sizeof(G1Affine), cudaMemcpyHostToDevice) != cudaSuccess) rc = set_error(ctx, SPB_ERR_CUDA, "spb_srs_read_file: H2D copy");
-        }
+        if (sh.count) rc = stream_file_to_device(ctx, d, f, *dst, sh.count * sizeof(G1Affine), "spb_srs_read_file");
         if (rc) break;
       }
     }
     if (rc == 0 && (fread(s->g2, 128, 1, f) != 1 || fread(s->s_g2, 128, 1, f) != 1)) rc = set_error(ctx, SPB_ERR_ARG, "spb_srs_read_file: %s has no G2 trailer", path);
-    cudaFreeHost(stage);
   }
   fclose(f);
   if (rc) { spb_srs_free(ctx, s); return rc; }
@@ -447,18 +439,14 @@ int spb_srs_write_file(spb_ctx* ctx, const spb_srs* srs, const char* path) {
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     fwrite(&srs->k, 4, 1, f);
-    const size_t chunk_pts = (size_t)1 << 18;
-    std::vector<G1Affine> stage(chunk_pts);
     for (int which = 0; which < 2 && rc == 0; which++)
       for (auto& sh : srs->shards) {
         const G1Affine* src = which == 0 ? sh.g : sh.g_lagrange;
         if (!src && sh.count) { rc = set_error(ctx, SPB_ERR_STATE, "spb_srs_write_file: basis %d not resident", which); break; }
-        cudaSetDevice(ctx->dev[sh.dev_index].device);
-        for (size_t off = 0; off < sh.count && rc == 0; off += chunk_pts) {
-          size_t cnt = sh.count - off < chunk_pts ? sh.count - off : chunk_pts;
-          if (cudaMemcpy(stage.data(), src + off, cnt * sizeof(G1Affine), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = set_error(ctx, SPB_ERR_CUDA, "spb_srs_write_file: D2H copy"); break; }
-          if (fwrite(stage.data(), sizeof(G1Affine), cnt, f) != cnt) rc = set_error(ctx, SPB_ERR_ARG, "spb_srs_write_file: short write");
-        }
+        DeviceState& d = ctx->dev[sh.dev_index];
+        cudaSetDevice(d.device);
+        if (sh.count) rc = stream_device_to_file(ctx, d, f, src, sh.count * sizeof(G1Affine), "spb_srs_write_file");
+        if (rc) break;
       }
     if (rc == 0) { fwrite(srs->g2, 128, 1, f); fwrite(srs->s_g2, 128, 1, f); }
   }

@@ -314,6 +314,13 @@ class Backend:
         self.check(self.lib.spb_permute_expression_pair_dev(self.ctx, _p(d_input), _p(d_table), ctypes.c_size_t(usable), _p(d_permuted_input),
                                                             _p(d_permuted_table)), "spb_permute_expression_pair_dev")
 
+    # ---- file <-> device streaming (params / proving-key files) -------------------------------------------
+    def read_file_dev(self, path, offset, d_dst, nbytes):
+        self.check(self.lib.spb_read_file_dev(self.ctx, path.encode(), ctypes.c_uint64(offset), _p(d_dst), ctypes.c_size_t(nbytes)), "spb_read_file_dev")
+
+    def write_file_dev(self, path, d_src, nbytes, append=True):
+        self.check(self.lib.spb_write_file_dev(self.ctx, path.encode(), ctypes.c_int(1 if append else 0), _p(d_src), ctypes.c_size_t(nbytes)), "spb_write_file_dev")
+
     # ---- utilities -------------------------------------------------------------------------------------
     def g1_fixed_base_mul(self, scalars):
         scalars = _fr_array(scalars)

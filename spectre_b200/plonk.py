@@ -251,6 +251,12 @@ class DeviceEngine:
         with self.torch.cuda.stream(self.stream):
             return uniform_residues(self.torch, rows, self.dev, generator)
     def sync(self): self.stream.synchronize()
+    # proving-key file: polynomials go file <-> HBM through the library's double-buffered pinned staging, never through numpy
+    def append_to_file(self, path, b, rows): self.be.write_file_dev(path, b.data_ptr(), rows * 32, append=True)
+    def read_from_file(self, path, offset, rows):
+        out = self.alloc_uninit(rows)
+        self.be.read_file_dev(path, offset, out.data_ptr(), rows * 32)
+        return out
 
     # commitments -> affine integer pairs
     def commit(self, basis, bufs, n):
@@ -409,6 +415,99 @@ def default_vk_digest(pk):
     for x, y in pk.fixed_commitments + pk.sigma_commitments:
         data += x.to_bytes(32, "big") + y.to_bytes(32, "big")
     return int.from_bytes(keccak256(bytes(data)), "big") % R_MOD
+
+
+# ---- ProvingKey::write / ::read (SerdeFormat::RawBytesUnchecked) ------------------------------------------------------------
+# Layout of [UPSTREAM] halo2_proofs/src/plonk.rs `ProvingKey::write` as Spectre stores it (`*.pkey`, read at start-up by
+# ProverState::new, prover/src/prover.rs:44-116, through lightclient-circuits/src/util/circuit.rs:104-115,273-280):
+#   VerifyingKey:  k (u32 BE) | #fixed commitments (u32 BE) | fixed commitments | permutation commitments | selectors
+#                  (none here: the shapes of this repo keep selectors as fixed columns, compress_selectors = false)
+#   l0 | l_last | l_active                          each a Polynomial: len (u32 BE) | values
+#   fixed_values | fixed_polys | fixed_cosets        each a slice: count (u32 BE) | Polynomial...
+#   permutation::ProvingKey: permutations | polys | cosets    (three slices)
+# Field elements and curve coordinates are their in-memory Montgomery limbs (RawBytes). The constraint system is not in the
+# file: like upstream's `ProvingKey::read::<_, ConcreteCircuit>(reader, format, params)` the reader gets it from the circuit.
+# This restates the upstream layout from memory (no Rust toolchain here to diff a real .pkey against it): files written and
+# read by this repo round-trip, byte compatibility with upstream's files is unverified.
+_FQ_MONT = (1 << 256) % P_MOD
+
+
+def _point_bytes(pt):
+    x, y = pt
+    return b"".join(((v * _FQ_MONT) % P_MOD).to_bytes(32, "little") for v in (x, y))
+
+
+def _point_from(raw):
+    inv = pow(_FQ_MONT, -1, P_MOD)
+    return tuple(int.from_bytes(raw[i:i + 32], "little") * inv % P_MOD for i in (0, 32))
+
+
+def write_pk(E, pk, path):
+    """ProvingKey::write(writer, SerdeFormat::RawBytesUnchecked): header and commitments from the host, every polynomial
+    streamed from device memory by the engine."""
+    with open(path, "wb") as f:
+        f.write(pk.k.to_bytes(4, "big") + len(pk.fixed_commitments).to_bytes(4, "big"))
+        for pt in pk.fixed_commitments + pk.sigma_commitments:
+            f.write(_point_bytes(pt))
+
+    def poly(b, rows):
+        with open(path, "ab") as f:
+            f.write(rows.to_bytes(4, "big"))
+        E.append_to_file(path, b, rows)
+
+    def polys(bufs, rows):
+        with open(path, "ab") as f:
+            f.write(len(bufs).to_bytes(4, "big"))
+        for b in bufs:
+            poly(b, rows)
+    ext = 1 << E.extended_k
+    for b in (pk.l0, pk.l_last, pk.l_active):
+        poly(b, ext)
+    polys(pk.fixed_values, pk.n); polys(pk.fixed_polys, pk.n); polys(pk.fixed_cosets, ext)
+    polys(pk.sigma_values, pk.n); polys(pk.sigma_polys, pk.n); polys(pk.sigma_cosets, ext)
+
+
+def read_pk(E, cs, path, vk_digest=None):
+    """ProvingKey::read: the inverse of write_pk; `cs` plays the role of the concrete circuit's configure()."""
+    pk = ProvingKey()
+    with open(path, "rb") as f:
+        head = f.read(8)
+        k, n_fixed = int.from_bytes(head[:4], "big"), int.from_bytes(head[4:], "big")
+        if k != E.k or n_fixed != cs.num_fixed:
+            raise ValueError("read_pk: %s is for k = %d with %d fixed columns, expected k = %d with %d" % (path, k, n_fixed, E.k, cs.num_fixed))
+        pts = [_point_from(f.read(64)) for _ in range(n_fixed + len(cs.permutation))]
+        pos = [f.tell()]
+        size = f.seek(0, 2)
+    n, ext = 1 << k, 1 << E.extended_k
+    pk.cs, pk.k, pk.n = cs, k, n
+    pk.blinding_factors = cs.blinding_factors(); pk.usable_rows = n - (pk.blinding_factors + 1)
+    pk.fixed_commitments, pk.sigma_commitments = pts[:n_fixed], pts[n_fixed:]
+
+    def u32():
+        with open(path, "rb") as f:
+            f.seek(pos[0]); v = int.from_bytes(f.read(4), "big")
+        pos[0] += 4
+        return v
+
+    def poly(rows):
+        if u32() != rows:
+            raise ValueError("read_pk: polynomial length mismatch in %s" % path)
+        b = E.read_from_file(path, pos[0], rows)
+        pos[0] += rows * 32
+        return b
+
+    def polys(count, rows):
+        if u32() != count:
+            raise ValueError("read_pk: slice length mismatch in %s" % path)
+        return [poly(rows) for _ in range(count)]
+    pk.l0, pk.l_last, pk.l_active = poly(ext), poly(ext), poly(ext)
+    pk.fixed_values, pk.fixed_polys, pk.fixed_cosets = polys(n_fixed, n), polys(n_fixed, n), polys(n_fixed, ext)
+    m = len(cs.permutation)
+    pk.sigma_values, pk.sigma_polys, pk.sigma_cosets = polys(m, n), polys(m, n), polys(m, ext)
+    if pos[0] != size:
+        raise ValueError("read_pk: %d trailing bytes in %s" % (size - pos[0], path))
+    pk.vk_digest = vk_digest if vk_digest is not None else default_vk_digest(pk)
+    return pk
 
 
 # ---- multi-open bookkeeping ---------------------------------------------------------------------------------------

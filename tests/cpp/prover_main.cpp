@@ -123,6 +123,11 @@ int main(int argc, char** argv) {
       for (auto* v : {&pk.fixed_commitments, &pk.sigma_commitments}) for (auto& p : *v) { uint8_t b[64]; hostfield::to_be(p.x, b); hostfield::to_be(p.y, b + 32); for (int i = 0; i < 64; i++) { char h[3]; std::snprintf(h, 3, "%02x", b[i]); vk << h; } vk << "\n"; }
       std::printf("proof %zu bytes, rng calls %zu/%zu\n", proof.size(), call, rng_counts.size());
     }
+#ifdef SPB_PROVER_WITH_CUDART
+    mem.trim();          // return the cached device blocks while the context (and its stream) still exist
+    spb_host_unregister(ctx, fixed_raw.data()); spb_host_unregister(ctx, advice_raw.data());
+    if (!rng_raw.empty()) spb_host_unregister(ctx, rng_raw.data());
+#endif
     spb_srs_free(ctx, srs);
     spb_shutdown(ctx);
     return 0;

@@ -34,6 +34,11 @@ class OracleEngine:
         b.a[start:start + rows.shape[0]] = rows
     def read_rows(self, b, start, count): return b.a[start:start + count].copy()
     def sync(self): pass
+    def append_to_file(self, path, b, rows):
+        with open(path, "ab") as f:
+            f.write(np.ascontiguousarray(b.a[:rows], dtype=np.uint64).tobytes())
+    def read_from_file(self, path, offset, rows):
+        return Buf(np.fromfile(path, dtype=np.uint64, count=rows * 4, offset=offset).reshape(rows, 4).copy())
 
     def commit(self, basis, bufs, n):
         if basis == halo2.BASIS_G:

@@ -274,3 +274,33 @@ def test_lookup_violation_is_reported_like_upstream(be, orc):
     pk = plonk.keygen(E, cs, k, fixed, copies)
     with pytest.raises(BackendError):
         plonk.create_proof(E, pk, [instances], [adv], SeededRng(2), EvmTranscriptWrite(pk.vk_digest))
+
+
+def test_proving_key_file_streams_between_disk_and_hbm(be, orc, tmp_path):
+    """*.pkey through spb_write_file_dev / spb_read_file_dev (double-buffered pinned staging): the file the device writes is
+    byte-identical to the one the CPU oracle engine writes for the same key, and the key read back into HBM proves to the
+    same bytes. Also ParamsKZG::write / ::read through the same streamer."""
+    from spectre_b200 import circuits, plonk
+    from spectre_b200.halo2 import ParamsKZG
+    from spectre_b200.transcript import EvmTranscriptWrite
+    from tests.plonk_oracle_engine import OracleEngine, SeededRng
+    k, instances = 9, [3, 1, 4]
+    cs = circuits.halo2lib_shape(3, 2)
+    fixed, adv, copies = circuits.halo2lib_witness(cs, k, instances, lookup_bits=4, groups=40, num_gate_advice=3, num_lookup_advice=2)
+    params = ParamsKZG.setup(be, k, orc.srs_tau())
+    E = plonk.DeviceEngine(be, params, k, cs.degree())
+    pk = plonk.keygen(E, cs, k, fixed, copies)
+    dev_path, cpu_path = str(tmp_path / "dev.pkey"), str(tmp_path / "cpu.pkey")
+    plonk.write_pk(E, pk, dev_path)
+    Ec = OracleEngine(k, cs.degree())
+    plonk.write_pk(Ec, plonk.keygen(Ec, cs, k, fixed, copies), cpu_path)
+    with open(dev_path, "rb") as f1, open(cpu_path, "rb") as f2:
+        assert f1.read() == f2.read()
+    pk2 = plonk.read_pk(E, cs, cpu_path)
+    proofs = [plonk.create_proof(E, key, [instances], adv, SeededRng(4), EvmTranscriptWrite(key.vk_digest)) for key in (pk, pk2)]
+    assert proofs[0] == proofs[1]
+    # params file round trip through the same streamer
+    ppath = str(tmp_path / "kzg_bn254_%d.srs" % k)
+    params.write(ppath)
+    back = ParamsKZG.read(be, ppath)
+    assert np.array_equal(back.get_g(), params.get_g()) and np.array_equal(back.get_g(basis=1), params.get_g(basis=1))

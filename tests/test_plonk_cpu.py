@@ -254,3 +254,25 @@ def test_create_proof_argument_errors(orc):
         plonk.create_proof(E, pk, [list(range(1 << k))], [adv], SeededRng(1), new_t())
     with pytest.raises(ValueError, match="advice columns"):
         plonk.create_proof(E, pk, [[1]], [adv, adv], SeededRng(1), new_t())
+
+
+def test_proving_key_file_round_trip(orc, tmp_path):
+    """ProvingKey::write / ::read in upstream's RawBytesUnchecked layout (spectre_b200/plonk.py write_pk / read_pk): the key
+    read back proves to the same bytes as the key it was written from, and a file for another shape is refused."""
+    k, instances = 7, [3, 1, 4]
+    cs = plonk_circuits.halo2lib_shape(3, 2)
+    fixed, adv, copies = plonk_circuits.halo2lib_witness(cs, k, instances, lookup_bits=4, groups=20, num_gate_advice=3, num_lookup_advice=2)
+    E = OracleEngine(k, cs.degree())
+    pk = plonk.keygen(E, cs, k, fixed, copies)
+    path = str(tmp_path / "shape.pkey")
+    plonk.write_pk(E, pk, path)
+    n, ext = 1 << k, 1 << E.extended_k
+    nf, m = cs.num_fixed, len(cs.permutation)
+    import os
+    assert os.path.getsize(path) == 8 + 64 * (nf + m) + 3 * (4 + 32 * ext) + 6 * 4 + (nf + m) * (2 * (4 + 32 * n) + 4 + 32 * ext)
+    pk2 = plonk.read_pk(E, cs, path)
+    assert (pk2.fixed_commitments, pk2.sigma_commitments, pk2.vk_digest) == (pk.fixed_commitments, pk.sigma_commitments, pk.vk_digest)
+    proofs = [plonk.create_proof(E, key, [instances], adv, SeededRng(4), EvmTranscriptWrite(key.vk_digest)) for key in (pk, pk2)]
+    assert proofs[0] == proofs[1]
+    with pytest.raises(ValueError):
+        plonk.read_pk(E, plonk_circuits.aggregation_shape(), path)
