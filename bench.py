@@ -431,10 +431,15 @@ def main():
     if world > 1 and not args.no_prove:
         cpu_barrier()
         if rank == 0:
+            be_multi = halo2.Backend(list(range(world)))
             try:
-                proof_multi = prove_aggregation(torch, halo2, [be, halo2.Backend(list(range(world)))], args.prove_k)
+                proof_multi = prove_aggregation(torch, halo2, [be, be_multi], args.prove_k)
             except Exception as e:
                 proof_multi = {"error": repr(e)}
+            # every torch tensor that was ever used on be_multi's stream is gone by now (they were locals of prove_aggregation):
+            # only then may the context -- and with it the stream torch recorded those uses on -- be destroyed
+            torch.cuda.synchronize()
+            be_multi.close()
         cpu_barrier()
 
     if rank != 0:
@@ -773,8 +778,6 @@ def prove_aggregation(torch, halo2, backends, k):
         proofs.append(proof)
         del E, pkey, srs
         torch.cuda.empty_cache()
-        if nd > 1:
-            be_.close()
     out["proof_equals_single_gpu"] = bool(proofs[0] == proofs[-1])
     out["speedup"] = out["devices_1"]["create_proof_s"] / out["devices_%d" % len(backends[-1].devices)]["create_proof_s"] if len(backends) > 1 else None
     out["what"] = ("one context over all N devices driven by rank 0: every commitment is an MSM sharded by point range (scalar ranges peer-copied), the quotient kernels "

@@ -194,6 +194,9 @@ int spb_vec_scale(spb_ctx* ctx, spb_fr* a, const spb_fr* alpha, size_t n);      
 /* device-resident variants of the batch ops (pointers on device 0 of the context; scalars / results on the host) */
 int spb_batch_invert_dev(spb_ctx* ctx, spb_fr* d_a, size_t n);
 int spb_eval_polynomial_dev(spb_ctx* ctx, const spb_fr* d_poly, size_t n, const spb_fr* point, spb_fr* out);
+/* out[q] = d_polys[q](points[q]) for `count` queries of n coefficients each in one launch (create_proof's evaluation stage
+ * after squeezing x: every opened polynomial at every queried rotation). d_polys: HOST array of device pointers. */
+int spb_eval_polynomial_many_dev(spb_ctx* ctx, const spb_fr* const* d_polys, size_t n, const spb_fr* points, size_t count, spb_fr* out);
 int spb_kate_division_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, const spb_fr* b, spb_fr* d_q);
 int spb_grand_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* d_z);
 /* row-sharded grand product: each rank takes spb_product_dev of its rows, the 32-byte totals are

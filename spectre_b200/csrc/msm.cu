@@ -38,10 +38,17 @@ static std::map<std::pair<spb_ctx*, int>, std::vector<Lane>> g_lanes;   // proce
 static std::mutex g_lanes_mu;
 static const size_t kLanePinnedBytes = 256 * 1024;  // window partials of one MSM (<= 128 windows x a few points)
 
+static const int kMaxLanes = 4;
+// lanes a batch cycles through: 2 by default (one MSM's latency-bound tail under the next one's accumulation); SPB_MSM_LANES=1..4
+static int lane_count() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("SPB_MSM_LANES"); v = e ? atoi(e) : 2; if (v < 1) v = 1; if (v > kMaxLanes) v = kMaxLanes; }
+  return v;
+}
 static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
   std::lock_guard<std::mutex> lk(g_lanes_mu);
   auto& v = g_lanes[std::make_pair(ctx, dev_index)];
-  if (v.size() < 2) v.resize(2);
+  if (v.size() < (size_t)kMaxLanes) v.resize(kMaxLanes);
   Lane& l = v[lane_index];
   if (!l.ready) {
     SPB_CUDA(ctx, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
@@ -139,13 +146,15 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   cudaEventRecord(ln.ev[3], st);
   msm_accumulate_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g, ent, d_bases, buckets, head_key, head, tail_key, tail);
   cudaEventRecord(ln.ev[4], st);
-  msm_stitch_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g.L, 24, head_key, head, tail_key, tail, buckets, giant, giant + 1);
+  const uint32_t kChainCap = 24;   // pieces summed inline by the group reduction; longer chains take the giant path
+  msm_giant_detect_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, g.L, kChainCap, offsets, giant, giant + 1);
   msm_giant_kernel<<<256, 128, 0, st>>>(total, g.L, giant, giant + 1, head_key, head, tail_key, tail, buckets, huge, huge + 2);
   msm_huge_kernel<<<kHugeBlocks, 128, 0, st>>>(huge, huge + 2, head, huge_part);
-  msm_huge_finish_kernel<<<8, 128, 0, st>>>(huge, huge + 2, kHugeBlocks, huge_part, tail_key, tail, buckets);
+  msm_huge_finish_kernel<<<64, 128, 0, st>>>(huge, huge + 2, kHugeBlocks, huge_part, tail_key, tail, buckets);
   cudaEventRecord(ln.ev[5], st);
   G1Xyzz *rows = seg_out, *cols = seg_out + (uint64_t)g.BW * R, *wrows = seg_out + (uint64_t)g.BW * (R + C);
-  msm_group_kernel<<<(unsigned)((ngroups + 127) / 128), 128, 0, st>>>(ngroups, tl.m_log, offsets, buckets, grp, grp + ngroups);
+  MsmPieces pc; pc.L = g.L; pc.cap = kChainCap; pc.buckets = buckets; pc.head = head; pc.tail = tail;
+  msm_group_kernel<<<(unsigned)((ngroups + 127) / 128), 128, 0, st>>>(ngroups, tl.m_log, offsets, pc, grp, grp + ngroups);
   cudaEventRecord(ln.ev[6], st);
   msm_rowcol_kernel<<<g.BW * (2 * R + C), 64, 0, st>>>(T1, tl, grp, grp + ngroups, rows, cols, wrows);
   msm_weighted_kernel<<<g.BW * (2 * tl.nbr + tl.nbc), 128, 0, st>>>(tl, rows, cols, wrows, win_out);
@@ -529,16 +538,17 @@ static int msm_batch_common(spb_ctx* ctx, const spb_srs* srs, int basis, const s
   if (!ctx || !srs || !out || (count && !scalars)) return SPB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->last_msm_adds = 0;
-  std::vector<MsmPart> jobs[2];
+  const size_t NL = (size_t)lane_count();
+  std::vector<MsmPart> jobs[kMaxLanes];
   for (size_t i = 0; i < count; i++) {
-    int lane = (int)(i & 1);
-    if (i >= 2) SPB_TRY(job_collect(ctx, lane, jobs[lane], &out[i - 2]));  // MSM i-2 ran on this lane
+    int lane = (int)(i % NL);
+    if (i >= NL) SPB_TRY(job_collect(ctx, lane, jobs[lane], &out[i - NL]));  // MSM i-NL ran on this lane
     if (n && !scalars[i]) return SPB_ERR_ARG;
     jobs[lane].clear();
     SPB_TRY(srs_parts(ctx, srs, basis, (const Fr*)scalars[i], on_device, n, jobs[lane]));
     SPB_TRY(job_enqueue(ctx, lane, jobs[lane]));
   }
-  for (size_t i = count >= 2 ? count - 2 : 0; i < count; i++) SPB_TRY(job_collect(ctx, (int)(i & 1), jobs[i & 1], &out[i]));
+  for (size_t i = count >= NL ? count - NL : 0; i < count; i++) SPB_TRY(job_collect(ctx, (int)(i % NL), jobs[i % NL], &out[i]));
   return 0;
 }
 

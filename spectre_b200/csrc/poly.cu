@@ -182,6 +182,28 @@ __global__ void __launch_bounds__(256) eval_strided_kernel(const Fr* poly, uint6
 }
 
 
+// the same for a whole list of (polynomial, point) queries in ONE launch: blockIdx.y = query (create_proof evaluates every
+// opened polynomial at every queried rotation after squeezing x: 153 queries in the sync-step shape)
+__global__ void __launch_bounds__(256) eval_many_kernel(const Fr* const* polys, const Fr* xs /* (x, x^T) per query */, uint64_t n, uint32_t T, Fr* partial) {
+  __shared__ Fr sh[128];
+  const uint32_t q = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  const Fr* poly = polys[q];
+  const Fr x = xs[2 * q], xT = xs[2 * q + 1];
+  Fr acc = fp_zero<FrParams>();
+  if (t < T && t < n) {
+    uint64_t last = t + ((n - 1 - t) / T) * T;
+    for (uint64_t i = last;; i -= T) { acc = fp_add(fp_mul(acc, xT), ntt_ldg(poly + i)); if (i < T) break; }
+    acc = fp_mul(acc, fp_pow_u64(x, t));
+  }
+  for (int stride = 128; stride >= 1; stride >>= 1) {
+    if ((int)threadIdx.x >= stride && (int)threadIdx.x < 2 * stride) sh[threadIdx.x - stride] = acc;
+    __syncthreads();
+    if ((int)threadIdx.x < stride) acc = fp_add(acc, sh[threadIdx.x]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(uint64_t)q * gridDim.x + blockIdx.x] = acc;
+}
+
 // out[i] = sum_p y^p * polys[p][i]  evaluated as Horner over p from the last polynomial down (the "fold with powers
 // of y" that evaluate_h, vanishing::evaluate and the SHPLONK opener all do): reads each polynomial once.
 __global__ void lincomb_kernel(const Fr* const* polys, uint32_t count, Fr y, Fr* out, uint64_t n) {
@@ -444,6 +466,35 @@ int spb_eval_polynomial_dev(spb_ctx* ctx, const spb_fr* d_poly, size_t n, const 
     SPB_TRY(dev_eval_polynomial(ctx, d, (const Fr*)d_poly, n, x, &acc));
   }
   memcpy(out, &acc, 32);
+  return 0;
+}
+int spb_eval_polynomial_many_dev(spb_ctx* ctx, const spb_fr* const* d_polys, size_t n, const spb_fr* points, size_t count, spb_fr* out) {
+  if (!ctx || (count && (!d_polys || !points || !out)) || !n) return SPB_ERR_ARG;
+  if (!count) return 0;
+  if (count > 65535) return set_error(ctx, SPB_ERR_ARG, "spb_eval_polynomial_many_dev: more than 65535 queries");
+  SPB_ENTER(ctx);
+  uint32_t T = 256;
+  while (T < 16384 && (uint64_t)T * 64 < n) T <<= 1;     // many queries fill the machine: longer Horner chains, fewer partials
+  const uint32_t blocks = T / 256;
+  const Fr* const* dptr = (const Fr* const*)slot(ctx, d, "evm_ptrs", count * sizeof(void*));
+  Fr* dxs = (Fr*)slot(ctx, d, "evm_xs", 2 * count * sizeof(Fr));
+  Fr* dpart = (Fr*)slot(ctx, d, "evm_partial", count * blocks * sizeof(Fr));
+  if (!dptr || !dxs || !dpart) return SPB_ERR_OOM;
+  std::vector<Fr> xs(2 * count);
+  for (size_t q = 0; q < count; q++) { memcpy(&xs[2 * q], &points[q], 32); xs[2 * q + 1] = fp_pow_u64(xs[2 * q], T); }
+  SPB_CUDA(ctx, cudaMemcpyAsync((void*)dptr, d_polys, count * sizeof(void*), cudaMemcpyHostToDevice, d.stream));
+  SPB_CUDA(ctx, cudaMemcpyAsync(dxs, xs.data(), xs.size() * sizeof(Fr), cudaMemcpyHostToDevice, d.stream));
+  eval_many_kernel<<<dim3(blocks, (unsigned)count), 256, 0, d.stream>>>(dptr, dxs, n, T, dpart);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches++;
+  std::vector<Fr> part(count * blocks);
+  SPB_CUDA(ctx, cudaMemcpyAsync(part.data(), dpart, part.size() * sizeof(Fr), cudaMemcpyDeviceToHost, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  for (size_t q = 0; q < count; q++) {
+    Fr acc = fp_zero<FrParams>();
+    for (uint32_t t = 0; t < blocks; t++) acc = fp_add(acc, part[q * blocks + t]);
+    memcpy(&out[q], &acc, 32);
+  }
   return 0;
 }
 int spb_eval_polynomial(spb_ctx* ctx, const spb_fr* poly, size_t n, const spb_fr* point, spb_fr* out) {

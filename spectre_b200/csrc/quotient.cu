@@ -66,14 +66,10 @@ std::vector<RowShard> row_shards(spb_ctx* ctx, uint64_t size) {
 int shard_begin(spb_ctx* ctx, const RowShard& sh) {
   DeviceState& d0 = ctx->dev[0];
   DeviceState& d = ctx->dev[sh.dev_index];
-  if (sh.dev_index != 0) {
-    SPB_CUDA(ctx, cudaSetDevice(d0.device));
-    SPB_CUDA(ctx, cudaEventRecord(d0.dep_ev, d0.stream));
-    SPB_CUDA(ctx, cudaSetDevice(d.device));
-    SPB_CUDA(ctx, cudaStreamWaitEvent(d.stream, d0.dep_ev, 0));
-  } else {
-    SPB_CUDA(ctx, cudaSetDevice(d.device));
-  }
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  // d0.dep_ev was recorded at entry (SPB_ENTER0), i.e. BEFORE the first device's own shard was enqueued: the other devices
+  // wait for the caller's inputs only, not for the first device's share of this pass
+  if (sh.dev_index != 0) SPB_CUDA(ctx, cudaStreamWaitEvent(d.stream, d0.dep_ev, 0));
   return 0;
 }
 // wait for every shard; last_kernel_ms = device time of the pass on the first device's clock
@@ -111,7 +107,8 @@ extern "C" {
   std::lock_guard<std::mutex> lk((ctx)->mu);    \
   DeviceState& d0 = (ctx)->dev[0];              \
   SPB_CUDA(ctx, cudaSetDevice(d0.device));      \
-  SPB_CUDA(ctx, cudaEventRecord(d0.ev0, d0.stream));
+  SPB_CUDA(ctx, cudaEventRecord(d0.ev0, d0.stream));  \
+  if ((ctx)->dev.size() > 1) SPB_CUDA(ctx, cudaEventRecord(d0.dep_ev, d0.stream));
 
 int spb_graph_evaluate_dev(spb_ctx* ctx, const spb_graph* g, const spb_fr* const* d_fixed, uint32_t n_fixed, const spb_fr* const* d_advice, uint32_t n_advice,
                            const spb_fr* const* d_instance, uint32_t n_instance, const spb_fr* challenges, uint32_t n_challenges, const spb_fr* beta,

@@ -211,6 +211,16 @@ class Backend:
         self.check(self.lib.spb_eval_polynomial_dev(self.ctx, _p(d_poly), ctypes.c_size_t(n), _p(_fr_array(point, 1)), _p(out)), "spb_eval_polynomial_dev")
         return out
 
+    def eval_polynomial_many_dev(self, d_polys, n, points):
+        """[(device address, point (4,))...] -> (count, 4) evaluations, one launch"""
+        count = len(d_polys)
+        out = np.empty((count, 4), dtype=np.uint64)
+        if count:
+            ptrs = (ctypes.c_void_p * count)(*d_polys)
+            pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(count, 4)
+            self.check(self.lib.spb_eval_polynomial_many_dev(self.ctx, ptrs, ctypes.c_size_t(n), _p(pts), ctypes.c_size_t(count), _p(out)), "spb_eval_polynomial_many_dev")
+        return out
+
     def kate_division_dev(self, d_a, n, b, d_q):
         self.check(self.lib.spb_kate_division_dev(self.ctx, _p(d_a), ctypes.c_size_t(n), _p(_fr_array(b, 1)), _p(d_q)), "spb_kate_division_dev")
 

@@ -309,6 +309,9 @@ class DeviceEngine:
 
     # batch ops
     def eval_polynomial(self, b, n, point): return self.be.eval_polynomial_dev(b.data_ptr(), n, point)
+    def eval_polynomial_many(self, pairs, n):
+        out = self.be.eval_polynomial_many_dev([b.data_ptr() for b, _ in pairs], n, fr_mont_rows([pt for _, pt in pairs]))
+        return [fr_int(r) for r in out]
     def lincomb(self, bufs, y, out, n): self.be.lincomb_dev([b.data_ptr() for b in bufs], y, out.data_ptr(), n)
     def vec_scale(self, b, alpha, n): self.be.vec_scale_dev(b.data_ptr(), alpha, n)
 
@@ -327,6 +330,13 @@ def lagrange_to_coeff_many(E, bufs):
     else:
         for b in bufs:
             E.lagrange_to_coeff(b)
+
+
+def eval_polynomial_many(E, pairs, n):
+    """[(buffer, point:int)...] -> [eval:int...]; engines with a batched entry point evaluate the whole list in one launch"""
+    if hasattr(E, "eval_polynomial_many"):
+        return E.eval_polynomial_many(pairs, n)
+    return [fr_int(E.eval_polynomial(buf, n, fr_mont(pt))) for buf, pt in pairs]
 
 
 def coeff_to_extended_many(E, bufs):
@@ -685,40 +695,42 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
     xm = fr_mont(x)
     x_pow = lambda rot: x * pow(w, rot % n, R_MOD) % R_MOD
 
-    # 8. evaluations, in the order the verifier reads them
-    polys, evals_q = {}, []                                  # poly id -> buffer; [(poly id, point, eval)] in multi-open order
+    # 8. evaluations, in the order the verifier reads them. Every (polynomial, point) query is collected first and evaluated by
+    # ONE engine call (one kernel launch for the whole list), then the scalars enter the transcript in upstream's order.
+    polys, evals_q, todo = {}, [], []                        # poly id -> buffer; [(poly id, point, eval)] in multi-open order
 
-    def ev(pid, buf, rot):
-        pt = x_pow(rot)
+    def ask(pid, buf, rot):
         polys[pid] = buf
-        return pt, fr_int(E.eval_polynomial(buf, n, fr_mont(pt)))
+        todo.append((buf, x_pow(rot)))
+        return len(todo) - 1
 
-    adv_e = [ev(("advice", c), advice_polys[c], r) for c, r in cs.advice_queries]
-    fix_e = [ev(("fixed", c), pk.fixed_polys[c], r) for c, r in cs.fixed_queries]
-    for _, e in adv_e: transcript.write_scalar(e)
-    for _, e in fix_e: transcript.write_scalar(e)
+    adv_i = [ask(("advice", c), advice_polys[c], r) for c, r in cs.advice_queries]
+    fix_i = [ask(("fixed", c), pk.fixed_polys[c], r) for c, r in cs.fixed_queries]
     # vanishing::evaluate: h(X) = sum_i x^(n i) h_i(X), and the random polynomial at x
     h_poly = E.alloc(n)
     E.lincomb(h_pieces, fr_mont(pow(x, n, R_MOD)), h_poly, n)
-    rnd_e = ev(("random",), random_poly, 0)
+    rnd_i = ask(("random",), random_poly, 0)
+    sig_i = [ask(("sigma", c), pk.sigma_polys[c], 0) for c in range(len(pk.sigma_polys))]
+    perm_i = [(ask(("perm", s), p, 0), ask(("perm", s), p, 1), ask(("perm", s), p, -(bf + 1)) if s + 1 < len(perm_polys) else None)
+              for s, p in enumerate(perm_polys)]
+    look_i = [(ask(("lk_z", li), L.product_poly, 0), ask(("lk_z", li), L.product_poly, 1), ask(("lk_a", li), L.permuted_input_poly, 0),
+               ask(("lk_a", li), L.permuted_input_poly, -1), ask(("lk_s", li), L.permuted_table_poly, 0)) for li, L in enumerate(lookups)]
+    h_i = ask(("h",), h_poly, 0)
+    values = eval_polynomial_many(E, todo, n)
+    got = lambda i: None if i is None else (todo[i][1], values[i])
+    adv_e, fix_e, rnd_e, sig_e = [got(i) for i in adv_i], [got(i) for i in fix_i], got(rnd_i), [got(i) for i in sig_i]
+    perm_e = [tuple(got(i) for i in t) for t in perm_i]
+    look_e = [tuple(got(i) for i in t) for t in look_i]
+    for _, e in adv_e: transcript.write_scalar(e)
+    for _, e in fix_e: transcript.write_scalar(e)
     transcript.write_scalar(rnd_e[1])
-    sig_e = [ev(("sigma", c), pk.sigma_polys[c], 0) for c in range(len(pk.sigma_polys))]
     for _, e in sig_e: transcript.write_scalar(e)
-    perm_e = []
-    for s, p in enumerate(perm_polys):
-        e0, e1 = ev(("perm", s), p, 0), ev(("perm", s), p, 1)
+    for e0, e1, el in perm_e:
         transcript.write_scalar(e0[1]); transcript.write_scalar(e1[1])
-        el = None
-        if s + 1 < len(perm_polys):
-            el = ev(("perm", s), p, -(bf + 1)); transcript.write_scalar(el[1])
-        perm_e.append((e0, e1, el))
-    look_e = []
-    for li, L in enumerate(lookups):
-        pe, pne = ev(("lk_z", li), L.product_poly, 0), ev(("lk_z", li), L.product_poly, 1)
-        ie, iie = ev(("lk_a", li), L.permuted_input_poly, 0), ev(("lk_a", li), L.permuted_input_poly, -1)
-        te = ev(("lk_s", li), L.permuted_table_poly, 0)
-        for _, e in (pe, pne, ie, iie, te): transcript.write_scalar(e)
-        look_e.append((pe, pne, ie, iie, te))
+        if el is not None:
+            transcript.write_scalar(el[1])
+    for t in look_e:
+        for _, e in t: transcript.write_scalar(e)
     lap("evaluations")
 
     # 9. multi-open queries in create_proof's order: advice, permutation z, lookups, fixed, sigma, vanishing
@@ -731,8 +743,7 @@ def create_proof(E, pk, instances, advice_columns, rng, transcript, timings=None
         evals_q += [(("lk_z", li), pe[0], pe[1]), (("lk_a", li), ie[0], ie[1]), (("lk_s", li), te[0], te[1]), (("lk_a", li), iie[0], iie[1]), (("lk_z", li), pne[0], pne[1])]
     for (c, r), (pt, e) in zip(cs.fixed_queries, fix_e): evals_q.append((("fixed", c), pt, e))
     for c, (pt, e) in enumerate(sig_e): evals_q.append((("sigma", c), pt, e))
-    polys[("h",)] = h_poly
-    h_eval = fr_int(E.eval_polynomial(h_poly, n, xm))
+    h_eval = got(h_i)[1]
     evals_q.append((("h",), x, h_eval)); evals_q.append((("random",), rnd_e[0], rnd_e[1]))
 
     sets = [(fr_mont_rows(pts), [polys[p] for p in pids], np.stack([fr_mont_rows(row) for row in evs])) for pts, pids, evs in rotation_sets(evals_q)]

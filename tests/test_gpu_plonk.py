@@ -300,7 +300,7 @@ def test_proving_key_file_streams_between_disk_and_hbm(be, orc, tmp_path):
     proofs = [plonk.create_proof(E, key, [instances], adv, SeededRng(4), EvmTranscriptWrite(key.vk_digest)) for key in (pk, pk2)]
     assert proofs[0] == proofs[1]
     # params file round trip through the same streamer
-    ppath = str(tmp_path / "kzg_bn254_%d.srs" % k)
+    ppath = str(tmp_path / ("kzg_bn254_%d.srs" % k))
     params.write(ppath)
     back = ParamsKZG.read(be, ppath)
     assert np.array_equal(back.get_g(), params.get_g()) and np.array_equal(back.get_g(basis=1), params.get_g(basis=1))
