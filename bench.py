@@ -485,7 +485,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_text(), "log_n": LOG_N, "msms_per_step": MSMS_PER_STEP, "scalar_bits": 252, "window_bits": c, "windows": W,
                    "precomputed_window_tables": not args.no_tables,
-                   "pipelining": "each step is one spb_msm_batch(_dev) call: two stream lanes overlap one MSM's tail with the next one's sort/accumulate",
+                   "pipelining": "each step is one spb_msm_batch(_dev) call: three stream lanes overlap one MSM's tail with the next one's sort/accumulate",
                    "l2": "scalars rotate over 8 resident sets (256 MiB > 126 MB L2); the 64 MiB basis is reused as in the prover",
                    "collective": "one all_gather of the step's 16 x 96-byte partial sums (NCCL) + one C fold" if world > 1 else "none",
                    "timing": "wall clock between barrier + cuda synchronize pairs around exactly K steps, max over ranks; per-kernel times are CUDA events on the library's streams"},

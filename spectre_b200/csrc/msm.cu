@@ -39,10 +39,11 @@ static std::mutex g_lanes_mu;
 static const size_t kLanePinnedBytes = 256 * 1024;  // window partials of one MSM (<= 128 windows x a few points)
 
 static const int kMaxLanes = 4;
-// lanes a batch cycles through: 2 by default (one MSM's latency-bound tail under the next one's accumulation); SPB_MSM_LANES=1..4
+// lanes a batch cycles through: 3 by default -- while one MSM accumulates, the latency-bound reduction tail of the previous one
+// and the sort of the next one fill the gaps (measured 2^20, ms per MSM: 1 lane 3.36, 2 lanes 2.95, 3 lanes 2.84); SPB_MSM_LANES=1..4
 static int lane_count() {
   static int v = 0;
-  if (!v) { const char* e = getenv("SPB_MSM_LANES"); v = e ? atoi(e) : 2; if (v < 1) v = 1; if (v > kMaxLanes) v = kMaxLanes; }
+  if (!v) { const char* e = getenv("SPB_MSM_LANES"); v = e ? atoi(e) : 3; if (v < 1) v = 1; if (v > kMaxLanes) v = kMaxLanes; }
   return v;
 }
 static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
@@ -146,15 +147,13 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   cudaEventRecord(ln.ev[3], st);
   msm_accumulate_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g, ent, d_bases, buckets, head_key, head, tail_key, tail);
   cudaEventRecord(ln.ev[4], st);
-  const uint32_t kChainCap = 24;   // pieces summed inline by the group reduction; longer chains take the giant path
-  msm_giant_detect_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, g.L, kChainCap, offsets, giant, giant + 1);
+  msm_stitch_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g.L, 24, head_key, head, tail_key, tail, buckets, giant, giant + 1);
   msm_giant_kernel<<<256, 128, 0, st>>>(total, g.L, giant, giant + 1, head_key, head, tail_key, tail, buckets, huge, huge + 2);
   msm_huge_kernel<<<kHugeBlocks, 128, 0, st>>>(huge, huge + 2, head, huge_part);
   msm_huge_finish_kernel<<<64, 128, 0, st>>>(huge, huge + 2, kHugeBlocks, huge_part, tail_key, tail, buckets);
   cudaEventRecord(ln.ev[5], st);
   G1Xyzz *rows = seg_out, *cols = seg_out + (uint64_t)g.BW * R, *wrows = seg_out + (uint64_t)g.BW * (R + C);
-  MsmPieces pc; pc.L = g.L; pc.cap = kChainCap; pc.buckets = buckets; pc.head = head; pc.tail = tail;
-  msm_group_kernel<<<(unsigned)((ngroups + 127) / 128), 128, 0, st>>>(ngroups, tl.m_log, offsets, pc, grp, grp + ngroups);
+  msm_group_kernel<<<(unsigned)((ngroups + 127) / 128), 128, 0, st>>>(ngroups, tl.m_log, offsets, buckets, grp, grp + ngroups);
   cudaEventRecord(ln.ev[6], st);
   msm_rowcol_kernel<<<g.BW * (2 * R + C), 64, 0, st>>>(T1, tl, grp, grp + ngroups, rows, cols, wrows);
   msm_weighted_kernel<<<g.BW * (2 * tl.nbr + tl.nbc), 128, 0, st>>>(tl, rows, cols, wrows, win_out);
@@ -600,6 +599,81 @@ int spb_srs_precompute(spb_ctx* ctx, spb_srs* srs) {
     }
   }
   srs->table_c = c;
+  return 0;
+}
+
+// ---- accumulation micro-benchmark (an experiment, not an estimate) -------------------------------------
+// Both kernels add `rounds` gathered affine points to every one of K running sums per thread, the points read from a table
+// at pseudo-random indices as the MSM's sorted entries do.
+//   mode 0: XYZZ mixed additions, the K sums visited one after the other (sum in registers while its `rounds` points arrive).
+//   mode 1: batched affine additions: per round the K pending additions of a thread share ONE inversion (Montgomery's trick):
+//           forward pass d_j = x_P - x_acc, prefix products to memory; Fermat inversion of the total; backward pass
+//           lambda = (y_P - y_acc) / d_j, x3 = lambda^2 - x_acc - x_P, y3 = lambda (x_acc - x3) - y_acc. Sums and prefix
+//           products live in global memory laid out [j][thread] (coalesced). Exceptional cases (equal x) cannot occur for the
+//           random table other than with negligible probability and are not handled: this is a throughput probe, not a product path.
+static __device__ __forceinline__ uint32_t bench_index(uint32_t tid, uint32_t j, uint32_t r, uint32_t mask) {
+  uint32_t h = tid * 2654435761u ^ (j * 40503u + r * 2246822519u);
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  return h & mask;
+}
+__global__ void __launch_bounds__(128) bench_acc_xyzz_kernel(const G1Affine* table, uint32_t mask, uint32_t K, uint32_t rounds, G1Xyzz* out) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  for (uint32_t j = 0; j < K; j++) {
+    G1Xyzz acc = xyzz_from_affine(msm_load_point(table, bench_index(tid, j, 0xffffu, mask)));
+    for (uint32_t r = 0; r < rounds; r++) xyzz_add_mixed(acc, msm_load_point(table, bench_index(tid, j, r, mask)));
+    out[(uint64_t)j * nthreads + tid] = acc;
+  }
+}
+__global__ void __launch_bounds__(128) bench_acc_affine_kernel(const G1Affine* table, uint32_t mask, uint32_t K, uint32_t rounds, G1Affine* sums, Fq* prefix) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  for (uint32_t j = 0; j < K; j++) sums[(uint64_t)j * nthreads + tid] = msm_load_point(table, bench_index(tid, j, 0xffffu, mask));
+  for (uint32_t r = 0; r < rounds; r++) {
+    Fq run = fp_one<FqParams>();
+    for (uint32_t j = 0; j < K; j++) {
+      const Fq ax = sums[(uint64_t)j * nthreads + tid].x;
+      const Fq px = table[bench_index(tid, j, r, mask)].x;
+      prefix[(uint64_t)j * nthreads + tid] = run;                       // product of the denominators before j
+      run = fp_mul(run, fp_sub(px, ax));
+    }
+    Fq inv = fp_inv(run);
+    for (int j = (int)K - 1; j >= 0; j--) {
+      const G1Affine a = sums[(uint64_t)j * nthreads + tid];
+      const G1Affine p = msm_load_point(table, bench_index(tid, (uint32_t)j, r, mask));
+      const Fq d = fp_sub(p.x, a.x);
+      const Fq dinv = fp_mul(inv, prefix[(uint64_t)j * nthreads + tid]);
+      inv = fp_mul(inv, d);
+      const Fq lambda = fp_mul(fp_sub(p.y, a.y), dinv);
+      G1Affine s;
+      s.x = fp_sub(fp_sub(fp_sqr(lambda), a.x), p.x);
+      s.y = fp_sub(fp_mul(lambda, fp_sub(a.x, s.x)), a.y);
+      sums[(uint64_t)j * nthreads + tid] = s;
+    }
+  }
+}
+
+int spb_bench_accumulate(spb_ctx* ctx, int mode, uint32_t threads, uint32_t K, uint32_t rounds, uint32_t table_log, float* ms, uint64_t* additions) {
+  if (!ctx || !ms || !K || !rounds || table_log < 4 || table_log > 24) return SPB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceState& d = ctx->dev[0];
+  SPB_CUDA(ctx, cudaSetDevice(d.device));
+  threads = (threads + 127) / 128 * 128;
+  const uint64_t tn = 1ull << table_log;
+  Fr* sc = (Fr*)slot(ctx, d, "srs_scalars", tn * sizeof(Fr));
+  G1Affine* table = (G1Affine*)slot(ctx, d, "bacc_table", tn * sizeof(G1Affine));
+  G1Xyzz* out = (G1Xyzz*)slot(ctx, d, "bacc_state", (uint64_t)threads * K * sizeof(G1Xyzz));      // XYZZ sums, or affine sums + prefix products
+  if (!sc || !table || !out) return SPB_ERR_OOM;
+  Fr g; { constexpr uint32_t v[8] = SPB_FR_DELTA_MONT; for (int i = 0; i < 8; i++) g.l[i] = v[i]; }
+  srs_scalars_kernel<<<(unsigned)((tn + 127) / 128), 128, 0, d.stream>>>(0, g, g, g, 1, tn, sc);       // table[i] = delta^(i+1) * G1: distinct points
+  g1_fixed_base_mul_kernel<<<(unsigned)((tn + 127) / 128), 128, 0, d.stream>>>(sc, tn, table);
+  SPB_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+  if (mode == 0) bench_acc_xyzz_kernel<<<threads / 128, 128, 0, d.stream>>>(table, (uint32_t)(tn - 1), K, rounds, out);
+  else bench_acc_affine_kernel<<<threads / 128, 128, 0, d.stream>>>(table, (uint32_t)(tn - 1), K, rounds, (G1Affine*)out, (Fq*)((G1Affine*)out + (uint64_t)threads * K));
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches += 3;
+  SPB_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  SPB_CUDA(ctx, cudaEventElapsedTime(ms, d.ev0, d.ev1));
+  if (additions) *additions = (uint64_t)threads * K * rounds;
   return 0;
 }
 

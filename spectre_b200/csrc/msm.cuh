@@ -19,8 +19,10 @@
 //                 (witness columns put hundreds of thousands of points into one bucket). A run of equal keys
 //                 that lies inside a chunk is a complete bucket and is stored directly; the run that leaves
 //                 a chunk ("tail") and the run that enters one ("head") are stored as chunk pieces.
-//   5. chains   : a bucket that spans chunks is the sum of its pieces; short chains are summed where the bucket is consumed
-//                 (step 6), chains longer than a cap (giant buckets) go to block-wide / grid-wide tree reductions first.
+//   5. stitch   : one thread per tail piece walks the following head pieces of the same key and stores the
+//                 bucket; chains longer than a cap (giant buckets) go to block-wide / grid-wide tree reductions.
+//                 (Summing the pieces inside the group reduction of step 6 instead was measured: -0.2 ms of stitch, +0.3 ms of
+//                 groups at 2^20 -- three adder sites in one thread either cost 255 registers or an out-of-line adder.)
 //   6. reduce   : per bucket set S = sum_b (b+1) * bucket[b]: groups of 8 buckets by a running sum per thread, then the group
 //                 sums viewed as an R x C matrix: sum_t t*S1_t = C * sum_r r*Row_r + sum_c c*Col_c -- tree sums and local
 //                 weights < 2^7 only.
@@ -182,25 +184,21 @@ SPB_HD void msm_accumulate_thread(uint64_t tid, uint64_t M, MsmGeom g, const Msm
   tail_key[tid] = tk;
 }
 
-// ---- step 5: buckets that span chunks ---------------------------------------------------------------------------------------
-// Bucket b owns the sorted entries [offsets[b], offsets[b+1]). When they lie inside one chunk the accumulation wrote buckets[b].
-// Otherwise the bucket is the sum of its pieces: tail[t0] (the chunk it starts in) and head[t0+1 .. t1] (the chunks it continues
-// through and ends in), t = entry / L. Short chains are summed where the bucket is consumed (msm_bucket_value, called by the group
-// reduction below: no separate stitch pass, no second trip through memory); chains longer than `cap` pieces (a witness column
-// puts 10^5 points into one bucket) are queued here for the block-wide / grid-wide reductions, which write buckets[b].
-SPB_HD void msm_giant_detect_thread(uint64_t b, uint64_t nb, uint32_t L, uint32_t cap, const uint32_t* offsets, uint32_t* giant_count, uint32_t* giant_list) {
-  if (b >= nb) return;
-  const uint32_t lo = offsets[b], hi = offsets[b + 1];
-  if (hi == lo) return;
-  const uint32_t t0 = lo / L, t1 = (hi - 1) / L;
-  if (t1 - t0 > cap) { uint32_t slot = spb_atomic_inc(giant_count); giant_list[slot] = t0; }
-}
-SPB_HD G1Xyzz msm_bucket_value(uint64_t b, uint32_t lo, uint32_t hi, uint32_t L, uint32_t cap, const G1Xyzz* buckets, const G1Xyzz* head, const G1Xyzz* tail) {
-  const uint32_t t0 = lo / L, t1 = (hi - 1) / L;
-  if (t0 == t1 || t1 - t0 > cap) return buckets[b];
-  G1Xyzz acc = tail[t0];
-  for (uint32_t t = t0 + 1; t <= t1; t++) xyzz_add(acc, head[t]);
-  return acc;
+// ---- step 5: stitch chains ------------------------------------------------------------------------------
+// chain started by tail[tid]: links are head[tid+1], head[tid+2], ... while their key matches.
+// Short chains are summed here; long ones are queued for msm_giant_block.
+SPB_HD void msm_stitch_thread(uint64_t tid, uint64_t T, uint32_t cap, const uint32_t* head_key, const G1Xyzz* head,
+                              const uint32_t* tail_key, const G1Xyzz* tail, G1Xyzz* buckets, uint32_t* giant_count,
+                              uint32_t* giant_list) {
+  if (tid >= T) return;
+  uint32_t key = tail_key[tid];
+  if (key == kNoKey) return;
+  uint64_t j = tid + 1, len = 0;
+  while (j < T && head_key[j] == key && len <= cap) { j++; len++; }
+  if (len > cap) { uint32_t slot = spb_atomic_inc(giant_count); giant_list[slot] = (uint32_t)tid; return; }
+  G1Xyzz acc = tail[tid];
+  for (uint64_t q = tid + 1; q < tid + 1 + len; q++) xyzz_add(acc, head[q]);
+  buckets[key] = acc;
 }
 
 // ---- step 6: weighted bucket sum  S_w = sum_b (b+1) * bucket[w][b] ---------------------------------------------
@@ -232,15 +230,14 @@ inline MsmTail msm_tail_shape(uint32_t c) {
 SPB_HD uint32_t msm_tail_partials(const MsmTail& t) { return 3 * t.nbr + 2 * t.nbc; }
 
 // (a): one group of buckets. `offsets` is the exclusive scan of the bucket counters (offsets[b+1] - offsets[b] entries in b).
-struct MsmPieces { uint32_t L, cap; const G1Xyzz* buckets; const G1Xyzz* head; const G1Xyzz* tail; };
-SPB_HD void msm_group_thread(uint64_t tid, uint64_t ngroups, uint32_t m_log, const uint32_t* offsets, MsmPieces pc, G1Xyzz* s1, G1Xyzz* w1) {
+SPB_HD void msm_group_thread(uint64_t tid, uint64_t ngroups, uint32_t m_log, const uint32_t* offsets, const G1Xyzz* buckets, G1Xyzz* s1, G1Xyzz* w1) {
   if (tid >= ngroups) return;
   const uint64_t b0 = tid << m_log;
   G1Xyzz run = xyzz_identity(), acc = xyzz_identity();
   uint32_t hi = offsets[b0 + (1u << m_log)];
   for (int j = (int)(1u << m_log) - 1; j >= 0; j--) {
     const uint32_t lo = offsets[b0 + (uint64_t)j];
-    if (hi != lo) xyzz_add(run, msm_bucket_value(b0 + (uint64_t)j, lo, hi, pc.L, pc.cap, pc.buckets, pc.head, pc.tail));
+    if (hi != lo) xyzz_add(run, buckets[b0 + (uint64_t)j]);
     hi = lo;
     if (j >= 1) xyzz_add(acc, run);   // after the loop: acc = sum_{j>=1} (sum_{i>=j} B_i) = sum_i i * B_i
   }
@@ -248,13 +245,13 @@ SPB_HD void msm_group_thread(uint64_t tid, uint64_t ngroups, uint32_t m_log, con
   w1[tid] = acc;
 }
 // host-side reference of the kernels below (tests/hostemu): buckets -> partials
-inline void msm_tail_host(const MsmGeom& g, const uint32_t* offsets, MsmPieces pc, G1Xyzz* partials) {
+inline void msm_tail_host(const MsmGeom& g, const uint32_t* offsets, const G1Xyzz* buckets, G1Xyzz* partials) {
   MsmTail t = msm_tail_shape(g.c);
   uint32_t R = 1u << t.r_log, C = 1u << t.c_log, per = msm_tail_partials(t);
   const uint64_t T = (uint64_t)g.B >> t.m_log;
   G1Xyzz* s1 = (G1Xyzz*)malloc(sizeof(G1Xyzz) * T * g.BW);
   G1Xyzz* w1 = (G1Xyzz*)malloc(sizeof(G1Xyzz) * T * g.BW);
-  for (uint64_t tid = 0; tid < T * g.BW; tid++) msm_group_thread(tid, T * g.BW, t.m_log, offsets, pc, s1, w1);
+  for (uint64_t tid = 0; tid < T * g.BW; tid++) msm_group_thread(tid, T * g.BW, t.m_log, offsets, buckets, s1, w1);
   for (uint32_t w = 0; w < g.BW; w++) {
     const G1Xyzz* X = s1 + (uint64_t)w * T;
     const G1Xyzz* V = w1 + (uint64_t)w * T;
@@ -364,8 +361,10 @@ __global__ void __launch_bounds__(128, SPB_ACC_MINBLOCKS) msm_accumulate_kernel(
                                                              uint32_t* tail_key, G1Xyzz* tail) {
   msm_accumulate_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, *total, g, ent, bases, buckets, head_key, head, tail_key, tail);
 }
-__global__ void msm_giant_detect_kernel(uint64_t nb, uint32_t L, uint32_t cap, const uint32_t* offsets, uint32_t* giant_count, uint32_t* giant_list) {
-  msm_giant_detect_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, nb, L, cap, offsets, giant_count, giant_list);
+__global__ void __launch_bounds__(128) msm_stitch_kernel(const uint32_t* total, uint32_t L, uint32_t cap, const uint32_t* head_key, const G1Xyzz* head,
+                                                         const uint32_t* tail_key, const G1Xyzz* tail, G1Xyzz* buckets, uint32_t* giant_count, uint32_t* giant_list) {
+  uint64_t T = ((uint64_t)*total + L - 1) / L;
+  msm_stitch_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, T, cap, head_key, head, tail_key, tail, buckets, giant_count, giant_list);
 }
 
 // block-wide sum of NT points held one per thread; result in thread 0's `v`
@@ -463,8 +462,8 @@ __global__ void __launch_bounds__(128) msm_huge_finish_kernel(const uint32_t* hu
 }
 
 // (a) one thread per group of 2^m_log buckets
-__global__ void __launch_bounds__(128) msm_group_kernel(uint64_t ngroups, uint32_t m_log, const uint32_t* offsets, MsmPieces pc, G1Xyzz* s1, G1Xyzz* w1) {
-  msm_group_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, ngroups, m_log, offsets, pc, s1, w1);
+__global__ void __launch_bounds__(128) msm_group_kernel(uint64_t ngroups, uint32_t m_log, const uint32_t* offsets, const G1Xyzz* buckets, G1Xyzz* s1, G1Xyzz* w1) {
+  msm_group_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, ngroups, m_log, offsets, buckets, s1, w1);
 }
 // (b) block (w, idx): idx < R -> row sum of S1, idx < R + C -> column sum of S1, else row sum of W1
 // 64 threads per vector: more serial additions per thread and a shorter tree keep more lanes busy than 128 would

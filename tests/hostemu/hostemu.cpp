@@ -70,7 +70,7 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
   std::vector<G1Xyzz> head(T + 1), tail(T + 1);
   for (uint64_t t = 0; t < T; t++) msm_accumulate_thread(t, M, g, ent.data(), pts, buckets.data(), hk.data(), head.data(), tk.data(), tail.data());
   uint32_t gcount = 0;
-  for (uint64_t b = 0; b < nb; b++) msm_giant_detect_thread(b, nb, g.L, cap, offsets.data(), &gcount, glist.data());
+  for (uint64_t t = 0; t < T; t++) msm_stitch_thread(t, T, cap, hk.data(), head.data(), tk.data(), tail.data(), buckets.data(), &gcount, glist.data());
   for (uint32_t gi = 0; gi < gcount; gi++) {  // what msm_giant_kernel does, serially
     uint64_t t0 = glist[gi]; uint32_t key = tk[t0];
     G1Xyzz acc = xyzz_identity();
@@ -82,8 +82,7 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
   MsmTail tl = msm_tail_shape(g.c);
   uint32_t per = msm_tail_partials(tl);
   std::vector<G1Xyzz> partials((uint64_t)g.BW * per), win(g.BW);
-  MsmPieces pc; pc.L = g.L; pc.cap = cap; pc.buckets = buckets.data(); pc.head = head.data(); pc.tail = tail.data();
-  msm_tail_host(g, offsets.data(), pc, partials.data());
+  msm_tail_host(g, offsets.data(), buckets.data(), partials.data());
   for (uint32_t w = 0; w < g.BW; w++) win[w] = msm_tail_finish(g, partials.data() + (uint64_t)w * per);
   *out = xyzz_to_affine(msm_combine_windows(win.data(), g.BW, g.c));
   return M;

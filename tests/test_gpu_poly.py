@@ -74,14 +74,6 @@ def test_device_resident_variants_and_lincomb(be, orc):
     assert np.array_equal(z.cpu().numpy().view(np.uint64), be.grand_product(polys[2]))
 
 
-def test_proof_replay_tiny_runs(be, orc):
-    """The proof-shaped replay (tools for BASELINE configs 3-5) executes every stage on a test-sized shape."""
-    from spectre_b200 import replay
-    out = replay.replay(be, "tiny_k10", orc.srs_tau())
-    assert out["msm_count"] == 3 + 2 + 3 + 1 + 3 + 2 and out["total_s"] > 0
-    assert set(out["stages_s"]) >= {"3_advice_commit", "4_lookup_permute_and_commit", "7_lagrange_to_coeff", "8a_coeff_to_extended", "8b_evaluate_h", "9_vanishing_construct_commit", "11_shplonk"}
-
-
 @pytest.mark.parametrize("n", [1, 63, 64, 65, 5000, 70001])
 def test_row_sharded_grand_product_pieces(be, orc, n):
     """spb_product_dev / spb_grand_product_seeded_dev: three row blocks scanned with exchanged totals give the same

@@ -38,6 +38,19 @@ def main():
                     ms, rate = be.bench_modmul(field, 148 * tpsm, 2000, ilp)
                     print(json.dumps({"bench": "modmul", "op": nm, "field": field, "threads_per_sm": tpsm, "ms": round(ms, 3), "gop_per_s": round(rate / 1e9, 2),
                                       "lib": os.path.basename(halo2.LIB_PATH)}), flush=True)
+    if "accumulate" in what:
+        # XYZZ mixed additions vs batched affine additions with K pending additions per thread sharing one inversion
+        for tpsm in (512,):
+            be.bench_accumulate(0, 148 * tpsm, 4, 8)
+            ms, rate = be.bench_accumulate(0, 148 * tpsm, 8, 32)
+            print(json.dumps({"bench": "accumulate", "schedule": "xyzz_mixed", "threads_per_sm": tpsm, "K": 8, "rounds": 32, "ms": round(ms, 3), "gadds_per_s": round(rate / 1e9, 3)}), flush=True)
+        for tpsm in (256, 512):
+            for K in (16, 32, 64, 128, 256, 512):
+                rounds = max(2, 2048 // K)
+                be.bench_accumulate(1, 148 * tpsm, K, 1)
+                ms, rate = be.bench_accumulate(1, 148 * tpsm, K, rounds)
+                print(json.dumps({"bench": "accumulate", "schedule": "batched_affine", "threads_per_sm": tpsm, "K": K, "rounds": rounds, "ms": round(ms, 3),
+                                  "gadds_per_s": round(rate / 1e9, 3)}), flush=True)
     if "pipe" in what:
         names = {0: "IMAD.WIDE.U32", 1: "IMAD", 2: "DFMA", 3: "IMAD.WIDE+DFMA (pairs)", 4: "IADD", 5: "IMAD.WIDE+IADD (pairs)"}
         for kind in range(6):
