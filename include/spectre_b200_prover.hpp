@@ -263,9 +263,15 @@ class Program {
     for (size_t i = 0; i < constants_.size(); i++) if (constants_[i] == v) return {K_CONST, (uint32_t)i};
     constants_.push_back(v); return {K_CONST, (uint32_t)constants_.size() - 1};
   }
+  // identical calculations are emitted once, as GraphEvaluator::add_calculation does upstream
   Src emit(uint32_t op, const std::vector<Src>& srcs, uint32_t nparts = 0) {
-    words_.push_back(op | (nparts << 8)); words_.push_back(ncalc_);
-    for (auto& s : srcs) { words_.push_back(s.first); words_.push_back(s.second); }
+    std::vector<uint32_t> key = {op | (nparts << 8)};
+    for (auto& s : srcs) { key.push_back(s.first); key.push_back(s.second); }
+    auto it = seen_.find(key);
+    if (it != seen_.end()) return {K_INTER, it->second};
+    seen_.emplace(key, ncalc_);
+    words_.push_back(key[0]); words_.push_back(ncalc_);
+    words_.insert(words_.end(), key.begin() + 1, key.end());
     return {K_INTER, ncalc_++};
   }
   Src src(const ExprP& e) {
@@ -299,6 +305,7 @@ class Program {
   }
   std::vector<uint32_t> words_; uint32_t ncalc_ = 0;
   std::vector<U256> constants_; std::vector<int32_t> rotations_;
+  std::map<std::vector<uint32_t>, uint32_t> seen_;
 };
 
 // ---- ConstraintSystem ---------------------------------------------------------------------------------------------------

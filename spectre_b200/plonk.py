@@ -90,6 +90,7 @@ class Program:
 
     def __init__(self):
         self.words, self.ncalc, self.constants, self.rotations = [], 0, [0, 1], []
+        self.seen = {}   # (op, sources) -> intermediate: identical calculations are emitted once (GraphEvaluator::add_calculation)
 
     def _const(self, v):
         if v not in self.constants:
@@ -102,6 +103,10 @@ class Program:
         return self.rotations.index(r)
 
     def _emit(self, op, srcs, nparts=0):
+        key = (op, nparts, tuple(srcs))
+        if key in self.seen:
+            return self.seen[key]
+        self.seen[key] = (K_INTER, self.ncalc)
         self.words += [op | (nparts << 8), self.ncalc]
         for s in srcs:
             self.words += [s[0], s[1]]

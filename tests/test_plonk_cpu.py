@@ -276,3 +276,33 @@ def test_proving_key_file_round_trip(orc, tmp_path):
     assert proofs[0] == proofs[1]
     with pytest.raises(ValueError):
         plonk.read_pk(E, plonk_circuits.aggregation_shape(), path)
+
+
+def test_program_emits_identical_calculations_once(orc):
+    """GraphEvaluator::add_calculation ([UPSTREAM] plonk/evaluation.rs) returns the existing intermediate for a repeated
+    calculation; the flat program does the same, so wide gate sets do not multiply the per-row scratch. The
+    value of the program is unchanged: checked against direct evaluation of the gates at every row."""
+    from spectre_b200.plonk import Advice, ConstraintSystem, Fixed, Prod, Sum, Scaled
+    shared = Prod(Advice(0), Advice(1, 1))
+    gates = [Prod(Fixed(0), Sum(shared, Advice(2))), Prod(Fixed(0), Sum(shared, Scaled(Advice(2), 5))), Prod(Fixed(0), Sum(shared, Advice(2)))]
+    cs = ConstraintSystem(1, 3, 0, gates, [], [])
+    p = cs.gates_program()
+    # shared product, a2*5, two distinct sums, two distinct gate products, one Horner: 7 (12 without the reuse)
+    assert p["ncalc"] == 7
+    n = 16
+    cols = [orc.fr_random_chacha(n, 40 + i) for i in range(4)]
+    y = orc.fr_random_chacha(1, 50)[0]
+    zero = np.zeros(4, np.uint64)
+    bgty = np.stack([zero, zero, zero, y])                       # beta, gamma, theta, y
+    got = orc.graph_evaluate(p["prog"], p["ncalc"], p["ncalc"], p["constants"], p["rotations"], [cols[0]], cols[1:], [], np.zeros((1, 4), np.uint64), bgty,
+                             np.zeros((n, 4), np.uint64), 1)
+    R = orc.R_MOD
+    f, a0, a1, a2 = [orc.fr_ints(c) for c in cols]
+    yv = orc.fr_ints(y.reshape(1, 4))[0]
+    for i in range(n):
+        sh = a0[i] * a1[(i + 1) % n] % R
+        g = [f[i] * (sh + a2[i]) % R, f[i] * (sh + 5 * a2[i]) % R, f[i] * (sh + a2[i]) % R]
+        want = 0
+        for v in g:
+            want = (want * yv + v) % R
+        assert orc.fr_ints(got[i:i + 1])[0] == want
