@@ -657,22 +657,19 @@ def quotient_roofline(torch, be, dev, hbm_gbs):
 
 
 class Draw:
-    """create_proof's rng: blinding rows from a host stream; the vanishing argument's random polynomial on the device when
-    `device_poly` (it never crosses PCIe then), seeded so that two engines draw the same values."""
+    """create_proof's rng: blinding rows from a host stream; the vanishing argument's random polynomial from the library's
+    device ChaCha20 stream when `device_poly` (spb_fr_random_chacha_dev: it never crosses PCIe), so two engines -- and the
+    compiled driver -- given the same seeds draw the same values."""
 
     def __init__(self, torch, seed, device_poly=True):
-        self.torch, self.g, self.seed, self.device_poly, self.gen = torch, np.random.default_rng(seed), seed, device_poly, {}
+        self.g, self.seed = np.random.default_rng(seed), seed
+        self.chacha_seed = (0xb200 + seed).to_bytes(32, "little")
         if device_poly:
-            self.device_rows = self._device_rows
+            self.device_rows = lambda E, count: E.random_chacha(self.chacha_seed, 0, count)
 
     def __call__(self, count):
         a = self.g.integers(0, 1 << 63, size=(count, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 60) - 1)
         return a
-
-    def _device_rows(self, E, count):
-        if E.dev not in self.gen:
-            self.gen[E.dev] = self.torch.Generator(device=E.dev); self.gen[E.dev].manual_seed(self.seed)
-        return E.random_rows(count, self.gen[E.dev])
 
 
 def make_case(torch, name, k, pin=True):
@@ -721,7 +718,8 @@ def prove_both(torch, halo2, be, args):
         # the compiled driver (include/spectre_b200_prover.hpp) on the same circuit, witness and RNG stream: host draws only
         if not args.no_cpp:
             try:
-                rec = cpp_driver.RecordingRng(Draw(torch, 9, device_poly=False))
+                host = Draw(torch, 9, device_poly=False)
+                rec = cpp_driver.RecordingRng(host, chacha_poly=host.chacha_seed)
                 t0 = time.perf_counter()
                 ref_proof = plonk.create_proof(E, pkey, [inst], pinned, rec, EvmTranscriptWrite(pkey.vk_digest))
                 E.sync(); t_py_host_rng = time.perf_counter() - t0
@@ -730,13 +728,13 @@ def prove_both(torch, halo2, be, args):
                 exe = cpp_driver.build_main_against_the_real_library()
                 with tempfile.TemporaryDirectory(dir="/tmp") as d:
                     head = "shape aggregation" if name == "aggregation_shape" else "shape halo2lib 15 2"
-                    cpp_driver.dump_case(d, head, k, BENCH_VK_DIGEST, inst, copies, rec.counts, fixed_cols, adv_cols, rec.rows, secret)
+                    cpp_driver.dump_case(d, head, k, BENCH_VK_DIGEST, inst, copies, rec.counts, fixed_cols, adv_cols, rec.rows, secret, chacha_poly=host.chacha_seed)
                     rc, log, cproof, ms, kg = cpp_driver.run(exe, d, repeat=3, tables=True)
                 row["compiled_driver"] = {"returncode": rc, "create_proof_s": (min(ms[1:]) / 1e3) if len(ms) > 1 else None, "first_create_proof_s": (ms[0] / 1e3) if ms else None,
                                           "keygen_s": kg / 1e3 if kg else None, "python_driver_same_rng_s": t_py_host_rng,
                                           "proof_equals_python_driver": bool(cproof is not None and cproof == ref_proof),
-                                          "note": "C++17 header-only driver over the same C ABI, CudaMemory on the context stream; the random polynomial is drawn on the host "
-                                                  "here (n x 32 B pageable H2D inside create_proof), on the device in the Python row above"}
+                                          "note": "C++17 header-only driver over the same C ABI, CudaMemory on the context stream; same host blinding rows and the same "
+                                                  "device ChaCha20 random polynomial (spb_fr_random_chacha_dev) as the Python driver it is compared with"}
                 if rc != 0:
                     row["compiled_driver"]["log"] = log[-400:]
             except Exception as e:

@@ -197,6 +197,11 @@ int spb_eval_polynomial_dev(spb_ctx* ctx, const spb_fr* d_poly, size_t n, const 
 /* out[q] = d_polys[q](points[q]) for `count` queries of n coefficients each in one launch (create_proof's evaluation stage
  * after squeezing x: every opened polynomial at every queried rotation). d_polys: HOST array of device pointers. */
 int spb_eval_polynomial_many_dev(spb_ctx* ctx, const spb_fr* const* d_polys, size_t n, const spb_fr* points, size_t count, spb_fr* out);
+/* d_out[i] = the (first + i)-th draw of `Fr::random(&mut ChaCha20Rng::from_seed(seed))` ([UPSTREAM] rand_chacha + halo2curves
+ * Fr::random = from_u512 of one 64-byte keystream block), generated on the device: the vanishing argument's random polynomial
+ * (2^k coefficients; [UPSTREAM] plonk/vanishing/prover.rs `commit`) and any other bulk randomness of create_proof need not be
+ * drawn on the host or cross PCIe. The same seed on a CPU ChaCha20Rng yields the same elements. */
+int spb_fr_random_chacha_dev(spb_ctx* ctx, const uint8_t seed[32], uint64_t first, spb_fr* d_out, size_t n);
 int spb_kate_division_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, const spb_fr* b, spb_fr* d_q);
 int spb_grand_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* d_z);
 /* row-sharded grand product: each rank takes spb_product_dev of its rows, the 32-byte totals are

@@ -521,6 +521,12 @@ class Engine {
     return fr_int(out);
   }
   void lincomb(const std::vector<const Fr*>& polys, const Fr& y, Buffer& out, size_t len) { check(spb_lincomb_dev(ctx_, polys.data(), polys.size(), &y, out.ptr(), len), "spb_lincomb_dev"); }
+  // rows `Fr::random` draws number first.. of ChaCha20Rng::from_seed(seed), generated in device memory
+  Buffer random_chacha(const uint8_t seed[32], uint64_t first, size_t rows) {
+    Buffer b(mem_, rows);
+    check(spb_fr_random_chacha_dev(ctx_, seed, first, b.ptr(), rows), "spb_fr_random_chacha_dev");
+    return b;
+  }
   void vec_scale(Buffer& b, const Fr& alpha, size_t len) { check(spb_vec_scale_dev(ctx_, b.ptr(), &alpha, len), "spb_vec_scale_dev"); }
 
   struct OpenSet { std::vector<Fr> points; std::vector<const Fr*> polys; std::vector<Fr> evals; };
@@ -653,9 +659,12 @@ inline std::vector<RotationSet> rotation_sets(const std::vector<OpenQuery>& quer
 
 // ---- create_proof ---------------------------------------------------------------------------------------------------------
 // rng(count, out): `count` Montgomery field elements, consumed in upstream's order. instances: canonical integers.
+// bulk(E, count) (optional): the vanishing argument's random polynomial drawn straight into device memory (e.g.
+// Engine::random_chacha) instead of `count` host draws followed by an upload; it stands for that one rng call.
 using Rng = std::function<void(size_t, Fr*)>;
+using BulkRng = std::function<Buffer(Engine&, size_t)>;
 inline std::vector<uint8_t> create_proof(Engine& E, const ProvingKey& pk, const std::vector<std::vector<U256>>& instances, const std::vector<const Fr*>& advice_columns,
-                                         const Rng& rng, EvmTranscriptWrite& transcript) {
+                                         const Rng& rng, EvmTranscriptWrite& transcript, const BulkRng& bulk = nullptr) {
   const ConstraintSystem& cs = pk.cs;
   const size_t n = pk.n, usable = pk.usable_rows;
   const uint32_t bf = pk.blinding_factors;
@@ -752,7 +761,8 @@ inline std::vector<uint8_t> create_proof(Engine& E, const ProvingKey& pk, const 
 
   // 6. vanishing argument: random polynomial
   Buffer random_poly;
-  { auto r = draw(n); random_poly = E.upload(r.data(), n); }
+  if (bulk) random_poly = bulk(E, n);
+  else { auto r = draw(n); random_poly = E.upload(r.data(), n); }
   draw(1);
   write_point(E.commit(SPB_BASIS_G, {random_poly.ptr()}, n)[0]);
 

@@ -612,6 +612,10 @@ void orc_chacha20_block(const uint8_t key[32], uint64_t counter, uint8_t out[64]
 void orc_fr_random_chacha(fe* out, size_t n, const uint8_t seed[32]) {
   for (size_t i = 0; i < n; i++) { uint8_t blk[64]; orc_chacha20_block(seed, i, blk); orc_fr_from_u512(&out[i], blk); }
 }
+/* the same stream from its `first`-th draw on (draw i = keystream block i) */
+void orc_fr_random_chacha_from(fe* out, size_t n, const uint8_t seed[32], uint64_t first) {
+  for (size_t i = 0; i < n; i++) { uint8_t blk[64]; orc_chacha20_block(seed, first + i, blk); orc_fr_from_u512(&out[i], blk); }
+}
 
 /* ------------------------------------------------------------------------------------------------
  * ParamsKZG::setup with the seed-0 RNG: [UPSTREAM] halo2_proofs/src/poly/kzg/commitment.rs `setup`

@@ -94,12 +94,13 @@ def affine_ints(arr):
 
 
 # ---- wrapped entry points --------------------------------------------------------------------------
-def fr_random_chacha(n, seed):
-    """n Fr elements as `Fr::random(&mut ChaCha20Rng::from_seed(seed))` would draw them. seed: int or 32 bytes."""
+def fr_random_chacha(n, seed, first=0):
+    """n Fr elements as `Fr::random(&mut ChaCha20Rng::from_seed(seed))` would draw them (from the `first`-th draw on).
+    seed: int or 32 bytes."""
     if isinstance(seed, int):
         seed = seed.to_bytes(32, "little")
     out = np.empty((n, 4), dtype=np.uint64)
-    lib().orc_fr_random_chacha(_p(out), ctypes.c_size_t(n), ctypes.c_char_p(seed))
+    lib().orc_fr_random_chacha_from(_p(out), ctypes.c_size_t(n), ctypes.c_char_p(bytes(seed)), ctypes.c_uint64(first))
     return out
 
 

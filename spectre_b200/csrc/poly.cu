@@ -276,6 +276,47 @@ int dev_eval_polynomial(spb_ctx* ctx, DeviceState& d, const Fr* dp, size_t n, co
 
 }  // namespace spb
 
+// ---- Fr::random from a ChaCha20 keystream, on the device -------------------------------------------------------------------
+// out[i] = the (first + i)-th `Fr::random(&mut ChaCha20Rng::from_seed(seed))` draw ([UPSTREAM] rand_chacha ChaCha20Rng: djb
+// variant, 64-bit block counter in words 12-13, stream id 0; halo2curves Fr::random = from_u512 of eight next_u64() draws =
+// exactly keystream block first + i). from_u512(lo + 2^256 hi) = lo * R2 + hi * R3 in Montgomery arithmetic; both 256-bit
+// halves are brought below r first (at most five conditional subtractions) because fp_mul takes reduced operands.
+// create_proof draws its blinding rows and the vanishing argument's random polynomial from the caller's RNG (upstream passes
+// OsRng at lightclient-circuits/src/util/circuit.rs:158,211): drawing the 2^k-coefficient polynomial here means it never
+// crosses PCIe, and seeding the host-side CPU restatement identically reproduces the same proof bytes.
+__device__ __forceinline__ uint32_t chacha_rotl(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
+#define SPB_CHACHA_QR(a, b, c, d) a += b; d ^= a; d = chacha_rotl(d, 16); c += d; b ^= c; b = chacha_rotl(b, 12); a += b; d ^= a; d = chacha_rotl(d, 8); c += d; b ^= c; b = chacha_rotl(b, 7);
+struct ChaChaKey { uint32_t w[8]; };
+__global__ void fr_random_chacha_kernel(ChaChaKey key, uint64_t first, uint64_t n, Fr* out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t counter = first + i;
+  uint32_t s[16], x[16];
+  s[0] = 0x61707865u; s[1] = 0x3320646eu; s[2] = 0x79622d32u; s[3] = 0x6b206574u;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s[4 + j] = key.w[j];
+  s[12] = (uint32_t)counter; s[13] = (uint32_t)(counter >> 32); s[14] = 0; s[15] = 0;
+#pragma unroll
+  for (int j = 0; j < 16; j++) x[j] = s[j];
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    SPB_CHACHA_QR(x[0], x[4], x[8], x[12]) SPB_CHACHA_QR(x[1], x[5], x[9], x[13]) SPB_CHACHA_QR(x[2], x[6], x[10], x[14]) SPB_CHACHA_QR(x[3], x[7], x[11], x[15])
+    SPB_CHACHA_QR(x[0], x[5], x[10], x[15]) SPB_CHACHA_QR(x[1], x[6], x[11], x[12]) SPB_CHACHA_QR(x[2], x[7], x[8], x[13]) SPB_CHACHA_QR(x[3], x[4], x[9], x[14])
+  }
+  Fr lo, hi, r2, r3, m;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { lo.l[j] = x[j] + s[j]; hi.l[j] = x[8 + j] + s[8 + j]; r2.l[j] = FrParams::r2(j); }
+  { constexpr uint32_t v[8] = SPB_FR_R3;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r3.l[j] = v[j]; }
+#pragma unroll
+  for (int j = 0; j < 8; j++) m.l[j] = FrParams::mod(j);
+  // fp_sub(a, r) = a - r if a >= r, else a (the borrow adds r back): 2^256 < 5.3 r, so five rounds bring any 256-bit value below r
+#pragma unroll
+  for (int t = 0; t < 5; t++) { lo = fp_sub(lo, m); hi = fp_sub(hi, m); }
+  out[i] = fp_add(fp_mul(lo, r2), fp_mul(hi, r3));
+}
+
 extern "C" {
 
 #define SPB_ENTER(ctx)                          \
@@ -509,6 +550,18 @@ int spb_eval_polynomial(spb_ctx* ctx, const spb_fr* poly, size_t n, const spb_fr
     SPB_TRY(dev_eval_polynomial(ctx, d, dp, n, x, &acc));
   }
   memcpy(out, &acc, 32);
+  return 0;
+}
+
+int spb_fr_random_chacha_dev(spb_ctx* ctx, const uint8_t seed[32], uint64_t first, spb_fr* d_out, size_t n) {
+  if (!ctx || !seed || (n && !d_out)) return SPB_ERR_ARG;
+  if (!n) return 0;
+  SPB_ENTER(ctx);
+  ChaChaKey key; memcpy(key.w, seed, 32);
+  fr_random_chacha_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(key, first, n, (Fr*)d_out);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches++;
+  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
   return 0;
 }
 

@@ -221,6 +221,13 @@ class Backend:
             self.check(self.lib.spb_eval_polynomial_many_dev(self.ctx, ptrs, ctypes.c_size_t(n), _p(pts), ctypes.c_size_t(count), _p(out)), "spb_eval_polynomial_many_dev")
         return out
 
+    def fr_random_chacha_dev(self, seed, first, d_out, n):
+        """d_out[i] = the (first + i)-th Fr::random draw of ChaCha20Rng::from_seed(seed) (seed: int or 32 bytes), made on the device"""
+        if isinstance(seed, int):
+            seed = seed.to_bytes(32, "little")
+        assert len(seed) == 32
+        self.check(self.lib.spb_fr_random_chacha_dev(self.ctx, ctypes.c_char_p(bytes(seed)), ctypes.c_uint64(first), _p(d_out), ctypes.c_size_t(n)), "spb_fr_random_chacha_dev")
+
     def kate_division_dev(self, d_a, n, b, d_q):
         self.check(self.lib.spb_kate_division_dev(self.ctx, _p(d_a), ctypes.c_size_t(n), _p(_fr_array(b, 1)), _p(d_q)), "spb_kate_division_dev")
 

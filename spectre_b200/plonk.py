@@ -206,6 +206,24 @@ def uniform_residues(torch, rows, device, generator=None):
     return torch.cat(out)[:rows].contiguous()
 
 
+class DeviceBulkRng:
+    """The `rng` argument of create_proof with its one bulk draw kept in HBM: blinding rows come from `host_rng(count)` (a
+    few rows per column), the vanishing argument's 2^k-coefficient random polynomial from the engine's ChaCha20 stream of
+    `seed` (Engine.random_chacha -> spb_fr_random_chacha_dev: `Fr::random(ChaCha20Rng::from_seed(seed))` draws 0..2^k-1), so
+    it is never drawn on the host and never crosses PCIe. Upstream passes OsRng here
+    (lightclient-circuits/src/util/circuit.rs:158,211); any CSPRNG stream is as good."""
+
+    def __init__(self, host_rng, seed):
+        self.host_rng = host_rng
+        self.seed = seed.to_bytes(32, "little") if isinstance(seed, int) else bytes(seed)
+
+    def __call__(self, count):
+        return self.host_rng(count)
+
+    def device_rows(self, E, count):
+        return E.random_chacha(self.seed, 0, count)
+
+
 # ---- the engine bound to libspectre_b200.so -----------------------------------------------------------------------
 class DeviceEngine:
     """Buffers are torch int64 tensors of shape (rows, 4) on the context's first device (PyTorch = device memory only).
@@ -255,6 +273,11 @@ class DeviceEngine:
     def random_rows(self, rows, generator=None):
         with self.torch.cuda.stream(self.stream):
             return uniform_residues(self.torch, rows, self.dev, generator)
+    def random_chacha(self, seed, first, rows):
+        """rows `Fr::random` draws number first.. of ChaCha20Rng::from_seed(seed), generated in HBM (spb_fr_random_chacha_dev)"""
+        out = self.alloc_uninit(rows)
+        self.be.fr_random_chacha_dev(seed, first, out.data_ptr(), rows)
+        return out
     def sync(self): self.stream.synchronize()
     # proving-key file: polynomials go file <-> HBM through the library's double-buffered pinned staging, never through numpy
     def append_to_file(self, path, b, rows): self.be.write_file_dev(path, b.data_ptr(), rows * 32, append=True)

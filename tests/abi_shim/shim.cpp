@@ -17,6 +17,8 @@ typedef struct { fe x, y; } g1a;
 typedef struct orc_domain orc_domain;
 typedef struct { const fe* points; uint32_t n_points; const fe* const* polys; uint32_t n_polys; const fe* evals; } orc_rotation_set;
 void orc_init(void);
+void orc_chacha20_block(const uint8_t key[32], uint64_t counter, uint8_t out[64]);
+void orc_fr_from_u512(fe* o, const uint8_t in[64]);
 void orc_g1_generator(g1a* o);
 void orc_srs_tau(fe* tau);
 void orc_fr_delta(fe* out);
@@ -165,6 +167,10 @@ int spb_lookup_product_dev(spb_ctx*, size_t n, const spb_fr* ci, const spb_fr* c
 }
 int spb_eval_polynomial_dev(spb_ctx*, const spb_fr* d_poly, size_t n, const spb_fr* point, spb_fr* out) { orc_eval_polynomial((fe*)out, (const fe*)d_poly, n, (const fe*)point); return 0; }
 int spb_lincomb_dev(spb_ctx*, const spb_fr* const* d_polys, size_t count, const spb_fr* y, spb_fr* d_out, size_t n) { orc_vec_fold((const fe* const*)d_polys, count, (const fe*)y, (fe*)d_out, n); return 0; }
+int spb_fr_random_chacha_dev(spb_ctx*, const uint8_t seed[32], uint64_t first, spb_fr* d_out, size_t n) {
+  for (size_t i = 0; i < n; i++) { uint8_t blk[64]; orc_chacha20_block(seed, first + i, blk); orc_fr_from_u512((fe*)d_out + i, blk); }
+  return 0;
+}
 int spb_vec_scale_dev(spb_ctx*, spb_fr* d_a, const spb_fr* alpha, size_t n) { orc_vec_scale((fe*)d_a, (const fe*)alpha, n); return 0; }
 
 int spb_shplonk_begin_dev(spb_ctx* ctx, const spb_srs* srs, size_t n, const spb_rotation_set* sets, uint32_t n_sets, const spb_fr* y, const spb_fr* v,

@@ -34,6 +34,7 @@ class OracleEngine:
         b.a[start:start + rows.shape[0]] = rows
     def read_rows(self, b, start, count): return b.a[start:start + count].copy()
     def sync(self): pass
+    def random_chacha(self, seed, first, rows): return Buf(orc.fr_random_chacha(rows, seed, first))
     def append_to_file(self, path, b, rows):
         with open(path, "ab") as f:
             f.write(np.ascontiguousarray(b.a[:rows], dtype=np.uint64).tobytes())

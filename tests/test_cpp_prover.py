@@ -104,8 +104,10 @@ def _build_shim_and_main():
 
 
 class _RecordingRng:
-    def __init__(self, inner):
+    def __init__(self, inner, chacha_poly=None):
         self.inner, self.calls = inner, []
+        if chacha_poly is not None:      # the bulk draw (random polynomial) comes from the engine's ChaCha20 stream, not from `inner`
+            self.device_rows = lambda E, count: E.random_chacha(chacha_poly, 0, count)
 
     def __call__(self, count):
         out = self.inner(count)
@@ -113,11 +115,12 @@ class _RecordingRng:
         return out
 
 
-@pytest.mark.parametrize("shape,k", [("aggregation", 7), ("halo2lib", 8)])
-def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k):
+@pytest.mark.parametrize("shape,k,chacha_poly", [("aggregation", 7, None), ("halo2lib", 8, None), ("aggregation", 7, bytes(range(32)))])
+def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k, chacha_poly):
     """include/spectre_b200_prover.hpp (keygen + create_proof in C++) over the test-only CPU shim of the C ABI produces the
     same VK commitments and the same proof bytes as spectre_b200/plonk.py on the oracle engine, from the same columns, copies
-    and RNG stream."""
+    and RNG stream -- also when the vanishing argument's random polynomial is drawn by the engine from a ChaCha20 seed
+    (spb_fr_random_chacha_dev in the product) instead of arriving through the host rng."""
     from spectre_b200 import circuits, plonk
     from tests.plonk_oracle_engine import OracleEngine, SeededRng
     exe = _build_shim_and_main()
@@ -133,14 +136,18 @@ def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k):
     digest = 0x1234567890abcdef1234
     E = OracleEngine(k, cs.degree())
     pk = plonk.keygen(E, cs, k, fixed, copies, vk_digest=digest)
-    rec = _RecordingRng(SeededRng(77))
+    rec = _RecordingRng(SeededRng(77), chacha_poly)
     proof = plonk.create_proof(E, pk, [instances], adv, rec, EvmTranscriptWrite(pk.vk_digest))
+    if chacha_poly is not None:
+        assert (1 << k) not in [c.shape[0] for c in rec.calls]      # the n-row draw never went through the host stream
     d = str(tmp_path)
     with open(os.path.join(d, "meta.txt"), "w") as f:
         f.write(head + "\nk %d\ndigest %x\ninstances %s\n" % (k, digest, " ".join("%x" % v for v in instances)))
         for (c1, r1), (c2, r2) in copies:
             f.write("copy %d %d %d %d\n" % (c1, r1, c2, r2))
         f.write("rng " + " ".join(str(c.shape[0]) for c in rec.calls) + "\n")
+        if chacha_poly is not None:
+            f.write("chacha_poly %s\n" % chacha_poly.hex())
     np.concatenate(fixed).tofile(os.path.join(d, "fixed.bin"))
     np.concatenate(adv).tofile(os.path.join(d, "advice.bin"))
     np.concatenate([c for c in rec.calls if c.shape[0]] or [np.zeros((0, 4), np.uint64)]).tofile(os.path.join(d, "rng.bin"))

@@ -325,3 +325,35 @@ def test_params_file_read_write_roundtrip(be, orc, tmp_path):
     assert open(src, "rb").read() == open(dst, "rb").read()
     with pytest.raises(Exception):
         ParamsKZG.read(be, str(tmp_path / "missing.srs"))
+
+
+@pytest.mark.parametrize("label", ["uniform", "all_minus_one", "witness_like", "zeros_and_ones"])
+def test_two_pass_binned_scatter_is_the_same_sort(be, orc, points, label, monkeypatch):
+    """Entry lists beyond the L2 are scattered in two passes (coarse bins, then the cursor atomics inside L2-resident
+    windows; msm.cuh). Forced on for small inputs here: best_multiexp (W bucket sets, no tables) and the tabled
+    commit_lagrange (one bucket set) must return the same points as the oracle for uniform and degenerate columns."""
+    from spectre_b200.halo2 import ParamsKZG
+    monkeypatch.setenv("SPB_MSM_BIN_MIN_ENTRIES", "0")
+    k = 13
+    n = 1 << k
+    rng = np.random.default_rng(17)
+    if label == "uniform":
+        sc = orc.fr_random_chacha(n, 0xb1)
+    elif label == "all_minus_one":
+        sc = orc.fr([pyref.R_MOD - 1] * n)
+    elif label == "zeros_and_ones":
+        sc = orc.fr([int(x) for x in rng.integers(0, 2, n)])
+    else:
+        ks = []
+        for i in range(n):
+            u = rng.random()
+            ks.append(0 if u < 0.7 else int(rng.integers(0, 1 << 16)) if u < 0.9 else int(rng.integers(0, 1 << 62)) ** 2 % (1 << 104) if u < 0.99 else int(rng.integers(1, 1 << 62)) ** 4 % pyref.R_MOD)
+        sc = orc.fr(ks)
+    want = affine_of(orc, orc.best_multiexp(sc, points[:n]))
+    assert np.array_equal(affine_of(orc, be.best_multiexp(sc, points[:n])), want)
+    for m in (n - 1, 777):                                      # ragged tile edges of pass A
+        assert np.array_equal(affine_of(orc, be.best_multiexp(sc[:m], points[:m])), affine_of(orc, orc.best_multiexp(sc[:m], points[:m])))
+    tabled = ParamsKZG.from_parts(be, k, g_lagrange=points[:n]).precompute()
+    assert np.array_equal(affine_of(orc, tabled.commit_lagrange(sc)), want)
+    monkeypatch.setenv("SPB_MSM_BIN_MIN_ENTRIES", str(1 << 40))
+    assert np.array_equal(affine_of(orc, tabled.commit_lagrange(sc)), want)

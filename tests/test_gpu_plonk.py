@@ -186,6 +186,29 @@ def test_device_proof_is_byte_identical_to_the_oracle_proof_and_verifies(be, orc
     assert plonk_verifier.verify(cs, k, pk_d.vk_digest, pk_d.fixed_commitments, pk_d.sigma_commitments, [instances], proof_d, tau)
 
 
+def test_random_polynomial_drawn_on_the_device_gives_the_oracle_proof(be, orc):
+    """plonk.DeviceBulkRng: the vanishing argument's random polynomial comes from spb_fr_random_chacha_dev (never on the host);
+    the oracle engine draws the same ChaCha20 stream on the CPU, so the proofs are byte-identical and verify."""
+    from spectre_b200 import circuits as plonk_circuits, plonk
+    from spectre_b200.halo2 import ParamsKZG
+    from spectre_b200.transcript import EvmTranscriptWrite
+    from tests import plonk_verifier
+    from tests.plonk_oracle_engine import OracleEngine, SeededRng
+    k, instances = 9, [2, 7, 1]
+    cs = plonk_circuits.halo2lib_shape(3, 2)
+    fixed, adv, copies = plonk_circuits.halo2lib_witness(cs, k, instances, lookup_bits=4, groups=40, num_gate_advice=3, num_lookup_advice=2)
+    proofs = []
+    for E in (plonk.DeviceEngine(be, ParamsKZG.setup(be, k, orc.srs_tau()), k, cs.degree()), OracleEngine(k, cs.degree())):
+        pk = plonk.keygen(E, cs, k, fixed, copies)
+        rng = plonk.DeviceBulkRng(SeededRng(31), 0xc0ffee)
+        proofs.append(plonk.create_proof(E, pk, [instances], adv, rng, EvmTranscriptWrite(pk.vk_digest)))
+    assert proofs[0] == proofs[1]
+    tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
+    assert plonk_verifier.verify(cs, k, pk.vk_digest, pk.fixed_commitments, pk.sigma_commitments, [instances], proofs[0], tau)
+    other = plonk.create_proof(E, pk, [instances], adv, plonk.DeviceBulkRng(SeededRng(31), 0xc0ffef), EvmTranscriptWrite(pk.vk_digest))
+    assert other != proofs[0]                                   # the seed matters
+
+
 def _fixture_paths():
     import glob
     import os

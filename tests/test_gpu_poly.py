@@ -97,3 +97,17 @@ def test_row_sharded_grand_product_pieces(be, orc, n):
         assert total == prod
         seed = seed * total % R
     assert np.array_equal(dz.cpu().numpy().view(np.uint64), want)
+
+
+def test_fr_random_chacha_on_the_device_is_the_cpu_stream(be, orc):
+    """spb_fr_random_chacha_dev draws `Fr::random(&mut ChaCha20Rng::from_seed(seed))` values in HBM: the same elements as the
+    oracle's CPU keystream (which the seed-0 SRS secret pins against the verifier contracts' -tau G2), also across the 2^32
+    word boundary of the block counter and for odd lengths; outputs are canonical residues."""
+    import torch
+    dev = torch.device("cuda", 0)
+    for seed, first, n in ((0, 0, 1), (0x5eed, 0, 4097), (b"\x07" * 32, (1 << 32) - 5, 300), (2 ** 255 + 12345, (1 << 40) + 3, 777)):
+        out = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        be.fr_random_chacha_dev(seed, first, out.data_ptr(), n)
+        got = out.cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, orc.fr_random_chacha(n, seed, first)), (seed, first, n)
+    assert np.array_equal(orc.fr_random_chacha(1, 0)[0], orc.srs_tau().reshape(4))   # draw 0 of seed 0 = the SRS secret

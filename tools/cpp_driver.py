@@ -26,14 +26,18 @@ def build_main_against_the_real_library():
     return exe
 
 
-def dump_case(d, head, k, digest, instances, copies, rng_counts, fixed, adv, rng_rows, tau):
+def dump_case(d, head, k, digest, instances, copies, rng_counts, fixed, adv, rng_rows, tau, chacha_poly=None):
     """head: 'shape aggregation' | 'shape halo2lib G L'; rng_counts: create_proof's draw sizes in order (zeros included);
-    rng_rows: the drawn rows for the non-zero counts, in order; tau: (4,) uint64 Montgomery SRS secret."""
+    rng_rows: the drawn rows for the non-zero counts, in order; tau: (4,) uint64 Montgomery SRS secret; chacha_poly: 32-byte
+    seed when the vanishing argument's random polynomial comes from the device ChaCha20 stream (that draw is then absent
+    from rng_counts / rng_rows)."""
     with open(os.path.join(d, "meta.txt"), "w") as f:
         f.write(head + "\nk %d\ndigest %x\ninstances %s\n" % (k, digest, " ".join("%x" % v for v in instances)))
         for (c1, r1), (c2, r2) in copies:
             f.write("copy %d %d %d %d\n" % (c1, r1, c2, r2))
         f.write("rng " + " ".join(str(c) for c in rng_counts) + "\n")
+        if chacha_poly is not None:
+            f.write("chacha_poly %s\n" % bytes(chacha_poly).hex())
     with open(os.path.join(d, "fixed.bin"), "wb") as f:
         for c in fixed:
             f.write(np.ascontiguousarray(c, dtype=np.uint64).tobytes())
@@ -64,8 +68,12 @@ def run(exe, d, repeat=1, tables=False, timeout=900):
 class RecordingRng:
     """wraps an rng(count) -> (count, 4) callable and keeps every draw, so the compiled driver can replay the same stream"""
 
-    def __init__(self, inner):
-        self.inner, self.calls = inner, []
+    def __init__(self, inner, chacha_poly=None):
+        """chacha_poly: 32-byte seed -> the bulk draw (the random polynomial) is made in device memory by the engine from that
+        ChaCha20 stream (rng.device_rows protocol of plonk.create_proof) and is not part of the recorded host stream"""
+        self.inner, self.calls, self.chacha_poly = inner, [], chacha_poly
+        if chacha_poly is not None:
+            self.device_rows = lambda E, count: E.random_chacha(bytes(chacha_poly), 0, count)
 
     def __call__(self, count):
         out = self.inner(count)
