@@ -50,7 +50,7 @@ static int lane_count() {
 // the size of the L2); SPB_MSM_BIN_MIN_ENTRIES overrides it (0 = always, a huge value = never)
 static uint64_t bin_min_entries() {
   if (const char* e = getenv("SPB_MSM_BIN_MIN_ENTRIES")) return (uint64_t)atoll(e);
-  return 1ull << 24;
+  return ~0ull;   // off: measured slower than the one-pass scatter at every size (profiles/r02_msm_probe.md)
 }
 static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
   std::lock_guard<std::mutex> lk(g_lanes_mu);
@@ -93,6 +93,10 @@ static void* lane_slot(spb_ctx* ctx, DeviceState& d, int lane, const char* name,
 static uint32_t choose_chunk(const DeviceState& d, uint64_t est_entries) {
   if (const char* e = getenv("SPB_MSM_CHUNK")) { int v = atoi(e); if (v >= 8 && v <= 256) return (uint32_t)v; }
   const double wave = (double)d.sm_count * 512.0;
+  // entry lists of 2^24 and more (2^21 pairs with tables): the chunk pieces (two 128-byte points per chunk) no longer fit the L2 and
+  // the stitch pass becomes DRAM-latency bound -- 2^22 pairs: 1.79 ms at L = 32, 0.31 ms at L = 96 for +0.14 ms of accumulation
+  // (profiles/r02_msm_probe.md); with hundreds of waves the tail of the last wave does not matter
+  if (est_entries >= kLongChunkMinEntries) return kLongChunk;
   double waves = (double)est_entries / 32.0 / wave;
   if (waves < 1.0) return 32;
   double w = waves < 1.5 ? 1.0 : (double)(uint64_t)(waves + 0.5);
@@ -107,7 +111,8 @@ static uint32_t choose_chunk(const DeviceState& d, uint64_t est_entries) {
 static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const Fr* d_scalars, const G1Affine* d_bases, uint64_t n, MsmGeom g) {
   const uint64_t nb = (uint64_t)g.BW * g.B;
   const uint64_t cap = n * g.W;                 // upper bound on entries
-  const uint64_t Tmax = (cap + g.L - 1) / g.L;  // upper bound on chunks
+  const uint32_t Lmin = g.L == kLongChunk ? kShortChunk : g.L;   // the kernels may fall back to the short chunk (msm_effective_chunk)
+  const uint64_t Tmax = (cap + Lmin - 1) / Lmin;  // upper bound on chunks
   if (cap >= 0x7fffffffull) return set_error(ctx, SPB_ERR_ARG, "msm: %llu entries exceed the 31-bit sort index", (unsigned long long)cap);
   uint32_t* counts = (uint32_t*)lane_slot(ctx, d, lane, "msm_counts", (nb + 1) * 4);
   uint32_t* offsets = (uint32_t*)lane_slot(ctx, d, lane, "msm_offsets", (nb + 1) * 4);

@@ -52,6 +52,13 @@ struct MsmGeom {
 
 struct alignas(8) MsmEntry { uint32_t key, val; };
 
+// Chunk length actually used for a sorted list of M entries. The host picks L from the upper bound n * W; the long chunk it picks
+// for lists beyond the L2 (kLongChunk) only pays when the list really is that long -- witness columns drop most of their
+// digits -- so every kernel that cuts the list derives the same effective length from the entry count on the device.
+static const uint32_t kLongChunk = 96, kShortChunk = 32;
+static const uint64_t kLongChunkMinEntries = 1ull << 24;
+SPB_HD uint32_t msm_effective_chunk(uint32_t L, uint64_t M) { return (L == kLongChunk && M < kLongChunkMinEntries) ? kShortChunk : L; }
+
 static const uint32_t kNoKey = 0xffffffffu;
 
 #if defined(__CUDA_ARCH__)
@@ -149,9 +156,10 @@ SPB_HD MsmEntry msm_load_entry(const MsmEntry* p) {
 SPB_HD void msm_accumulate_thread(uint64_t tid, uint64_t M, MsmGeom g, const MsmEntry* ent,
                                   const G1Affine* bases, G1Xyzz* buckets, uint32_t* head_key, G1Xyzz* head,
                                   uint32_t* tail_key, G1Xyzz* tail) {
-  uint64_t lo = tid * g.L;
+  const uint32_t L = msm_effective_chunk(g.L, M);
+  uint64_t lo = tid * L;
   if (lo >= M) return;
-  uint64_t hi = lo + g.L < M ? lo + g.L : M;
+  uint64_t hi = lo + L < M ? lo + L : M;
   uint32_t hk = kNoKey, tk = kNoKey;
   MsmEntry first = msm_load_entry(ent + lo);
   uint32_t cur = first.key;
@@ -434,6 +442,7 @@ __global__ void __launch_bounds__(128, SPB_ACC_MINBLOCKS) msm_accumulate_kernel(
 }
 __global__ void __launch_bounds__(128) msm_stitch_kernel(const uint32_t* total, uint32_t L, uint32_t cap, const uint32_t* head_key, const G1Xyzz* head,
                                                          const uint32_t* tail_key, const G1Xyzz* tail, G1Xyzz* buckets, uint32_t* giant_count, uint32_t* giant_list) {
+  L = msm_effective_chunk(L, *total);
   uint64_t T = ((uint64_t)*total + L - 1) / L;
   msm_stitch_thread(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, T, cap, head_key, head, tail_key, tail, buckets, giant_count, giant_list);
 }
@@ -472,6 +481,7 @@ __global__ void __launch_bounds__(128) msm_giant_kernel(const uint32_t* total, u
                                                         G1Xyzz* buckets, uint32_t* huge_count, uint32_t* huge_list /* pairs: t0, end */) {
   __shared__ G1Xyzz sh[64];
   __shared__ uint64_t s_end;
+  L = msm_effective_chunk(L, *total);
   const uint64_t T = ((uint64_t)*total + L - 1) / L;
   const uint32_t count = *giant_count;
   for (uint32_t gi = blockIdx.x; gi < count; gi += gridDim.x) {

@@ -65,7 +65,8 @@ uint64_t he_msm(G1Affine* out, const Fr* scalars, const G1Affine* bases, size_t 
   for (uint64_t t = 0; t < n; t++) msm_scatter_thread(t, n, scalars, g, cursor.data(), ent.data());
   std::vector<G1Xyzz> buckets(nb);
   memset(buckets.data(), 0xAB, nb * sizeof(G1Xyzz));   // never cleared on the device either: only written buckets may be read
-  uint64_t T = (M + g.L - 1) / g.L;
+  const uint32_t Leff = msm_effective_chunk(g.L, M);
+  uint64_t T = (M + Leff - 1) / Leff;
   std::vector<uint32_t> hk(T + 1, 0x12345678u), tk(T + 1, 0x12345678u), glist(T + 2);
   std::vector<G1Xyzz> head(T + 1), tail(T + 1);
   for (uint64_t t = 0; t < T; t++) msm_accumulate_thread(t, M, g, ent.data(), pts, buckets.data(), hk.data(), head.data(), tk.data(), tail.data());
