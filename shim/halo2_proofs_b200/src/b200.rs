@@ -108,6 +108,9 @@ extern "C" {
     pub fn spb_kate_division(ctx: *mut spb_ctx, a: *const Fr, n: usize, b: *const Fr, q: *mut Fr) -> c_int;
     pub fn spb_eval_polynomial_dev(ctx: *mut spb_ctx, d_poly: *const Fr, n: usize, point: *const Fr, out: *mut Fr) -> c_int;
     pub fn spb_lincomb_dev(ctx: *mut spb_ctx, d_polys: *const *const Fr, count: usize, y: *const Fr, d_out: *mut Fr, n: usize) -> c_int;
+    /// d_out[i] = draw number first + i of `Fr::random(&mut ChaCha20Rng::from_seed(seed))`, generated in device memory (the
+    /// vanishing argument's random polynomial of a device-resident create_proof)
+    pub fn spb_fr_random_chacha_dev(ctx: *mut spb_ctx, seed: *const u8, first: u64, d_out: *mut Fr, n: usize) -> c_int;
     // ---- evaluate_h ----
     pub fn spb_graph_evaluate_dev(
         ctx: *mut spb_ctx, g: *const spb_graph, d_fixed: *const *const Fr, n_fixed: u32, d_advice: *const *const Fr, n_advice: u32,
