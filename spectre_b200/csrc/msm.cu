@@ -46,12 +46,6 @@ static int lane_count() {
   if (!v) { const char* e = getenv("SPB_MSM_LANES"); v = e ? atoi(e) : 3; if (v < 1) v = 1; if (v > kMaxLanes) v = kMaxLanes; }
   return v;
 }
-// entry count from which the counting sort scatters in two L2-friendly passes (default 2^24 entries = 128 MiB of 8-byte entries,
-// the size of the L2); SPB_MSM_BIN_MIN_ENTRIES overrides it (0 = always, a huge value = never)
-static uint64_t bin_min_entries() {
-  if (const char* e = getenv("SPB_MSM_BIN_MIN_ENTRIES")) return (uint64_t)atoll(e);
-  return ~0ull;   // off: measured slower than the one-pass scatter at every size (profiles/r02_msm_probe.md)
-}
 static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
   std::lock_guard<std::mutex> lk(g_lanes_mu);
   auto& v = g_lanes[std::make_pair(ctx, dev_index)];
@@ -141,12 +135,12 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   if ((size_t)g.BW * per * sizeof(G1Xyzz) + 16 > kLanePinnedBytes) return set_error(ctx, SPB_ERR_STATE, "msm: %u window partials exceed the pinned staging area", g.BW * per);
 
   cudaStream_t st = ln.stream;
-  SPB_CUDA(ctx, cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
   // the bucket array is NOT cleared: every non-empty bucket is written exactly once (accumulate / stitch / giant paths) and
   // the reduction reads a bucket only where the sort's offsets say it has entries
   SPB_CUDA(ctx, cudaMemsetAsync(giant, 0, 4, st));
   SPB_CUDA(ctx, cudaMemsetAsync(huge, 0, 4, st));
   const unsigned tb = 256;
+  SPB_CUDA(ctx, cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
   cudaEventRecord(ln.ev[0], st);
   msm_count_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(n, d_scalars, g, counts);
   cudaEventRecord(ln.ev[1], st);
@@ -154,21 +148,9 @@ static int msm_enqueue(spb_ctx* ctx, DeviceState& d, int lane, Lane& ln, const F
   // cursor := offsets (the counters are dead after the scan; reuse their storage)
   SPB_CUDA(ctx, cudaMemcpyAsync(counts, offsets, (nb + 1) * 4, cudaMemcpyDeviceToDevice, st));
   cudaEventRecord(ln.ev[2], st);
-  if (cap >= bin_min_entries()) {
-    // entry list beyond the L2: two passes with L2-resident write windows (msm.cuh, "step 3 for entry lists that do not fit")
-    uint32_t bits = 0; while ((1ull << bits) < nb) bits++;
-    const uint32_t shift = bits > kBinLog ? bits - kBinLog : 0;
-    uint32_t* bin_cursor = (uint32_t*)lane_slot(ctx, d, lane, "msm_bin_cursor", (1u << kBinLog) * 4);
-    MsmEntry* tmp = (MsmEntry*)lane_slot(ctx, d, lane, "msm_entries_tmp", (cap + 1) * sizeof(MsmEntry));
-    if (!bin_cursor || !tmp) return SPB_ERR_OOM;
-    SPB_CUDA(ctx, cudaMemsetAsync(bin_cursor, 0, (1u << kBinLog) * 4, st));
-    const uint64_t tile = (uint64_t)tb * kBinItems;
-    msm_bin_scatter_kernel<<<(unsigned)((n + tile - 1) / tile), tb, 0, st>>>(n, d_scalars, g, shift, offsets, bin_cursor, tmp);
-    msm_bin_sort_kernel<<<(unsigned)((cap + tb - 1) / tb), tb, 0, st>>>(offsets + nb, tmp, counts, ent);
-    ctx->n_kernel_launches++;
-  } else {
-    msm_scatter_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(n, d_scalars, g, counts, ent);
-  }
+  // (Two alternatives to this one-pass counting sort were built and measured slower at every size -- a second scatter pass with
+  // L2-resident write windows, and a bin-local sort ranking in shared memory: profiles/r02_msm_probe.md.)
+  msm_scatter_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(n, d_scalars, g, counts, ent);
   const uint32_t* total = offsets + nb;  // number of entries M, resident on the device
   cudaEventRecord(ln.ev[3], st);
   msm_accumulate_kernel<<<(unsigned)((Tmax + 127) / 128), 128, 0, st>>>(total, g, ent, d_bases, buckets, head_key, head, tail_key, tail);

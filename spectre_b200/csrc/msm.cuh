@@ -317,6 +317,17 @@ inline G1Xyzz msm_tail_finish(const MsmGeom& g, const G1Xyzz* part) {
 // (witness columns are full of repeated small values) are found with match.any and served by ONE atomic, so a column
 // of equal scalars costs one atomic per warp and window instead of 32 serialised ones on the same address. The loop
 // is kept convergent (inactive lanes carry a flag instead of leaving) so the warp-level primitives are well defined.
+// Lanes of the warp holding the same key as the caller (inactive lanes pass kNoKey). MATCH.ANY costs ~80 issue cycles per warp on
+// sm_100a and was what bound the histogram and sort kernels (ncu: top stall of msm_count / msm_bin_local_sort), while only columns
+// of repeated values need the grouping -- and those show equal keys in NEIGHBOURING lanes. So: one shuffle + vote decide; without
+// neighbouring duplicates every lane is its own group (any duplicates elsewhere in the warp just take their own atomics, which is
+// always correct -- the grouping is an optimisation).
+__device__ __forceinline__ unsigned msm_warp_peers(uint32_t key, uint32_t lane) {
+  const uint32_t next = __shfl_down_sync(0xffffffffu, key, 1);
+  const bool dup = lane < 31u && next == key && key != kNoKey;
+  if (__any_sync(0xffffffffu, dup)) return __match_any_sync(0xffffffffu, key);
+  return 1u << lane;
+}
 __global__ void msm_count_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* counts) {
   const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
@@ -329,11 +340,8 @@ __global__ void msm_count_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint3
     const bool act = live && d != 0;
     const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
     const uint32_t key = (g.precomp ? 0u : w * g.B) + mag - 1;
-    const unsigned actmask = __ballot_sync(0xffffffffu, act);
-    if (act) {
-      const unsigned peers = __match_any_sync(actmask, key);
-      if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
-    }
+    const unsigned peers = msm_warp_peers(act ? key : kNoKey, lane);
+    if (act && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
   }
 }
 __global__ void msm_scatter_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t* cursor, MsmEntry* ent) {
@@ -348,88 +356,18 @@ __global__ void msm_scatter_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uin
     const bool act = live && d != 0;
     const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
     const uint32_t key = (g.precomp ? 0u : w * g.B) + mag - 1;
-    const unsigned actmask = __ballot_sync(0xffffffffu, act);
+    // whole-warp match and shuffle (inactive lanes carry a key no bucket has): a shuffle under per-group masks would be executed
+    // once per group -- 32 times for 32 distinct keys
+    const unsigned peers = msm_warp_peers(act ? key : kNoKey, lane);
+    const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+    uint32_t base = 0;
+    if (act && lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
     if (act) {
-      const unsigned peers = __match_any_sync(actmask, key);
-      const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
-      base = __shfl_sync(peers, base, leader);
       const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
       MsmEntry e; e.key = key; e.val = ((uint32_t)tid + (g.precomp ? w * g.tab_stride : 0u)) | (d < 0 ? 0x80000000u : 0u);
       ent[pos] = e;
     }
-  }
-}
-// ---- step 3 for entry lists that do not fit the L2 (n * W * 8 B well above 126 MB: 2^22 pairs and more) -------------------
-// The one-pass scatter above writes 8-byte entries at random positions of the whole list: beyond the L2 every such write is
-// a partial 32-byte sector that DRAM has to merge (2^23 pairs: 3.3 ms for 0.8 GB). Two passes keep every write window
-// L2-resident instead:
-//   A  msm_bin_scatter_kernel: a block takes a tile of scalars, histograms its entries over 2^kBinLog coarse key ranges
-//      ("bins") in shared memory, reserves one contiguous run per bin with ONE global atomic per (block, bin) and writes
-//      the entries into `tmp` -- the same layout as the final list (bin b occupies [offsets[b << shift], offsets[(b+1) <<
-//      shift])), only unordered inside a bin; the runs of one block are ~100 entries long, so sectors fill while resident.
-//   B  msm_bin_sort_kernel: reads `tmp` front to back (coalesced) and places every entry with the usual cursor atomic; the
-//      blocks in flight cover a few MB of `tmp`, i.e. a few bins, so their writes and their cursor atomics stay in the L2.
-static const uint32_t kBinLog = 7;
-static const uint32_t kBinItems = 4;      // scalars per thread of pass A (tile = blockDim * kBinItems scalars)
-__global__ void __launch_bounds__(256) msm_bin_scatter_kernel(uint64_t n, const Fr* scalars, MsmGeom g, uint32_t shift, const uint32_t* offsets,
-                                                              uint32_t* bin_cursor, MsmEntry* tmp) {
-  __shared__ uint32_t s_count[1u << kBinLog];
-  __shared__ uint32_t s_base[1u << kBinLog];
-  const uint64_t tile0 = (uint64_t)blockIdx.x * blockDim.x * kBinItems;
-  for (uint32_t b = threadIdx.x; b < (1u << kBinLog); b += blockDim.x) s_count[b] = 0;
-  __syncthreads();
-  for (uint32_t r = 0; r < kBinItems; r++) {
-    const uint64_t i = tile0 + (uint64_t)r * blockDim.x + threadIdx.x;
-    if (i >= n) continue;
-    Fr s = fp_from_mont(scalars[i]);
-    if (fp_is_zero(s)) continue;
-    DigitIter it; it.init(s, g.c);
-    for (uint32_t w = 0; w < g.W; w++) {
-      const int32_t d = it.next();
-      if (d == 0) continue;
-      const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      atomicAdd(&s_count[((g.precomp ? 0u : w * g.B) + mag - 1) >> shift], 1u);
-    }
-  }
-  __syncthreads();
-  for (uint32_t b = threadIdx.x; b < (1u << kBinLog); b += blockDim.x) {
-    const uint32_t cnt = s_count[b];
-    s_base[b] = cnt ? offsets[(uint64_t)b << shift] + atomicAdd(&bin_cursor[b], cnt) : 0u;   // an empty bin may lie beyond the last bucket
-    s_count[b] = 0;
-  }
-  __syncthreads();
-  for (uint32_t r = 0; r < kBinItems; r++) {
-    const uint64_t i = tile0 + (uint64_t)r * blockDim.x + threadIdx.x;
-    if (i >= n) continue;
-    Fr s = fp_from_mont(scalars[i]);
-    if (fp_is_zero(s)) continue;
-    DigitIter it; it.init(s, g.c);
-    for (uint32_t w = 0; w < g.W; w++) {
-      const int32_t d = it.next();
-      if (d == 0) continue;
-      const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      const uint32_t key = (g.precomp ? 0u : w * g.B) + mag - 1, bin = key >> shift;
-      MsmEntry e; e.key = key; e.val = ((uint32_t)i + (g.precomp ? w * g.tab_stride : 0u)) | (d < 0 ? 0x80000000u : 0u);
-      tmp[s_base[bin] + atomicAdd(&s_count[bin], 1u)] = e;
-    }
-  }
-}
-__global__ void __launch_bounds__(256) msm_bin_sort_kernel(const uint32_t* total, const MsmEntry* tmp, uint32_t* cursor, MsmEntry* ent) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31u;
-  const bool act = i < *total;
-  MsmEntry e; e.key = 0; e.val = 0;
-  if (act) e = msm_load_entry(tmp + i);
-  const unsigned actmask = __ballot_sync(0xffffffffu, act);
-  if (act) {
-    const unsigned peers = __match_any_sync(actmask, e.key);
-    const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(&cursor[e.key], (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    ent[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = e;
   }
 }
 #ifndef SPB_ACC_MINBLOCKS

@@ -327,13 +327,13 @@ def test_params_file_read_write_roundtrip(be, orc, tmp_path):
         ParamsKZG.read(be, str(tmp_path / "missing.srs"))
 
 
-@pytest.mark.parametrize("label", ["uniform", "all_minus_one", "witness_like", "zeros_and_ones"])
-def test_two_pass_binned_scatter_is_the_same_sort(be, orc, points, label, monkeypatch):
-    """Entry lists beyond the L2 are scattered in two passes (coarse bins, then the cursor atomics inside L2-resident
-    windows; msm.cuh). Forced on for small inputs here: best_multiexp (W bucket sets, no tables) and the tabled
-    commit_lagrange (one bucket set) must return the same points as the oracle for uniform and degenerate columns."""
+@pytest.mark.parametrize("label", ["uniform", "all_minus_one", "witness_like", "zeros_and_ones", "pairs"])
+def test_counting_sort_groups_repeated_digits_only_when_neighbours_repeat(be, orc, points, label):
+    """The histogram / scatter kernels serve equal digits of a warp with one atomic only when neighbouring lanes repeat
+    (msm_warp_peers: the MATCH.ANY grouping is skipped otherwise); duplicates that are NOT neighbours take their own atomics.
+    All of these columns -- uniform, constant, witness-like, 0/1, and values repeated at distance 2 -- must give the oracle's
+    points through best_multiexp (W bucket sets) and the tabled commit_lagrange (one bucket set), ragged lengths included."""
     from spectre_b200.halo2 import ParamsKZG
-    monkeypatch.setenv("SPB_MSM_BIN_MIN_ENTRIES", "0")
     k = 13
     n = 1 << k
     rng = np.random.default_rng(17)
@@ -343,6 +343,9 @@ def test_two_pass_binned_scatter_is_the_same_sort(be, orc, points, label, monkey
         sc = orc.fr([pyref.R_MOD - 1] * n)
     elif label == "zeros_and_ones":
         sc = orc.fr([int(x) for x in rng.integers(0, 2, n)])
+    elif label == "pairs":                                          # a, b, a, b, ... : every digit repeated at distance 2, never adjacent
+        sc = orc.fr_random_chacha(n, 0xb2)
+        sc[2::4] = sc[0::4]; sc[3::4] = sc[1::4]
     else:
         ks = []
         for i in range(n):
@@ -351,9 +354,7 @@ def test_two_pass_binned_scatter_is_the_same_sort(be, orc, points, label, monkey
         sc = orc.fr(ks)
     want = affine_of(orc, orc.best_multiexp(sc, points[:n]))
     assert np.array_equal(affine_of(orc, be.best_multiexp(sc, points[:n])), want)
-    for m in (n - 1, 777):                                      # ragged tile edges of pass A
-        assert np.array_equal(affine_of(orc, be.best_multiexp(sc[:m], points[:m])), affine_of(orc, orc.best_multiexp(sc[:m], points[:m])))
+    for m in (n - 1, 777):
+        assert np.array_equal(affine_of(orc, be.best_multiexp(sc[:m], points[:m])), affine_of(orc, orc.best_multiexp(sc[:m], points[:m]))), m
     tabled = ParamsKZG.from_parts(be, k, g_lagrange=points[:n]).precompute()
-    assert np.array_equal(affine_of(orc, tabled.commit_lagrange(sc)), want)
-    monkeypatch.setenv("SPB_MSM_BIN_MIN_ENTRIES", str(1 << 40))
     assert np.array_equal(affine_of(orc, tabled.commit_lagrange(sc)), want)

@@ -1,7 +1,6 @@
 #!/usr/bin/env python3
 """MSM schedule probe on one GPU: device ms (CUDA events inside the library) and per-stage split for a few sizes while the
 run-time knobs of csrc/msm.cu are varied in-process (they are read from the environment on every call):
-  SPB_MSM_BIN_MIN_ENTRIES  entry count from which the counting sort scatters in two L2-friendly passes
   SPB_MSM_CHUNK            entries per accumulation chunk (default: chosen per size, 24..48)
 usage: python tools/msm_probe.py [k ...]   -> JSON lines"""
 import json
@@ -25,14 +24,12 @@ def main():
         n = 1 << k
         hk = np.concatenate([bench.rand_fr(1 << 20, 500 + b) for b in range(max(1, n >> 20))])[:n]
         params = halo2.ParamsKZG.from_parts(be, k, g_lagrange=be.g1_fixed_base_mul(hk)).precompute()
-        for dist in ("uniform", "witness_like"):
-            sc = np.concatenate([bench.scalars_distribution(dist, 1 << 20, 900 + b) for b in range(max(1, n >> 20))])[:n]
+        for dist in ("uniform", "witness_like", "all_minus_one"):
+            sc = np.concatenate([bench.scalars_distribution(dist, 1 << 20, 900 + b) for b in range(max(1, n >> 20))])[:n] if dist != "all_minus_one" else bench.scalars_distribution(dist, n, 0)
             d = torch.from_numpy(sc.view(np.int64)).to(dev)
             ref = None
-            for knobs in ({"SPB_MSM_BIN_MIN_ENTRIES": str(1 << 40)}, {"SPB_MSM_BIN_MIN_ENTRIES": "0"},
-                          {"SPB_MSM_BIN_MIN_ENTRIES": "0", "SPB_MSM_CHUNK": "48"}, {"SPB_MSM_BIN_MIN_ENTRIES": "0", "SPB_MSM_CHUNK": "64"},
-                          {"SPB_MSM_BIN_MIN_ENTRIES": "0", "SPB_MSM_CHUNK": "96"}):
-                for v in ("SPB_MSM_BIN_MIN_ENTRIES", "SPB_MSM_CHUNK"):
+            for knobs in ({}, {"SPB_MSM_CHUNK": "32"}, {"SPB_MSM_CHUNK": "64"}, {"SPB_MSM_CHUNK": "96"}):
+                for v in ("SPB_MSM_CHUNK",):
                     os.environ.pop(v, None)
                 os.environ.update(knobs)
                 ts, st = [], {}
