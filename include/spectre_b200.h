@@ -295,6 +295,12 @@ void spb_shplonk_abort(spb_ctx* ctx, spb_shplonk* s);
 /* ---- test / bench utilities -------------------------------------------------------------------------------- */
 /* out[i] = scalars[i] * G1 (affine), computed on the device */
 int spb_g1_fixed_base_mul(spb_ctx* ctx, const spb_fr* scalars, size_t n, spb_g1_affine* out);
+/* The host-side scheduling pass spb_graph_evaluate_dev applies to a program before it runs it (one-part Horner steps placed next to
+ * the calculation that produces the part; intermediates renamed to scratch slots by liveness -- csrc/quotient.cu), without any
+ * device work: out_words receives the rescheduled program (same encoding, targets = slots < *num_slots). Returns SPB_ERR_STATE
+ * when the pass declines (malformed program, a target written twice): the caller's program is then run as it is. */
+int spb_test_schedule_program(const uint32_t* program, size_t program_words, uint32_t num_calculations, uint32_t* out_words, size_t out_capacity,
+                              size_t* out_count, uint32_t* num_slots, uint32_t* out_calculations);
 /* Elementwise device arithmetic exposed for parity tests of the field/curve layer: op 0 mul, 1 add, 2 sub;
  * field 0 = Fr, 1 = Fq. */
 int spb_test_field_op(spb_ctx* ctx, int field, int op, const spb_fr* a, const spb_fr* b, spb_fr* out, size_t n);

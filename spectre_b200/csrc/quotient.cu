@@ -15,6 +15,9 @@
 #include "quotient.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <utility>
+#include <vector>
 
 using namespace spb;
 
@@ -99,6 +102,99 @@ const Fr* const* upload_ptrs(spb_ctx* ctx, DeviceState& d, const char* name, con
   return (const Fr* const*)dst;
 }
 
+// ---- program scheduling: fewer live intermediates per row ------------------------------------------------------------------
+// GraphEvaluator's calculations come in "one intermediate per node" form, and its final Horner folds every gate at once, so all
+// gate values are alive until the very end: 76 intermediates for the 15-gate halo2-lib shape, i.e. 2.4 KB of scratch per thread and
+// 184 MB for the grid -- more than the L2, so the scratch traffic (not the column reads) set the kernel's time. The program is
+// tiny and evaluated for millions of rows, so it is rescheduled here, once per call, on the host:
+//  1. a Horner over k parts becomes k one-part Horner steps (same arithmetic: acc = acc * factor + part), each placed right after
+//     the calculation that produces its part, so a gate's value dies as soon as it is folded in;
+//  2. intermediates are renamed to scratch slots by liveness (a slot is reused once its value has been read for the last time).
+// Values are unchanged bit for bit (the same field operations in the same operand order); only scratch addresses and the order of
+// independent calculations move. Programs that write a target twice are left as they are.
+struct Calc { uint32_t op, nparts, target; std::vector<std::pair<uint32_t, uint32_t>> src; double key; };
+bool schedule_program(const uint32_t* words, size_t nwords, uint32_t ncalc, std::vector<uint32_t>& out, uint32_t& nslots_out, uint32_t& ncalc_out) {
+  std::vector<Calc> calcs;
+  size_t w = 0;
+  uint32_t max_id = 0;
+  for (uint32_t c = 0; c < ncalc; c++) {
+    if (w + 2 > nwords) return false;
+    Calc k; k.op = words[w] & 0xffu; k.nparts = words[w] >> 8; k.target = words[w + 1]; k.key = 0;
+    const uint32_t ns = k.op <= 2 ? 2u : (k.op == 6 ? 2u + k.nparts : 1u);
+    if (k.op > 7 || w + 2 + 2 * (size_t)ns > nwords) return false;
+    for (uint32_t i = 0; i < ns; i++) k.src.push_back({words[w + 2 + 2 * i], words[w + 3 + 2 * i]});
+    w += 2 + 2 * (size_t)ns;
+    if (k.target > max_id) max_id = k.target;
+    calcs.push_back(std::move(k));
+  }
+  if (calcs.empty()) return false;
+  std::vector<int> producer(max_id + 1, -1);
+  for (size_t i = 0; i < calcs.size(); i++) {
+    if (producer[calcs[i].target] != -1) return false;           // a target written twice: keep the caller's schedule
+    producer[calcs[i].target] = (int)i;
+  }
+  auto produced_at = [&](const std::pair<uint32_t, uint32_t>& s) -> int {   // index of the calculation a source waits for, -1 if none
+    if (s.first != 1) return -1;
+    const uint32_t id = s.second & 0xffffu;
+    return id <= max_id ? producer[id] : -1;
+  };
+  // 1. split the Horners; key = position in the original order (+ a small offset that keeps the chain ordered)
+  std::vector<Calc> sched;
+  uint32_t next_id = max_id + 1;
+  for (size_t i = 0; i < calcs.size(); i++) {
+    Calc& k = calcs[i];
+    for (auto& s : k.src) if (s.first == 1 && produced_at(s) < 0) return false;   // reads an intermediate nobody wrote
+    if (k.op != 6 || k.nparts < 2) { k.key = (double)i; sched.push_back(k); continue; }
+    const int ready0 = std::max(produced_at(k.src[0]), produced_at(k.src[1]));
+    double prev_key = -1.0;
+    std::pair<uint32_t, uint32_t> acc = k.src[0];
+    for (uint32_t p = 0; p < k.nparts; p++) {
+      Calc h; h.op = 6; h.nparts = 1;
+      h.target = p + 1 == k.nparts ? k.target : next_id++;
+      h.src = {acc, k.src[1], k.src[2 + p]};
+      const int ready = std::max(ready0, produced_at(k.src[2 + p]));
+      double key = (double)ready + 0.5;                            // right after the last producer it waits for ...
+      if (key <= prev_key) key = prev_key + 1e-4;                  // ... but after the previous link of the chain
+      if (key > (double)i) key = (double)i;                        // never later than the original Horner
+      h.key = key; prev_key = key;
+      acc = {1u, h.target};
+      sched.push_back(std::move(h));
+    }
+  }
+  if (next_id > 0xffffu) return false;
+  // the row's result is whatever the LAST calculation produced: the caller's last calculation (or the last link of its Horner) stays last
+  for (auto& k : sched) if (k.target == calcs.back().target) k.key = 1e18;
+  std::stable_sort(sched.begin(), sched.end(), [](const Calc& a, const Calc& b) { return a.key < b.key; });
+  // 2. liveness -> slots
+  std::vector<int> last_use(next_id, -1);
+  for (size_t i = 0; i < sched.size(); i++) for (auto& s : sched[i].src) if (s.first == 1) last_use[s.second & 0xffffu] = (int)i;
+  std::vector<uint32_t> slot_of(next_id, 0xffffffffu), free_slots;
+  uint32_t nslots = 0;
+  out.clear();
+  for (size_t i = 0; i < sched.size(); i++) {
+    Calc& k = sched[i];
+    std::vector<uint32_t> dying;
+    for (auto& s : k.src) {
+      if (s.first != 1) continue;
+      const uint32_t id = s.second & 0xffffu;
+      if (slot_of[id] == 0xffffffffu) return false;                // read before written: the sort broke a dependency (cannot happen)
+      s.second = slot_of[id];
+      if (last_use[id] == (int)i) dying.push_back(id);
+    }
+    std::sort(dying.begin(), dying.end()); dying.erase(std::unique(dying.begin(), dying.end()), dying.end());
+    for (uint32_t id : dying) { free_slots.push_back(slot_of[id]); slot_of[id] = 0xfffffffeu; }   // the row body reads every source before it stores
+    uint32_t sl;
+    if (!free_slots.empty()) { sl = free_slots.back(); free_slots.pop_back(); } else sl = nslots++;
+    slot_of[k.target] = sl;
+    if (last_use[k.target] < 0 && i + 1 != sched.size()) free_slots.push_back(sl);   // never read (dead code): its slot is free at once
+    out.push_back(k.op | (k.nparts << 8)); out.push_back(sl);
+    for (auto& s : k.src) { out.push_back(s.first); out.push_back(s.second); }
+  }
+  nslots_out = nslots ? nslots : 1;
+  ncalc_out = (uint32_t)sched.size();
+  return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -115,6 +211,16 @@ int spb_graph_evaluate_dev(spb_ctx* ctx, const spb_graph* g, const spb_fr* const
                            const spb_fr* gamma, const spb_fr* theta, const spb_fr* y, spb_fr* d_values, uint64_t size, int32_t rot_scale) {
   if (!ctx || !g || !d_values || !beta || !gamma || !theta || !y || (g->program_words && !g->program)) return SPB_ERR_ARG;
   if (g->num_intermediates > 0xffff || g->num_constants > 0x10000 || g->num_rotations > 0xffff) return set_error(ctx, SPB_ERR_ARG, "graph: index fields are 16 bits");
+  // reschedule the program for few live intermediates (schedule_program above); fall back to the caller's words if it declines
+  std::vector<uint32_t> prog_words;
+  uint32_t n_inter = g->num_intermediates, n_calc = g->num_calculations;
+  const uint32_t* prog = g->program;
+  size_t prog_n = g->program_words;
+  if (g->program_words && !getenv("SPB_GRAPH_NO_SCHEDULE") && schedule_program(g->program, g->program_words, g->num_calculations, prog_words, n_inter, n_calc)) {
+    prog = prog_words.data(); prog_n = prog_words.size();
+  } else {
+    n_inter = g->num_intermediates; n_calc = g->num_calculations;
+  }
   SPB_ENTER0(ctx);
   std::vector<Fr> sc(4 + n_challenges);
   memcpy(&sc[0], beta, 32); memcpy(&sc[1], gamma, 32); memcpy(&sc[2], theta, 32); memcpy(&sc[3], y, 32);
@@ -126,13 +232,13 @@ int spb_graph_evaluate_dev(spb_ctx* ctx, const spb_graph* g, const spb_fr* const
     const uint32_t threads = 256, blocks = (uint32_t)d.sm_count * 2;   // grid-stride: 2 x 256 threads per SM
     const uint64_t nslots = (uint64_t)threads * blocks;
     GraphArgs a; memset(&a, 0, sizeof a);
-    uint32_t* dprog = (uint32_t*)slot(ctx, d, "q_prog", (g->program_words ? g->program_words : 1) * 4);
+    uint32_t* dprog = (uint32_t*)slot(ctx, d, "q_prog", (prog_n ? prog_n : 1) * 4);
     Fr* dconst = (Fr*)slot(ctx, d, "q_const", (g->num_constants ? g->num_constants : 1) * sizeof(Fr));
     int32_t* drot = (int32_t*)slot(ctx, d, "q_rot", (g->num_rotations ? g->num_rotations : 1) * 4);
     Fr* dscal = (Fr*)slot(ctx, d, "q_scalars", (4 + (size_t)n_challenges) * sizeof(Fr));
-    Fr* scratch = (Fr*)slot(ctx, d, "q_scratch", (g->num_intermediates ? g->num_intermediates : 1) * nslots * sizeof(Fr));
+    Fr* scratch = (Fr*)slot(ctx, d, "q_scratch", (n_inter ? n_inter : 1) * nslots * sizeof(Fr));
     if (!dprog || !dconst || !drot || !dscal || !scratch) return SPB_ERR_OOM;
-    SPB_CUDA(ctx, cudaMemcpyAsync(dprog, g->program, g->program_words * 4, cudaMemcpyHostToDevice, d.stream));
+    SPB_CUDA(ctx, cudaMemcpyAsync(dprog, prog, prog_n * 4, cudaMemcpyHostToDevice, d.stream));
     if (g->num_constants) SPB_CUDA(ctx, cudaMemcpyAsync(dconst, g->constants, (size_t)g->num_constants * 32, cudaMemcpyHostToDevice, d.stream));
     if (g->num_rotations) SPB_CUDA(ctx, cudaMemcpyAsync(drot, g->rotations, (size_t)g->num_rotations * 4, cudaMemcpyHostToDevice, d.stream));
     SPB_CUDA(ctx, cudaMemcpyAsync(dscal, sc.data(), sc.size() * 32, cudaMemcpyHostToDevice, d.stream));
@@ -140,13 +246,25 @@ int spb_graph_evaluate_dev(spb_ctx* ctx, const spb_graph* g, const spb_fr* const
     a.advice = upload_ptrs(ctx, d, "q_advice", d_advice, n_advice);
     a.instance = upload_ptrs(ctx, d, "q_instance", d_instance, n_instance);
     if (!a.fixed || !a.advice || !a.instance) return set_error(ctx, SPB_ERR_CUDA, "graph: pointer table upload failed");
-    a.prog = dprog; a.ncalc = g->num_calculations; a.constants = dconst; a.rotations = drot; a.scalars = dscal;
+    a.prog = dprog; a.ncalc = n_calc; a.constants = dconst; a.rotations = drot; a.scalars = dscal;
     a.values = (Fr*)d_values; a.scratch = scratch; a.size = size; a.rot_scale = rot_scale; a.row_lo = sh.lo; a.row_hi = sh.hi;
     graph_evaluate_kernel<<<blocks, threads, 0, d.stream>>>(a);
     SPB_CUDA(ctx, cudaGetLastError());
     ctx->n_kernel_launches++;
   }
   return shards_finish(ctx, shards);  // synchronises: `sc` and the caller's arrays outlive the copies
+}
+
+// the scheduling pass alone (no device involved): lets the CPU tests run the scheduled program through the oracle's interpreter
+int spb_test_schedule_program(const uint32_t* program, size_t program_words, uint32_t num_calculations, uint32_t* out_words, size_t out_capacity,
+                              size_t* out_count, uint32_t* num_slots, uint32_t* out_calculations) {
+  if (!program || !out_words || !out_count || !num_slots || !out_calculations) return SPB_ERR_ARG;
+  std::vector<uint32_t> w; uint32_t ns = 0, nc = 0;
+  if (!schedule_program(program, program_words, num_calculations, w, ns, nc)) return SPB_ERR_STATE;
+  if (w.size() > out_capacity) return SPB_ERR_ARG;
+  memcpy(out_words, w.data(), w.size() * 4);
+  *out_count = w.size(); *num_slots = ns; *out_calculations = nc;
+  return 0;
 }
 
 int spb_permutation_constraints_dev(spb_ctx* ctx, spb_fr* d_values, uint64_t size, int32_t rot_scale, int32_t last_rotation, uint32_t n_sets, uint32_t chunk_len,

@@ -68,3 +68,48 @@ def test_permutation_and_lookup_terms(orc):
         v = (v * yy + (a[i] - t[i]) * (a[i] - a[rp]) * lai[i]) % R
         want.append(v)
     assert got == want
+
+
+def _schedule(prog, ncalc):
+    """libspectre_b200's host-side scheduling pass (no device needed) -> (words, slots, calculations)"""
+    import ctypes
+    from spectre_b200 import halo2
+    lib = halo2.load_library()
+    prog = np.ascontiguousarray(prog, dtype=np.uint32)
+    out = np.zeros(4 * len(prog) + 64, dtype=np.uint32)
+    cnt, slots, nc = ctypes.c_size_t(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
+    rc = lib.spb_test_schedule_program(prog.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(prog)), ctypes.c_uint32(ncalc), out.ctypes.data_as(ctypes.c_void_p),
+                                       ctypes.c_size_t(len(out)), ctypes.byref(cnt), ctypes.byref(slots), ctypes.byref(nc))
+    assert rc == 0, rc
+    return out[:cnt.value].copy(), slots.value, nc.value
+
+
+def test_scheduled_program_is_the_same_function_with_few_live_intermediates(orc):
+    """spb_graph_evaluate_dev reschedules the flat GraphEvaluator program before running it (Horner split into one-part steps next
+    to their producers, intermediates renamed to slots by liveness: csrc/quotient.cu). The rescheduled words, run through the
+    oracle's interpreter, give the same value on every row as the original program; the 15-gate halo2-lib shape drops from 76
+    intermediates to a handful of slots, the lookup-compression and lookup-value programs keep working."""
+    from spectre_b200 import circuits
+    cs = circuits.halo2lib_shape()
+    n = 64
+    fixed = [orc.fr_random_chacha(n, 300 + i) for i in range(cs.num_fixed)]
+    advice = [orc.fr_random_chacha(n, 400 + i) for i in range(cs.num_advice)]
+    inst = [orc.fr_random_chacha(n, 500)]
+    bgty = orc.fr_random_chacha(4, 600)
+    prev = orc.fr_random_chacha(n, 700)
+    ch = np.zeros((1, 4), np.uint64)
+    progs = [cs.gates_program(), cs.lookup_value_program(len(cs.lookups) - 1), cs.lookup_compress_program(cs.lookups[-1][0])]
+    for p in progs:
+        words, slots, nc = _schedule(p["prog"], p["ncalc"])
+        assert slots <= 8 and slots <= p["ncalc"]
+        want = orc.graph_evaluate(p["prog"], p["ncalc"], p["ncalc"], p["constants"], p["rotations"], fixed, advice, inst, ch, bgty, prev, 1)
+        got = orc.graph_evaluate(words, nc, slots, p["constants"], p["rotations"], fixed, advice, inst, ch, bgty, prev, 1)
+        assert np.array_equal(got, want)
+    assert progs[0]["ncalc"] >= 60 and _schedule(progs[0]["prog"], progs[0]["ncalc"])[1] <= 6
+    # a program that writes one target twice is left alone (the pass declines)
+    import ctypes
+    from spectre_b200 import halo2
+    twice = np.array([0, 0, 3, 0, 3, 1 << 16, 0, 0, 1, 0, 3, 0], dtype=np.uint32)      # t0 = a0 + a0'; t0 = t0 + a0
+    out = np.zeros(64, np.uint32); cnt, slots, nc = ctypes.c_size_t(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
+    assert halo2.load_library().spb_test_schedule_program(twice.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(twice)), ctypes.c_uint32(2),
+                                                          out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(64), ctypes.byref(cnt), ctypes.byref(slots), ctypes.byref(nc)) != 0
