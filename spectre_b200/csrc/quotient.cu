@@ -211,6 +211,7 @@ int spb_graph_evaluate_dev(spb_ctx* ctx, const spb_graph* g, const spb_fr* const
                            const spb_fr* gamma, const spb_fr* theta, const spb_fr* y, spb_fr* d_values, uint64_t size, int32_t rot_scale) {
   if (!ctx || !g || !d_values || !beta || !gamma || !theta || !y || (g->program_words && !g->program)) return SPB_ERR_ARG;
   if (g->num_intermediates > 0xffff || g->num_constants > 0x10000 || g->num_rotations > 0xffff) return set_error(ctx, SPB_ERR_ARG, "graph: index fields are 16 bits");
+  if (!size || (size & (size - 1))) return set_error(ctx, SPB_ERR_ARG, "graph: the extended domain size must be a power of two");
   // reschedule the program for few live intermediates (schedule_program above); fall back to the caller's words if it declines
   std::vector<uint32_t> prog_words;
   uint32_t n_inter = g->num_intermediates, n_calc = g->num_calculations;
@@ -274,6 +275,7 @@ int spb_permutation_constraints_dev(spb_ctx* ctx, spb_fr* d_values, uint64_t siz
   if (!ctx || !d_values || !beta || !gamma || !y || !extended_omega || !d_l0 || !d_l_last || !d_l_active) return SPB_ERR_ARG;
   if (!n_sets) return 0;
   if (!d_z || !chunk_len || (n_cols && (!d_col_values || !d_sigma))) return SPB_ERR_ARG;
+  if (!size || (size & (size - 1))) return set_error(ctx, SPB_ERR_ARG, "permutation constraints: the extended domain size must be a power of two");
   SPB_ENTER0(ctx);
   PermArgs a; memset(&a, 0, sizeof a);
   a.values = (Fr*)d_values; a.size = size; a.rot_scale = rot_scale; a.last_rotation = last_rotation;
@@ -309,6 +311,7 @@ int spb_lookup_constraints_dev(spb_ctx* ctx, spb_fr* d_values, uint64_t size, in
                                const spb_fr* d_l_active, const spb_fr* beta, const spb_fr* gamma, const spb_fr* y) {
   if (!ctx || !d_values || !d_product || !d_permuted_input || !d_permuted_table || !d_table_value || !d_l0 || !d_l_last || !d_l_active || !beta || !gamma || !y)
     return SPB_ERR_ARG;
+  if (!size || (size & (size - 1))) return set_error(ctx, SPB_ERR_ARG, "lookup constraints: the extended domain size must be a power of two");
   SPB_ENTER0(ctx);
   LookupArgs a;
   a.values = (Fr*)d_values; a.size = size; a.rot_scale = rot_scale;

@@ -16,6 +16,11 @@ struct GraphArgs {
 };
 
 SPB_HD uint64_t rotation_idx(uint64_t idx, int32_t rot, int32_t rot_scale, uint64_t size) {
+#if defined(__CUDA_ARCH__)
+  // extended domains are powers of two (the entry points of quotient.cu reject anything else): wrap with a mask -- two's complement
+  // makes it right for negative rotations too -- instead of a 64-bit remainder per column read
+  return (idx + (uint64_t)((long long)rot * rot_scale)) & (size - 1);
+#endif
   long long v = ((long long)idx + (long long)rot * rot_scale) % (long long)size;
   if (v < 0) v += (long long)size;
   return (uint64_t)v;
