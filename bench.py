@@ -528,6 +528,21 @@ def main():
             torch.cuda.empty_cache()
         line["msm_sizes"] = sizes
 
+    # ---- the plain best_multiexp front door (what an unpatched call site binds): host scalars AND host bases per call vs resident bases
+    if not args.no_sizes and world == 1:
+        sc = host_np[0]
+        walls = {"msm_raw": [], "resident_bases": []}
+        res_b = halo2.ParamsKZG.from_bases(be, pts)
+        for it in range(5):
+            t0 = time.perf_counter(); r1 = be.best_multiexp(sc, pts); walls["msm_raw"].append(time.perf_counter() - t0)
+            t0 = time.perf_counter(); r2 = res_b.multiexp(sc); walls["resident_bases"].append(time.perf_counter() - t0)
+        line["best_multiexp_front_door"] = {
+            "spb_msm_raw_ms": float(np.median(walls["msm_raw"][1:])) * 1e3, "spb_bases_upload_then_spb_msm_ms": float(np.median(walls["resident_bases"][1:])) * 1e3,
+            "same_point": bool(np.array_equal(r1, r2)),
+            "what": "wall ms of ONE 2^20 best_multiexp through the C ABI from pinned host scalars: spb_msm_raw re-uploads the 64 MiB of bases and runs without "
+                    "window tables (c = 16, 16 bucket sets); against bases uploaded once (spb_bases_upload, no tables) only the 32 MiB of scalars move"}
+        del res_b
+
     # ---- NTT throughput (the other half of BASELINE.json's metric), device-resident, rank 0 ------------------
     if not args.no_ntt:
         ntt = {}

@@ -114,6 +114,10 @@ uint32_t spb_srs_k(const spb_srs* srs);
 /* best_multiexp(coeffs, bases) -> G1 ([UPSTREAM] halo2_proofs/src/arithmetic.rs): sum_i scalars[i] * bases[i].
  * `out` is the Jacobian point normalised to z = 1 (identity: x = 0, y = 1, z = 0). */
 int spb_msm_raw(spb_ctx* ctx, const spb_fr* scalars, const spb_g1_affine* bases, size_t n, spb_g1* out);
+/* best_multiexp against bases the caller reuses: upload ANY n bases once (the handle is an SRS handle with only basis SPB_BASIS_G
+ * resident; free it with spb_srs_free, widen its window with spb_srs_precompute), then spb_msm / spb_msm_batch(handle, SPB_BASIS_G,
+ * ...) move only the 32 B x n of scalars per call instead of spb_msm_raw's 96 B x n. */
+int spb_bases_upload(spb_ctx* ctx, const spb_g1_affine* bases, size_t n, spb_srs** out);
 /* Params::commit / commit_lagrange: MSM of `n` scalars against the first n points of a resident basis. */
 int spb_msm(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* scalars, size_t n, spb_g1* out);
 /* same with the scalars already resident on device 0 of the context */

@@ -84,6 +84,8 @@ extern "C" {
     pub fn spb_srs_k(srs: *const spb_srs) -> u32;
     // ---- MSM ----
     pub fn spb_msm_raw(ctx: *mut spb_ctx, scalars: *const Fr, bases: *const G1Affine, n: usize, out: *mut G1) -> c_int;
+    /// bases of any length kept resident (an SRS handle with only basis G set): `spb_msm(handle, SPB_BASIS_G, ..)` then moves the scalars only
+    pub fn spb_bases_upload(ctx: *mut spb_ctx, bases: *const G1Affine, n: usize, out: *mut *mut spb_srs) -> c_int;
     pub fn spb_msm(ctx: *mut spb_ctx, srs: *const spb_srs, basis: c_int, scalars: *const Fr, n: usize, out: *mut G1) -> c_int;
     pub fn spb_msm_batch(ctx: *mut spb_ctx, srs: *const spb_srs, basis: c_int, scalars: *const *const Fr, n: usize, count: usize, out: *mut G1) -> c_int;
     pub fn spb_msm_dev(ctx: *mut spb_ctx, srs: *const spb_srs, basis: c_int, d_scalars: *const Fr, n: usize, out: *mut G1) -> c_int;
@@ -234,6 +236,17 @@ impl GpuSrs {
             }
         }
         Some(GpuSrs { ctx, h, k })
+    }
+
+    /// Bases of any length kept resident for repeated `best_multiexp` calls against the same slice (e.g. a caller-held
+    /// generator vector): `commit(SPB_BASIS_G, coeffs)` on the result is `best_multiexp(coeffs, &bases[..coeffs.len()])` and moves
+    /// 32 B per pair instead of the 96 B of `msm_raw`. The caller owns the association between the slice and the handle.
+    pub fn from_bases(bases: &[G1Affine]) -> Option<Self> {
+        let ctx = ctx()?;
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe { spb_bases_upload(ctx, bases.as_ptr(), bases.len(), &mut h) };
+        ok(ctx, rc, "spb_bases_upload")?;
+        Some(GpuSrs { ctx, h, k: usize::BITS - bases.len().saturating_sub(1).leading_zeros() })
     }
 
     /// `Params::commit` (basis = SPB_BASIS_G) / `commit_lagrange` (SPB_BASIS_G_LAGRANGE) of host scalars.

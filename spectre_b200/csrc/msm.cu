@@ -311,6 +311,35 @@ fail:
   return SPB_ERR_CUDA;
 }
 
+// Arbitrary bases kept resident: what a caller of best_multiexp that reuses one base vector (any length) uploads once instead of
+// paying 64 B x n of PCIe per call through spb_msm_raw. The handle is an SRS handle with only `g` set and n = the given length.
+int spb_bases_upload(spb_ctx* ctx, const spb_g1_affine* bases, size_t n, spb_srs** out) {
+  if (!ctx || !out || !bases || !n || n > ((size_t)1 << 28)) return SPB_ERR_ARG;
+  uint32_t k = 0; while (((size_t)1 << k) < n) k++;
+  spb_srs* s;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    s = srs_alloc(ctx, k);
+    s->n = n;
+    const size_t D = ctx->dev.size();
+    for (size_t i = 0; i < D; i++) { s->shards[i].start = n * i / D; s->shards[i].count = n * (i + 1) / D - s->shards[i].start; }
+    for (auto& sh : s->shards) {
+      if (!sh.count) continue;
+      DeviceState& d = ctx->dev[sh.dev_index];
+      cudaError_t e = cudaSetDevice(d.device);
+      if (e == cudaSuccess) e = cudaMalloc(&sh.g, sh.count * sizeof(G1Affine));
+      if (e == cudaSuccess) e = cudaMemcpyAsync(sh.g, (const G1Affine*)bases + sh.start, sh.count * sizeof(G1Affine), cudaMemcpyHostToDevice, d.stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+      if (e != cudaSuccess) { set_error(ctx, SPB_ERR_CUDA, "spb_bases_upload: %s", cudaGetErrorString(e)); goto fail; }
+    }
+    *out = s;
+    return 0;
+  }
+fail:
+  spb_srs_free(ctx, s);
+  return SPB_ERR_CUDA;
+}
+
 int spb_srs_setup(spb_ctx* ctx, uint32_t k, const spb_fr* secret, spb_srs** out) {
   if (!ctx || !out || !secret || k > 28) return SPB_ERR_ARG;
   spb_srs* s;

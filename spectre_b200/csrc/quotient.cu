@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) graph_evaluate_kernel(GraphArgs a) {
 
 // one extended_omega power per block (thread 0: 2 log2(idx) products) times a 256-entry table entry per thread, instead of
 // a full exponentiation per row
-__global__ void __launch_bounds__(256) permutation_constraints_kernel(PermArgs a) {
+__global__ void __launch_bounds__(256, 3) permutation_constraints_kernel(PermArgs a) {
   __shared__ Fr base;
   const uint64_t block_row = a.row_lo + blockIdx.x * (uint64_t)blockDim.x;   // row_lo is a multiple of 256
   if (threadIdx.x == 0) base = fp_pow_u64(a.extended_omega, block_row);

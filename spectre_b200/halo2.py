@@ -483,6 +483,21 @@ class ParamsKZG:
         return cls(backend, k, h)
 
     @classmethod
+    def from_bases(cls, backend, bases):
+        """Any n bases kept resident (spb_bases_upload): `multiexp(scalars)` is then best_multiexp(scalars, bases[:len(scalars)])
+        without the 64 B x n upload spb_msm_raw pays per call. Only the monomial-basis slot of the handle is set."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        h = ctypes.c_void_p()
+        backend.check(backend.lib.spb_bases_upload(backend.ctx, _p(bases), ctypes.c_size_t(bases.shape[0]), ctypes.byref(h)), "spb_bases_upload")
+        obj = cls(backend, max(0, (bases.shape[0] - 1).bit_length()), h)
+        obj.n = bases.shape[0]
+        return obj
+
+    def multiexp(self, scalars):
+        """best_multiexp(scalars, the resident bases[:len(scalars)])"""
+        return self._commit(BASIS_G, scalars)
+
+    @classmethod
     def read(cls, backend, path):
         """ParamsKZG::read(reader) for SerdeFormat::RawBytes (the params/kzg_bn254_{k}.srs cache of gen_srs)."""
         h = ctypes.c_void_p()

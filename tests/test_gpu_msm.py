@@ -358,3 +358,19 @@ def test_counting_sort_groups_repeated_digits_only_when_neighbours_repeat(be, or
         assert np.array_equal(affine_of(orc, be.best_multiexp(sc[:m], points[:m])), affine_of(orc, orc.best_multiexp(sc[:m], points[:m]))), m
     tabled = ParamsKZG.from_parts(be, k, g_lagrange=points[:n]).precompute()
     assert np.array_equal(affine_of(orc, tabled.commit_lagrange(sc)), want)
+
+
+@pytest.mark.parametrize("n", [1, 1000, 5000, (1 << 13) + 17])
+def test_resident_bases_of_any_length(be, orc, points, n):
+    """spb_bases_upload: bases of any length stay resident, spb_msm against them is best_multiexp without the per-call upload of
+    spb_msm_raw -- same points, with and without window tables, also for a prefix of the bases."""
+    from spectre_b200.halo2 import ParamsKZG
+    sc = orc.fr_random_chacha(n, 0xba5e + n)
+    want = affine_of(orc, orc.best_multiexp(sc, points[:n]))
+    res = ParamsKZG.from_bases(be, points[:n])
+    assert np.array_equal(affine_of(orc, res.multiexp(sc)), want)
+    assert np.array_equal(affine_of(orc, be.best_multiexp(sc, points[:n])), want)
+    m = max(1, n // 3)
+    assert np.array_equal(affine_of(orc, res.multiexp(sc[:m])), affine_of(orc, orc.best_multiexp(sc[:m], points[:m])))
+    res.precompute()
+    assert np.array_equal(affine_of(orc, res.multiexp(sc)), want)
