@@ -97,6 +97,7 @@ int ntt_multi_host(spb_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, const Fr
 int dev_grand_product(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, Fr* dz, const Fr& init);  // z[i] = init * prod_{j<i} a[j]
 int dev_kate_division(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, const Fr& b, Fr* dq);
 int dev_batch_invert(spb_ctx* ctx, DeviceState& d, Fr* da, size_t n);
+int dev_product_enqueue(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, Fr** d_total);  // *d_total: one Fr on device d, valid after the enqueued work
 int dev_eval_polynomial(spb_ctx* ctx, DeviceState& d, const Fr* dp, size_t n, const Fr& x, Fr* out_host);  // synchronises
 
 // ---- host field helpers (64-bit path) ----

@@ -433,6 +433,7 @@ static int srs_downsize_locked(spb_ctx* ctx, const spb_srs* srs, uint32_t k, spb
 }
 int spb_srs_downsize(spb_ctx* ctx, const spb_srs* srs, uint32_t k, spb_srs** out) {
   if (!ctx || !srs || !out || k > srs->k) return SPB_ERR_ARG;
+  if (srs->n != ((size_t)1 << srs->k)) return set_error(ctx, SPB_ERR_STATE, "spb_srs_downsize: the handle holds %zu plain bases (spb_bases_upload), not a 2^k SRS", srs->n);
   if (srs->table_c) return set_error(ctx, SPB_ERR_STATE, "spb_srs_downsize: call before spb_srs_precompute (the table rows replaced the plain basis layout)");
   spb_srs* made = nullptr;
   int rc;
@@ -477,6 +478,7 @@ int spb_srs_read_file(spb_ctx* ctx, const char* path, spb_srs** out) {
 
 int spb_srs_write_file(spb_ctx* ctx, const spb_srs* srs, const char* path) {
   if (!ctx || !srs || !path) return SPB_ERR_ARG;
+  if (srs->n != ((size_t)1 << srs->k)) return set_error(ctx, SPB_ERR_STATE, "spb_srs_write_file: the handle holds %zu plain bases (spb_bases_upload), not a 2^k SRS", srs->n);
   if (srs->table_c) return set_error(ctx, SPB_ERR_STATE, "spb_srs_write_file: call before spb_srs_precompute (rows 1.. are derived data)");
   FILE* f = fopen(path, "wb");
   if (!f) return set_error(ctx, SPB_ERR_ARG, "spb_srs_write_file: cannot create %s", path);

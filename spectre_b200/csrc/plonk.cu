@@ -37,12 +37,14 @@ inline Fr fr_omega(uint32_t k) {
 
 // omega^i = omega^(256 * block) * omega^thread: one long power per block (thread 0), an 8-bit power per thread; the row
 // bodies are perm_terms_row / lookup_terms_row in quotient.cuh.
-__global__ void __launch_bounds__(256) perm_terms_kernel(PermTermArgs a, uint64_t n, Fr* num, Fr* den) {
+// rows [row_lo, row_hi) of the column (row_lo a multiple of 256); num / den receive them at local index row - row_lo
+__global__ void __launch_bounds__(256) perm_terms_kernel(PermTermArgs a, uint64_t row_lo, uint64_t row_hi, Fr* num, Fr* den) {
   __shared__ Fr block_base;
-  if (threadIdx.x == 0) block_base = fp_pow_u64(a.omega, blockIdx.x * (uint64_t)blockDim.x);
+  const uint64_t block_row = row_lo + blockIdx.x * (uint64_t)blockDim.x;
+  if (threadIdx.x == 0) block_base = fp_pow_u64(a.omega, block_row);
   __syncthreads();
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < n) perm_terms_row(a, i, fp_mul(block_base, fp_pow_u64(a.omega, threadIdx.x)), num, den);
+  uint64_t i = block_row + threadIdx.x;
+  if (i < row_hi) perm_terms_row(a, i, fp_mul(block_base, fp_pow_u64(a.omega, threadIdx.x)), num - row_lo, den - row_lo);
 }
 __global__ void __launch_bounds__(256) lookup_terms_kernel(const Fr* ci, const Fr* ct, const Fr* pi, const Fr* pt, Fr beta, Fr gamma, uint64_t n, Fr* num, Fr* den) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -76,16 +78,77 @@ __global__ void sub_small_kernel(Fr* a, SmallPoly s) {
 
 namespace {
 
-// z[0] = init, z[i+1] = z[i] * num[i] / den[i]; num/den are consumed. Then the last n_blinds entries <- blinds and
-// *tail_out <- z[n - n_blinds - 1] (synchronises).
-int fraction_product(spb_ctx* ctx, DeviceState& d, Fr* num, Fr* den, size_t n, const Fr& init, const spb_fr* blinds, uint32_t n_blinds, Fr* dz, Fr* tail_out) {
-  SPB_TRY(dev_batch_invert(ctx, d, den, n));
-  frac_mul_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(num, den, n);
-  ctx->n_kernel_launches++;
-  SPB_TRY(dev_grand_product(ctx, d, num, n, dz, init));
-  if (n_blinds) SPB_CUDA(ctx, cudaMemcpyAsync(dz + (n - n_blinds), blinds, (size_t)n_blinds * 32, cudaMemcpyHostToDevice, d.stream));
-  if (tail_out) SPB_CUDA(ctx, cudaMemcpyAsync(tail_out, dz + (n - n_blinds - 1), 32, cudaMemcpyDeviceToHost, d.stream));
-  SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+// Row ranges of one grand-product column over the devices of the context (SURVEY.md 8e "grand product ... one all-gather of G
+// partial products + local fix-up"): multiples of 256 rows, one range per device; a single range when the context has one device,
+// no peer access, or the column is short (launch-bound; tests lower the threshold with SPB_SHARD_MIN_ROWS).
+struct ProdRange { int dev_index; size_t lo, hi; };
+std::vector<ProdRange> product_ranges(spb_ctx* ctx, size_t n) {
+  std::vector<ProdRange> v;
+  const size_t D = ctx->dev.size();
+  size_t min_rows = (size_t)1 << 16;
+  if (const char* e = getenv("SPB_SHARD_MIN_ROWS")) { long long m = atoll(e); if (m >= 256) min_rows = (size_t)m; }
+  if (D > 1 && ctx->peer_access && n >= min_rows) {
+    const size_t per = ((n + D - 1) / D + 255) / 256 * 256;
+    for (size_t i = 0; i < D; i++) { size_t lo = per * i, hi = lo + per < n ? lo + per : n; if (lo < hi) v.push_back(ProdRange{(int)i, lo, hi}); }
+  } else {
+    v.push_back(ProdRange{0, 0, n});
+  }
+  return v;
+}
+
+// z[0] = init, z[i+1] = z[i] * num[i] / den[i] over the n rows of one column, then the last n_blinds entries <- blinds and
+// *tail_out <- z[n - n_blinds - 1] (synchronises). `terms(d, lo, cnt, num, den)` enqueues on d.stream the kernel that writes the
+// cnt numerators / denominators of rows lo.. into the device-local buffers.
+// One device: terms, chunked batch inversion, product pass, chunked scan. Several devices (row ranges): every device does the
+// same on its range in its own HBM, reading the column inputs from the first device over NVLink; the 32-byte range totals are the
+// ONE exchange (through the host: G - 1 field products give every range its seed); the seeded scans then write their slice of z
+// straight into the caller's buffer on the first device. Bit-identical to the one-device scan (exact field arithmetic).
+template <class Terms>
+int fraction_product(spb_ctx* ctx, size_t n, const Terms& terms, const Fr& init, const spb_fr* blinds, uint32_t n_blinds, Fr* dz, Fr* tail_out) {
+  DeviceState& d0 = ctx->dev[0];
+  const std::vector<ProdRange> ranges = product_ranges(ctx, n);
+  const size_t G = ranges.size();
+  std::vector<Fr*> nums(G, nullptr), dtot(G, nullptr);
+  if (G > 1) { SPB_CUDA(ctx, cudaSetDevice(d0.device)); SPB_CUDA(ctx, cudaEventRecord(d0.dep_ev, d0.stream)); }   // the caller's inputs are ordered on d0.stream
+  for (size_t r = 0; r < G; r++) {
+    DeviceState& d = ctx->dev[ranges[r].dev_index];
+    const size_t cnt = ranges[r].hi - ranges[r].lo;
+    SPB_CUDA(ctx, cudaSetDevice(d.device));
+    if (ranges[r].dev_index != 0) SPB_CUDA(ctx, cudaStreamWaitEvent(d.stream, d0.dep_ev, 0));
+    Fr* num = (Fr*)slot(ctx, d, "plonk_num", cnt * 32); Fr* den = (Fr*)slot(ctx, d, "plonk_den", cnt * 32);
+    if (!num || !den) return SPB_ERR_OOM;
+    nums[r] = num;
+    terms(d, ranges[r].lo, cnt, num, den);
+    SPB_CUDA(ctx, cudaGetLastError());
+    ctx->n_kernel_launches++;
+    SPB_TRY(dev_batch_invert(ctx, d, den, cnt));
+    frac_mul_kernel<<<nblk(cnt, 256), 256, 0, d.stream>>>(num, den, cnt);
+    ctx->n_kernel_launches++;
+    if (G > 1) SPB_TRY(dev_product_enqueue(ctx, d, num, cnt, &dtot[r]));
+  }
+  // seeds: seed_0 = init, seed_r = seed_{r-1} * total_{r-1}
+  std::vector<Fr> seed(G, init);
+  if (G > 1) {
+    std::vector<Fr> total(G);
+    for (size_t r = 0; r < G; r++) {
+      DeviceState& d = ctx->dev[ranges[r].dev_index];
+      SPB_CUDA(ctx, cudaSetDevice(d.device));
+      SPB_CUDA(ctx, cudaMemcpyAsync(&total[r], dtot[r], 32, cudaMemcpyDeviceToHost, d.stream));
+      SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    }
+    for (size_t r = 1; r < G; r++) seed[r] = fp_mul(seed[r - 1], total[r - 1]);
+  }
+  for (size_t r = 0; r < G; r++) {
+    DeviceState& d = ctx->dev[ranges[r].dev_index];
+    SPB_CUDA(ctx, cudaSetDevice(d.device));
+    SPB_TRY(dev_grand_product(ctx, d, nums[r], ranges[r].hi - ranges[r].lo, dz + ranges[r].lo, seed[r]));   // peer store into the first device's z
+    if (ranges[r].dev_index != 0) { SPB_CUDA(ctx, cudaEventRecord(d.dep_ev, d.stream)); }
+  }
+  SPB_CUDA(ctx, cudaSetDevice(d0.device));
+  for (size_t r = 0; r < G; r++) if (ranges[r].dev_index != 0) SPB_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->dev[ranges[r].dev_index].dep_ev, 0));
+  if (n_blinds) SPB_CUDA(ctx, cudaMemcpyAsync(dz + (n - n_blinds), blinds, (size_t)n_blinds * 32, cudaMemcpyHostToDevice, d0.stream));
+  if (tail_out) SPB_CUDA(ctx, cudaMemcpyAsync(tail_out, dz + (n - n_blinds - 1), 32, cudaMemcpyDeviceToHost, d0.stream));
+  SPB_CUDA(ctx, cudaStreamSynchronize(d0.stream));
   return 0;
 }
 
@@ -184,13 +247,11 @@ int spb_permutation_product_dev(spb_ctx* ctx, uint32_t k, const spb_fr* const* d
   for (uint32_t c = 0; c < n_cols; c++) { a.values[c] = (const Fr*)d_values[c]; a.sigma[c] = (const Fr*)d_sigma[c]; }
   a.n_cols = n_cols; a.beta = fr_load(beta); a.gamma = fr_load(gamma); a.delta = fr_delta(); a.omega = fr_omega(k);
   a.delta_start = fp_mul(a.beta, fp_pow_u64(a.delta, first_col));
-  Fr* num = (Fr*)slot(ctx, d, "plonk_num", n * 32); Fr* den = (Fr*)slot(ctx, d, "plonk_den", n * 32);
-  if (!num || !den) return SPB_ERR_OOM;
-  perm_terms_kernel<<<nblk(n, 256), 256, 0, d.stream>>>(a, n, num, den);
-  SPB_CUDA(ctx, cudaGetLastError());
-  ctx->n_kernel_launches++;
   Fr tail;
-  SPB_TRY(fraction_product(ctx, d, num, den, n, fr_load(last_z), blinds, n_blinds, (Fr*)d_z, &tail));
+  auto terms = [&](DeviceState& dv, size_t lo, size_t cnt, Fr* num, Fr* den) {
+    perm_terms_kernel<<<nblk(cnt, 256), 256, 0, dv.stream>>>(a, lo, lo + cnt, num, den);
+  };
+  SPB_TRY(fraction_product(ctx, n, terms, fr_load(last_z), blinds, n_blinds, (Fr*)d_z, &tail));
   memcpy(last_z, &tail, 32);
   return 0;
 }
@@ -202,13 +263,12 @@ int spb_lookup_product_dev(spb_ctx* ctx, size_t n, const spb_fr* d_compressed_in
     return set_error(ctx, SPB_ERR_ARG, "spb_lookup_product_dev: null argument");
   if (n == 0 || (size_t)n_blinds + 1 > n) return set_error(ctx, SPB_ERR_ARG, "spb_lookup_product_dev: more blinding rows than rows");
   SPB_ENTER(ctx);
-  Fr* num = (Fr*)slot(ctx, d, "plonk_num", n * 32); Fr* den = (Fr*)slot(ctx, d, "plonk_den", n * 32);
-  if (!num || !den) return SPB_ERR_OOM;
-  lookup_terms_kernel<<<nblk(n, 256), 256, 0, d.stream>>>((const Fr*)d_compressed_input, (const Fr*)d_compressed_table, (const Fr*)d_permuted_input,
-                                                          (const Fr*)d_permuted_table, fr_load(beta), fr_load(gamma), n, num, den);
-  SPB_CUDA(ctx, cudaGetLastError());
-  ctx->n_kernel_launches++;
-  return fraction_product(ctx, d, num, den, n, fp_one<FrParams>(), blinds, n_blinds, (Fr*)d_z, nullptr);
+  const Fr b = fr_load(beta), g = fr_load(gamma);
+  auto terms = [&](DeviceState& dv, size_t lo, size_t cnt, Fr* num, Fr* den) {
+    lookup_terms_kernel<<<nblk(cnt, 256), 256, 0, dv.stream>>>((const Fr*)d_compressed_input + lo, (const Fr*)d_compressed_table + lo, (const Fr*)d_permuted_input + lo,
+                                                              (const Fr*)d_permuted_table + lo, b, g, cnt, num, den);
+  };
+  return fraction_product(ctx, n, terms, fp_one<FrParams>(), blinds, n_blinds, (Fr*)d_z, nullptr);
 }
 
 int spb_weighted_sum_dev(spb_ctx* ctx, const spb_fr* const* d_polys, const spb_fr* weights, size_t count, spb_fr* d_out, size_t n) {

@@ -231,6 +231,20 @@ int dev_grand_product(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, Fr* 
   return 0;
 }
 
+// product of da[0..n) -> *d_total (one Fr in device memory of d, in the slot "poly_total"); enqueue only
+int dev_product_enqueue(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, Fr** d_total) {
+  size_t m = (n + kScanChunk - 1) / kScanChunk;
+  Fr* dp = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32);
+  Fr* dt = (Fr*)slot(ctx, d, "poly_total", 32);
+  if (!dp || !dt) return SPB_ERR_OOM;
+  chunk_product_kernel<<<nblk(m, 128), 128, 0, d.stream>>>(da, n, dp);
+  total_product_kernel<<<1, 1024, 0, d.stream>>>(dp, m, dt);
+  SPB_CUDA(ctx, cudaGetLastError());
+  ctx->n_kernel_launches += 2;
+  *d_total = dt;
+  return 0;
+}
+
 int dev_kate_division(spb_ctx* ctx, DeviceState& d, const Fr* da, size_t n, const Fr& bb, Fr* dq) {
   size_t nq = n - 1, m = (nq + kScanChunk - 1) / kScanChunk;
   Fr* dh = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32);
@@ -441,13 +455,9 @@ int spb_product_dev(spb_ctx* ctx, const spb_fr* d_a, size_t n, spb_fr* out) {
   SPB_ENTER(ctx);
   Fr total = fp_one<FrParams>();
   if (n) {
-    size_t m = (n + kScanChunk - 1) / kScanChunk;
-    Fr* dp = (Fr*)slot(ctx, d, "poly_partial", 2 * m * 32 + 32);
-    if (!dp) return SPB_ERR_OOM;
-    chunk_product_kernel<<<nblk(m, 128), 128, 0, d.stream>>>((const Fr*)d_a, n, dp);
-    total_product_kernel<<<1, 1024, 0, d.stream>>>(dp, m, dp + 2 * m);
-    ctx->n_kernel_launches += 2;
-    SPB_CUDA(ctx, cudaMemcpyAsync(&total, dp + 2 * m, 32, cudaMemcpyDeviceToHost, d.stream));
+    Fr* dt = nullptr;
+    SPB_TRY(dev_product_enqueue(ctx, d, (const Fr*)d_a, n, &dt));
+    SPB_CUDA(ctx, cudaMemcpyAsync(&total, dt, 32, cudaMemcpyDeviceToHost, d.stream));
     SPB_CUDA(ctx, cudaStreamSynchronize(d.stream));
   }
   memcpy(out, &total, 32);

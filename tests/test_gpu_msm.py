@@ -374,3 +374,22 @@ def test_resident_bases_of_any_length(be, orc, points, n):
     assert np.array_equal(affine_of(orc, res.multiexp(sc[:m])), affine_of(orc, orc.best_multiexp(sc[:m], points[:m])))
     res.precompute()
     assert np.array_equal(affine_of(orc, res.multiexp(sc)), want)
+
+
+def test_plain_bases_handle_rejects_srs_only_operations(be, orc, points, tmp_path):
+    """A spb_bases_upload handle is not a 2^k SRS: downsize / write (which assume g[2^k] and g_lagrange) fail with an error text,
+    more scalars than bases are refused, and a quotient pass over a size that is not a power of two is refused at the boundary."""
+    import torch
+    from spectre_b200.halo2 import BackendError, ParamsKZG
+    res = ParamsKZG.from_bases(be, points[:1000])
+    with pytest.raises(BackendError, match="plain bases"):
+        res.downsize(3)
+    with pytest.raises(BackendError, match="plain bases"):
+        res.write(str(tmp_path / "x.srs"))
+    with pytest.raises((BackendError, AssertionError)):
+        res.multiexp(orc.fr_random_chacha(1001, 3))
+    dev = torch.device("cuda", 0)
+    z = torch.zeros((96, 4), dtype=torch.int64, device=dev)
+    with pytest.raises(BackendError, match="power of two"):
+        be.lookup_constraints_dev(z.data_ptr(), 96, 1, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(),
+                                  orc.fr([1])[0], orc.fr([2])[0], orc.fr([3])[0])

@@ -282,6 +282,45 @@ def test_proof_with_msm_sharded_over_two_devices_if_available(orc, monkeypatch):
         be2.close()
 
 
+@pytest.mark.parametrize("k", [10, 13])
+def test_grand_products_sharded_by_row_range_over_the_devices_if_available(orc, monkeypatch, k):
+    """SURVEY.md 8e "grand product": on a context over several devices the permutation and lookup product columns are built per
+    row range (terms, batch inversion and local products in each device's HBM, inputs read over NVLink), the range totals are the
+    one exchange, and the seeded scans write their slices of z into the first device's buffer: the columns -- blinding tail and
+    the chained last_z included -- equal the oracle's, i.e. the one-device scan, bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    monkeypatch.setenv("SPB_SHARD_MIN_ROWS", "256")
+    from spectre_b200 import halo2
+    be2 = halo2.Backend(list(range(min(torch.cuda.device_count(), 8))))
+    try:
+        n, n_cols, chunk, n_blinds = 1 << k, 5, 2, 5
+        values = [orc.fr_random_chacha(n, 100 + c) for c in range(n_cols)]
+        sigma = [orc.fr_random_chacha(n, 200 + c) for c in range(n_cols)]
+        values[0][3] = 0; sigma[0][5] = 0
+        beta, gamma = orc.fr_random_chacha(2, 300 + k)
+        dv, ds = [_dev(torch, a) for a in values], [_dev(torch, a) for a in sigma]
+        dz = torch.empty((n, 4), dtype=torch.int64, device="cuda:0")
+        last_o = last_g = orc.fr([1])[0]
+        for s_, lo in enumerate(range(0, n_cols, chunk)):
+            hi = min(lo + chunk, n_cols)
+            blinds = orc.fr_random_chacha(n_blinds, 400 + s_).reshape(-1, 4)
+            z_want, last_o = orc.permutation_product(k, values[lo:hi], sigma[lo:hi], lo, beta, gamma, blinds, last_o)
+            last_g = be2.permutation_product_dev(k, [t.data_ptr() for t in dv[lo:hi]], [t.data_ptr() for t in ds[lo:hi]], lo, beta, gamma, blinds, last_g, dz.data_ptr())
+            assert np.array_equal(_host(dz), z_want)
+            assert np.array_equal(last_g, last_o.reshape(4))
+        arrs = [orc.fr_random_chacha(n, 500 + i) for i in range(4)]
+        arrs[3][9] = orc.fr([-orc.fr_ints(gamma.reshape(1, 4))[0]])[0]
+        blinds = orc.fr_random_chacha(n_blinds, 602).reshape(-1, 4)
+        d = [_dev(torch, a) for a in arrs]
+        be2.lookup_product_dev(n, *[t.data_ptr() for t in d], beta, gamma, blinds, dz.data_ptr())
+        assert np.array_equal(_host(dz), orc.lookup_product(*arrs, beta, gamma, blinds))
+    finally:
+        torch.cuda.synchronize()
+        be2.close()
+
+
 def test_lookup_violation_is_reported_like_upstream(be, orc):
     """an advice value outside the table: permute_expression_pair fails (upstream: Error::ConstraintSystemFailure) and
     create_proof raises instead of producing a proof"""
