@@ -27,6 +27,16 @@ struct NttTables {
   Fr* tw_full = nullptr;  // 2^k (optional)
 };
 
+// One MSM lane of a device: own stream, workspace slots (named "...#lane"), events and pinned result area. Consecutive MSMs of a
+// batch cycle over the lanes so the latency-bound tail of one overlaps the sort and accumulation of the next (msm.cu).
+struct MsmLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* pinned = nullptr;
+  bool ready = false;
+};
+static const int kMaxMsmLanes = 4;
+
 struct DeviceState {
   int device = 0;
   int sm_count = 0;
@@ -35,6 +45,7 @@ struct DeviceState {
   cudaEvent_t dep_ev = nullptr;  // recorded on `stream` when other streams (MSM lanes, peer devices) must wait for it
   cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // MSM stage boundaries
   std::map<std::string, DevBuf> slots;
+  MsmLane lanes[kMaxMsmLanes];   // created on first use, released with the context (all access under the context lock)
   std::vector<NttTables> ntt_tables;
   void* pinned = nullptr;  // small pinned staging area for results
   size_t pinned_cap = 0;

@@ -25,20 +25,10 @@ struct spb_srs {
 
 namespace spb {
 
-// Two independent lanes per device (own stream, workspace slots, pinned result area): consecutive MSMs of a batch
-// alternate lanes so the latency-bound tail of one (stitch / running sums / host Horner) overlaps the sort and
-// accumulation of the next.
-struct Lane {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  void* pinned = nullptr;
-  bool ready = false;
-};
-static std::map<std::pair<spb_ctx*, int>, std::vector<Lane>> g_lanes;   // process-wide: guarded by g_lanes_mu
-static std::mutex g_lanes_mu;
+// The lanes of a device (common.cuh: MsmLane) live in its DeviceState, i.e. in the context: nothing here is process-wide.
+typedef MsmLane Lane;
 static const size_t kLanePinnedBytes = 256 * 1024;  // window partials of one MSM (<= 128 windows x a few points)
-
-static const int kMaxLanes = 4;
+static const int kMaxLanes = kMaxMsmLanes;
 // lanes a batch cycles through: 3 by default -- while one MSM accumulates, the latency-bound reduction tail of the previous one
 // and the sort of the next one fill the gaps (measured 2^20, ms per MSM: 1 lane 3.36, 2 lanes 2.95, 3 lanes 2.84); SPB_MSM_LANES=1..4
 static int lane_count() {
@@ -46,11 +36,9 @@ static int lane_count() {
   if (!v) { const char* e = getenv("SPB_MSM_LANES"); v = e ? atoi(e) : 3; if (v < 1) v = 1; if (v > kMaxLanes) v = kMaxLanes; }
   return v;
 }
+// call with the context lock held (every entry point that runs an MSM holds it)
 static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
-  std::lock_guard<std::mutex> lk(g_lanes_mu);
-  auto& v = g_lanes[std::make_pair(ctx, dev_index)];
-  if (v.size() < (size_t)kMaxLanes) v.resize(kMaxLanes);
-  Lane& l = v[lane_index];
+  Lane& l = ctx->dev[dev_index].lanes[lane_index];
   if (!l.ready) {
     SPB_CUDA(ctx, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 9; i++) SPB_CUDA(ctx, cudaEventCreate(&l.ev[i]));
@@ -62,18 +50,16 @@ static int get_lane(spb_ctx* ctx, int dev_index, int lane_index, Lane** out) {
 }
 
 void msm_release_ctx(spb_ctx* ctx) {
-  std::lock_guard<std::mutex> lk(g_lanes_mu);
-  for (auto it = g_lanes.begin(); it != g_lanes.end();) {
-    if (it->first.first != ctx) { ++it; continue; }
-    cudaSetDevice(ctx->dev[it->first.second].device);
-    for (auto& l : it->second) {
+  for (auto& d : ctx->dev) {
+    cudaSetDevice(d.device);
+    for (auto& l : d.lanes) {
       if (!l.ready) continue;
       cudaStreamSynchronize(l.stream);
       for (int i = 0; i < 9; i++) cudaEventDestroy(l.ev[i]);
       cudaFreeHost(l.pinned);
       cudaStreamDestroy(l.stream);
+      l = Lane();
     }
-    it = g_lanes.erase(it);
   }
 }
 
