@@ -44,6 +44,27 @@ assert np.array_equal(be.batch_invert(p), orc.batch_invert(p))
 assert np.array_equal(be.eval_polynomial(p, x), orc.eval_polynomial(p, x))
 assert np.array_equal(be.kate_division(p, x), orc.kate_division(p, x))
 be.grand_product(p); be.vec_mul(p, p); be.vec_axpy(p, x, p); be.vec_scale(p, x)
+# round 2: device ChaCha20 Fr::random, resident plain bases, ParamsKZG::downsize (group inverse DFT), the many-query evaluation,
+# a giant bucket (block-wide chain reduction) and a huge chain (grid-wide reduction), the 96-entry chunk path is size-gated and
+# covered by the 2^22+ parity tests instead
+import torch  # noqa: E402
+t = torch.empty((777, 4), dtype=torch.int64, device="cuda")
+be.fr_random_chacha_dev(0x5eed, (1 << 32) - 3, t.data_ptr(), 777)
+assert np.array_equal(t.cpu().numpy().view(np.uint64), orc.fr_random_chacha(777, 0x5eed, (1 << 32) - 3))
+pts = orc.g1_fixed_base_mul(orc.fr_random_chacha(300, 21))
+sc = orc.fr_random_chacha(300, 22)
+assert np.array_equal(orc.g1_to_affine(halo2.ParamsKZG.from_bases(be, pts).multiexp(sc)), orc.g1_to_affine(orc.best_multiexp(sc, pts)))
+small = halo2.ParamsKZG.setup(be, 6, orc.srs_tau()).downsize(4)
+q = orc.fr_random_chacha(16, 23)
+assert np.array_equal(orc.g1_to_affine(small.commit_lagrange(q)), orc.commit_lagrange_known_tau(4, q))
+dp = [torch.from_numpy(orc.fr_random_chacha(1000, 30 + i).view(np.int64)).cuda() for i in range(3)]
+xs = orc.fr_random_chacha(3, 33)
+ev = be.eval_polynomial_many_dev([x_.data_ptr() for x_ in dp], 1000, xs)
+for i in range(3):
+    assert np.array_equal(ev[i], orc.eval_polynomial(dp[i].cpu().numpy().view(np.uint64), xs[i]))
+ones = np.repeat(orc.fr([1]), 1 << 13, axis=0)
+gp = orc.g1_fixed_base_mul(orc.fr_random_chacha(1 << 13, 40))
+assert np.array_equal(orc.g1_to_affine(be.best_multiexp(ones, gp)), orc.g1_to_affine(orc.best_multiexp(ones, gp)))
 # one whole proof of the multi-column shape: graph / permutation / lookup constraint kernels, the lookup sort, the argument
 # provers and the SHPLONK opener (device buffers through torch), byte-compared with the oracle-engine proof
 from spectre_b200 import circuits, plonk  # noqa: E402
