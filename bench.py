@@ -272,7 +272,7 @@ def main():
         return spb_dist.fold_partials(partials, world, device=dev)
 
     def run_dev(first, steps):
-        """`steps` steps of MSMS_PER_STEP commitments each through the batch entry point (two stream lanes), scalars in HBM"""
+        """`steps` steps of MSMS_PER_STEP commitments each through the batch entry point (three stream lanes), scalars in HBM"""
         for s in range(steps):
             ptrs = [dev_sets[(first + s * MSMS_PER_STEP + i) % N_SCALAR_SETS].data_ptr() for i in range(MSMS_PER_STEP)]
             last["dev"] = (first + s * MSMS_PER_STEP, fold(params.commit_batch_dev(halo2.BASIS_G_LAGRANGE, ptrs, N_PAIRS)))
@@ -450,7 +450,7 @@ def main():
 
     peaks, peak_src = measured_peaks()
     c, W = be.msm_geometry(N_PAIRS, tables=not args.no_tables)
-    # Launch duration of the dominant kernel: CUDA events on the lane stream it runs on. Inside the timed region two lanes are in
+    # Launch duration of the dominant kernel: CUDA events on the lane stream it runs on. Inside the timed region three lanes are in
     # flight, so a launch's events also span the slices the OTHER lane's kernels got on the same SMs (two accumulate kernels
     # interleave: each takes ~2x as long and two finish per interval); the launch duration that states the GPU's rate on this
     # kernel is the one with the device to itself, measured by the same events on the 4 single-MSM calls above.

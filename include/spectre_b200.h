@@ -123,8 +123,9 @@ int spb_msm(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* scalars, 
 /* same with the scalars already resident on device 0 of the context */
 int spb_msm_dev(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* d_scalars, size_t n, spb_g1* out);
 /* `count` MSMs of n scalars each against the same resident basis (create_proof commits its advice / permutation /
- * lookup columns back to back against g_lagrange). Consecutive MSMs alternate between two stream lanes so the
- * latency-bound tail of one overlaps the sort + accumulation of the next; out[i] belongs to scalars[i]. */
+ * lookup columns back to back against g_lagrange). Consecutive MSMs cycle over three stream lanes (SPB_MSM_LANES) so the
+ * latency-bound tail of one and the sort of the next overlap the accumulation of the one in between; out[i] belongs to
+ * scalars[i]. */
 int spb_msm_batch(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* const* scalars, size_t n, size_t count, spb_g1* out);
 int spb_msm_batch_dev(spb_ctx* ctx, const spb_srs* srs, int basis, const spb_fr* const* d_scalars, size_t n, size_t count, spb_g1* out);
 /* Precompute the 2^(c*j) multiples of the resident bases (W x the basis memory, one-time). Afterwards every MSM on

@@ -552,7 +552,7 @@ class ParamsKZG:
         return self
 
     def commit_batch(self, basis, polys):
-        """count commitments against one basis, pipelined on two stream lanes. polys: list of (n,4) host arrays."""
+        """count commitments against one basis, pipelined over the library's stream lanes. polys: list of (n,4) host arrays."""
         polys = [_fr_array(p) for p in polys]
         n = polys[0].shape[0]
         assert all(p.shape[0] == n for p in polys) and n <= self.n
