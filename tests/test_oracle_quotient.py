@@ -1,5 +1,6 @@
 """CPU: the oracle's evaluate_h restatement against plain-Python integer arithmetic on tiny systems."""
 import numpy as np
+import pytest
 
 from tests import pyref
 from tests.quotient_common import ADD, MUL, HORNER, K_ADVICE, K_FIXED, K_INTER, K_PREV, K_Y, K_CONST
@@ -113,3 +114,49 @@ def test_scheduled_program_is_the_same_function_with_few_live_intermediates(orc)
     out = np.zeros(64, np.uint32); cnt, slots, nc = ctypes.c_size_t(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
     assert halo2.load_library().spb_test_schedule_program(twice.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(twice)), ctypes.c_uint32(2),
                                                           out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(64), ctypes.byref(cnt), ctypes.byref(slots), ctypes.byref(nc)) != 0
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_scheduler_on_random_programs(orc, seed):
+    """Random flat programs (every op code, Horners of 0..5 parts whose parts are produced out of order, repeated sources,
+    PreviousValue, dead calculations, results that are never read): the rescheduled words evaluate to the same value on every row
+    as the original ones, use no more slots than there were intermediates, and the row's result is still the last calculation's."""
+    rng = np.random.default_rng(1000 + seed)
+    n, nf, na = 32, 3, 4
+    fixed = [orc.fr_random_chacha(n, 800 + i) for i in range(nf)]
+    advice = [orc.fr_random_chacha(n, 810 + i) for i in range(na)]
+    inst = [orc.fr_random_chacha(n, 820)]
+    constants = orc.fr([0, 1, 7, 2 ** 200 + 5])
+    rotations = np.array([0, 1, -1, 3], dtype=np.int32)
+    bgty = orc.fr_random_chacha(4, 830 + seed)
+    prev = orc.fr_random_chacha(n, 840 + seed)
+    ch = orc.fr_random_chacha(2, 850)
+    ncalc = int(rng.integers(1, 40))
+    words = []
+
+    def source(c):
+        kind = int(rng.choice([0, 1, 1, 1, 2, 3, 3, 4, 5, 6, 7, 8, 9, 10])) if c else int(rng.choice([0, 2, 3, 4, 5, 6, 9, 10]))
+        if kind == 0: return [0, int(rng.integers(0, 4))]
+        if kind == 1: return [1, int(rng.integers(0, c))]
+        if kind == 2: return [2, int(rng.integers(0, nf)) | int(rng.integers(0, 4)) << 16]
+        if kind == 3: return [3, int(rng.integers(0, na)) | int(rng.integers(0, 4)) << 16]
+        if kind == 4: return [4, 0 | int(rng.integers(0, 4)) << 16]
+        if kind == 5: return [5, int(rng.integers(0, 2))]
+        return [kind, 0]
+    for c in range(ncalc):
+        op = int(rng.choice([0, 1, 2, 2, 3, 4, 5, 6, 6, 7]))
+        if op <= 2:
+            words += [op, c] + source(c) + source(c)
+        elif op == 6:
+            parts = int(rng.integers(0, 6))
+            words += [6 | parts << 8, c] + source(c) + source(c)
+            for _ in range(parts):
+                words += source(c)
+        else:
+            words += [op, c] + source(c)
+    prog = np.array(words, dtype=np.uint32)
+    new_words, slots, nc = _schedule(prog, ncalc)
+    assert slots <= ncalc and nc >= ncalc
+    want = orc.graph_evaluate(prog, ncalc, ncalc, constants, rotations, fixed, advice, inst, ch, bgty, prev, 1)
+    got = orc.graph_evaluate(new_words, nc, slots, constants, rotations, fixed, advice, inst, ch, bgty, prev, 1)
+    assert np.array_equal(got, want)
