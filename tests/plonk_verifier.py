@@ -46,13 +46,14 @@ def lagrange_evals(k, x, rows):
     return out
 
 
-def verify(cs, k, vk_digest, fixed_commitments, sigma_commitments, instances, proof, tau):
-    """True / raises AssertionError with the failing check."""
+def verify(cs, k, vk_digest, fixed_commitments, sigma_commitments, instances, proof, tau, transcript_read=EvmTranscriptRead):
+    """True / raises AssertionError with the failing check. transcript_read: the reading transcript class (Keccak EVM transcript by
+    default, spectre_b200.poseidon.PoseidonTranscriptRead for proofs made over the Poseidon transcript)."""
     n = 1 << k
     bf = cs.blinding_factors()
     usable = n - (bf + 1)
     w = pyref.omega(k)
-    T = EvmTranscriptRead(vk_digest, proof)
+    T = transcript_read(vk_digest, proof)
     for col in instances:
         for v in col:
             T.common_scalar(v)
