@@ -185,6 +185,107 @@ class EvmTranscriptWrite {
   std::vector<size_t> absorbed_;
 };
 
+// ---- Poseidon over Fr and the inner snark's transcript (the C++ twin of spectre_b200/poseidon.py) ---------------------------
+// Parameter generation (Grain LFSR -> round constants, Cauchy matrix) and permutation are pinned by the known-answer vector of the
+// Poseidon reference implementation (tests/test_cpp_prover.py checks this class against it through the Python twin); the sponge
+// framing and the transcript conventions are snark-verifier's as remembered and UNPINNED -- see the Python module's docstring.
+class PoseidonSpec {
+ public:
+  using U256 = hostfield::U256;
+  PoseidonSpec(uint32_t t, uint32_t r_f, uint32_t r_p, uint32_t field_bits = 254) : t_(t), r_f_(r_f), r_p_(r_p) {
+    const auto& P = hostfield::fr_params();
+    std::vector<int> bits;
+    auto put = [&](uint32_t v, int n) { for (int i = n - 1; i >= 0; i--) bits.push_back((v >> i) & 1); };
+    put(1, 2); put(0, 4); put(field_bits, 12); put(t, 12); put(r_f, 10); put(r_p, 10); for (int i = 0; i < 30; i++) bits.push_back(1);
+    size_t head = 0;                                                     // ring buffer of the 80-bit state
+    auto step = [&]() { int b = bits[(head + 62) % 80] ^ bits[(head + 51) % 80] ^ bits[(head + 38) % 80] ^ bits[(head + 23) % 80] ^ bits[(head + 13) % 80] ^ bits[head];
+                        bits[head] = b; head = (head + 1) % 80; return b; };
+    for (int i = 0; i < 160; i++) step();
+    auto out_bit = [&]() { int b = step(); while (b == 0) { step(); b = step(); } return step(); };
+    auto draw = [&]() { U256 v = {0, 0, 0, 0}; for (uint32_t i = 0; i < field_bits; i++) { v[3] = (v[3] << 1) | (v[2] >> 63); v[2] = (v[2] << 1) | (v[1] >> 63); v[1] = (v[1] << 1) | (v[0] >> 63); v[0] = (v[0] << 1) | (uint64_t)out_bit(); } return v; };
+    for (uint32_t r = 0; r < r_f + r_p; r++)
+      for (uint32_t i = 0; i < t; i++) { U256 v = draw(); while (hostfield::geq(v, P.mod)) v = draw(); constants_.push_back(hostfield::to_mont(P, v)); }
+    for (;;) {
+      std::vector<U256> xy;
+      for (uint32_t i = 0; i < 2 * t; i++) xy.push_back(hostfield::reduce(P, draw()));
+      bool ok = true;
+      for (size_t a = 0; a < xy.size() && ok; a++) for (size_t b = a + 1; b < xy.size(); b++) if (xy[a] == xy[b]) { ok = false; break; }
+      std::vector<U256> den;
+      for (uint32_t i = 0; i < t && ok; i++) for (uint32_t j = 0; j < t; j++) {
+        U256 d = hostfield::add(P, hostfield::to_mont(P, xy[i]), hostfield::to_mont(P, xy[t + j]));
+        if (!(d[0] | d[1] | d[2] | d[3])) { ok = false; break; }
+        den.push_back(d);
+      }
+      if (!ok) continue;
+      for (auto& d : den) mds_.push_back(hostfield::inv(P, d));
+      break;
+    }
+  }
+  // state: t Montgomery field elements
+  void permute(std::vector<U256>& s) const {
+    const auto& P = hostfield::fr_params();
+    const uint32_t half = r_f_ / 2;
+    auto pow5 = [&](const U256& x) { U256 x2 = hostfield::mul(P, x, x); return hostfield::mul(P, hostfield::mul(P, x2, x2), x); };
+    for (uint32_t rnd = 0; rnd < r_f_ + r_p_; rnd++) {
+      for (uint32_t i = 0; i < t_; i++) s[i] = hostfield::add(P, s[i], constants_[(size_t)rnd * t_ + i]);
+      if (rnd < half || rnd >= half + r_p_) { for (auto& x : s) x = pow5(x); } else s[0] = pow5(s[0]);
+      std::vector<U256> o(t_, U256{0, 0, 0, 0});
+      for (uint32_t i = 0; i < t_; i++) for (uint32_t j = 0; j < t_; j++) o[i] = hostfield::add(P, o[i], hostfield::mul(P, mds_[(size_t)i * t_ + j], s[j]));
+      s = o;
+    }
+  }
+  uint32_t t() const { return t_; }
+
+ private:
+  uint32_t t_, r_f_, r_p_;
+  std::vector<U256> constants_, mds_;   // Montgomery form
+};
+
+class PoseidonTranscriptWrite {
+ public:
+  using U256 = hostfield::U256;
+  explicit PoseidonTranscriptWrite(const U256& vk_digest, uint32_t t = 3, uint32_t r_f = 8, uint32_t r_p = 57) : spec_(t, r_f, r_p), rate_(t - 1) {
+    const auto& P = hostfield::fr_params();
+    state_.assign(t, U256{0, 0, 0, 0});
+    state_[0] = hostfield::to_mont(P, U256{0, 1, 0, 0});               // 2^64
+    common_scalar(vk_digest);                                             // VerifyingKey::hash_into
+  }
+  void common_scalar(const U256& v) { buf_.push_back(hostfield::to_mont(hostfield::fr_params(), hostfield::reduce(hostfield::fr_params(), v))); }
+  void common_ec_point(const U256& x, const U256& y) {
+    if (!(x[0] | x[1] | x[2] | x[3] | y[0] | y[1] | y[2] | y[3])) throw std::runtime_error("PoseidonTranscript cannot absorb the point at infinity");
+    common_scalar(x); common_scalar(y);                                   // Fq coordinates reduced into Fr
+  }
+  void write_scalar(const U256& v) { common_scalar(v); append_le(hostfield::reduce(hostfield::fr_params(), v), 0); }
+  void write_ec_point(const U256& x, const U256& y) { common_ec_point(x, y); append_le(x, (uint8_t)((y[0] & 1) << 7)); }   // compressed: parity of y in the top bit
+  U256 squeeze_challenge() {
+    const auto& P = hostfield::fr_params();
+    std::vector<U256> buf; buf.swap(buf_);
+    for (size_t i = 0; i < buf.size(); i += rate_) absorb(buf.data() + i, std::min<size_t>(rate_, buf.size() - i));
+    if (buf.size() % rate_ == 0) absorb(nullptr, 0);
+    buf_.push_back(state_[1]);                                             // the challenge is fed back
+    return hostfield::from_mont(P, state_[1]);
+  }
+  const std::vector<uint8_t>& proof() const { return proof_; }
+
+ private:
+  void absorb(const U256* chunk, size_t len) {
+    const auto& P = hostfield::fr_params();
+    for (size_t i = 0; i < len; i++) state_[1 + i] = hostfield::add(P, state_[1 + i], chunk[i]);
+    if (len < rate_) state_[1 + len] = hostfield::add(P, state_[1 + len], hostfield::from_u64(P, 1));
+    spec_.permute(state_);
+  }
+  void append_le(const U256& v, uint8_t top) {
+    uint8_t b[32];
+    for (int i = 0; i < 32; i++) b[i] = (uint8_t)(v[i / 8] >> (8 * (i % 8)));
+    b[31] |= top;
+    proof_.insert(proof_.end(), b, b + 32);
+  }
+  PoseidonSpec spec_;
+  size_t rate_;
+  std::vector<U256> state_, buf_;
+  std::vector<uint8_t> proof_;
+};
+
 
 // =====================================================================================================================
 // keygen_pk / create_proof over the C ABI (the C++ twin of spectre_b200/plonk.py; stage numbers as there)
@@ -663,8 +764,11 @@ inline std::vector<RotationSet> rotation_sets(const std::vector<OpenQuery>& quer
 // Engine::random_chacha) instead of `count` host draws followed by an upload; it stands for that one rng call.
 using Rng = std::function<void(size_t, Fr*)>;
 using BulkRng = std::function<Buffer(Engine&, size_t)>;
+// Transcript: EvmTranscriptWrite (the outer, EVM-verified proof) or PoseidonTranscriptWrite (the inner snark) -- any class with
+// common_scalar / write_scalar / write_ec_point / squeeze_challenge / proof().
+template <class Transcript>
 inline std::vector<uint8_t> create_proof(Engine& E, const ProvingKey& pk, const std::vector<std::vector<U256>>& instances, const std::vector<const Fr*>& advice_columns,
-                                         const Rng& rng, EvmTranscriptWrite& transcript, const BulkRng& bulk = nullptr) {
+                                         const Rng& rng, Transcript& transcript, const BulkRng& bulk = nullptr) {
   const ConstraintSystem& cs = pk.cs;
   const size_t n = pk.n, usable = pk.usable_rows;
   const uint32_t bf = pk.blinding_factors;

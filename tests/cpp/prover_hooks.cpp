@@ -27,4 +27,24 @@ size_t ph_transcript(const uint64_t* digest, const int* ops, size_t n_ops, const
   for (size_t i = 0; i < t.absorbed().size(); i++) absorbed[i] = t.absorbed()[i];
   return t.proof().size();
 }
+// Poseidon: permutation of `t` canonical elements in place; the transcript script as above (ops 0..3), over PoseidonTranscriptWrite
+void ph_poseidon_permute(uint32_t t, uint32_t r_f, uint32_t r_p, uint64_t* state) {
+  PoseidonSpec spec(t, r_f, r_p);
+  std::vector<U256> s;
+  for (uint32_t i = 0; i < t; i++) s.push_back(hostfield::to_mont(hostfield::fr_params(), ld(state + 4 * i)));
+  spec.permute(s);
+  for (uint32_t i = 0; i < t; i++) st(hostfield::from_mont(hostfield::fr_params(), s[i]), state + 4 * i);
+}
+size_t ph_poseidon_transcript(const uint64_t* digest, const int* ops, size_t n_ops, const uint64_t* vals, uint64_t* chal, uint8_t* proof) {
+  PoseidonTranscriptWrite t(ld(digest));
+  size_t v = 0, c = 0;
+  for (size_t i = 0; i < n_ops; i++) {
+    if (ops[i] == 0) t.common_scalar(ld(vals + 4 * v++));
+    else if (ops[i] == 1) t.write_scalar(ld(vals + 4 * v++));
+    else if (ops[i] == 2) { t.write_ec_point(ld(vals + 4 * v), ld(vals + 4 * v + 4)); v += 2; }
+    else st(t.squeeze_challenge(), chal + 4 * c++);
+  }
+  memcpy(proof, t.proof().data(), t.proof().size());
+  return t.proof().size();
+}
 }

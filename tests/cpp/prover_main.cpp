@@ -62,6 +62,7 @@ int main(int argc, char** argv) {
     std::ifstream meta(dir + "/meta.txt");
     std::string shape; uint32_t G = 0, L = 0, k = 0; U256 digest{}; std::vector<U256> inst; std::vector<std::pair<Cell, Cell>> copies; std::vector<size_t> rng_counts;
     std::string line;
+    bool poseidon = false;                                       // "transcript poseidon": the inner snark's transcript instead of the EVM one
     uint8_t chacha_seed[32] = {0}; bool have_chacha = false;   // the random polynomial from the device ChaCha20 stream instead of rng.bin
     while (std::getline(meta, line)) {
       std::istringstream is(line); std::string key; is >> key;
@@ -71,6 +72,7 @@ int main(int argc, char** argv) {
       else if (key == "instances") { std::string h; while (is >> h) inst.push_back(parse_hex(h)); }
       else if (key == "copy") { uint32_t c1, c2; uint64_t r1, r2; is >> c1 >> r1 >> c2 >> r2; copies.push_back({{c1, r1}, {c2, r2}}); }
       else if (key == "rng") { size_t c; while (is >> c) rng_counts.push_back(c); }
+      else if (key == "transcript") { std::string name; is >> name; poseidon = name == "poseidon"; }
       else if (key == "chacha_poly") { std::string h; is >> h; if (h.size() != 64) throw std::runtime_error("chacha_poly: 64 hex digits expected"); for (int i = 0; i < 32; i++) chacha_seed[i] = (uint8_t)std::stoul(h.substr(2 * i, 2), nullptr, 16); have_chacha = true; }
     }
     ConstraintSystem cs = shape == "aggregation" ? aggregation_shape() : halo2lib_shape(G, L);
@@ -112,11 +114,12 @@ int main(int argc, char** argv) {
       std::printf("keygen_ms %.3f\n", std::chrono::duration<double, std::milli>(t_k1 - t_k0).count());
       for (int rep = 0; rep < repeat; rep++) {
         call = 0; pos = 0;
-        EvmTranscriptWrite T(pk.vk_digest);
         auto t0 = std::chrono::steady_clock::now();
         BulkRng bulk = nullptr;
         if (have_chacha) bulk = [&](Engine& e, size_t count) { return e.random_chacha(chacha_seed, 0, count); };
-        std::vector<uint8_t> pr = create_proof(E, pk, {inst}, advice, rng, T, bulk);
+        std::vector<uint8_t> pr;
+        if (poseidon) { PoseidonTranscriptWrite T(pk.vk_digest); pr = create_proof(E, pk, {inst}, advice, rng, T, bulk); }
+        else { EvmTranscriptWrite T(pk.vk_digest); pr = create_proof(E, pk, {inst}, advice, rng, T, bulk); }
         std::printf("create_proof_ms %.3f\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         if (rep && pr != proof) throw std::runtime_error("repeated proof differs");
         proof = pr;

@@ -84,6 +84,44 @@ def test_keccak_and_transcript(hooks):
     assert list(absorbed[:len(T.absorbed)]) == T.absorbed
 
 
+def test_poseidon_permutation_and_transcript_twin(hooks):
+    """The C++ PoseidonSpec / PoseidonTranscriptWrite against spectre_b200/poseidon.py: the permutation for t = 3 (incl. the
+    reference implementation's known-answer vector) and t = 12, and a random transcript script (challenges and proof bytes)."""
+    from spectre_b200 import poseidon
+    state = np.stack([_u(v) for v in (0, 1, 2)])
+    hooks.ph_poseidon_permute(3, 8, 57, _p(state))
+    assert [_i(r) for r in state] == [0x115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a,
+                                      0x0fca49b798923ab0239de1c9e7a4a9a2210312b6a2f616d18b5a87f9b628ae29,
+                                      0x0e7ae82e40091e63cbd4f16a6d16310b3729d4b6e138fcf54110e2867045a30c]
+    rng = random.Random(12)
+    vals12 = [rng.randrange(pyref.R_MOD) for _ in range(12)]
+    state = np.stack([_u(v) for v in vals12])
+    hooks.ph_poseidon_permute(12, 8, 60, _p(state))
+    assert [_i(r) for r in state] == poseidon.Spec(12, 8, 60).permute(vals12)
+    digest = rng.randrange(pyref.R_MOD)
+    T = poseidon.PoseidonTranscriptWrite(digest)
+    ops, vals, chal = [], [], []
+    for step in range(70):
+        op = rng.choice([0, 1, 2, 3, 3])
+        ops.append(op)
+        if op == 0:
+            v = rng.randrange(pyref.R_MOD); vals.append(v); T.common_scalar(v)
+        elif op == 1:
+            v = rng.randrange(pyref.R_MOD); vals.append(v); T.write_scalar(v)
+        elif op == 2:
+            pt = pyref.ec_mul((1, 2), rng.randrange(1, pyref.R_MOD)); vals += [pt[0], pt[1]]; T.write_ec_point(pt)
+        else:
+            chal.append(T.squeeze_challenge())
+    ops_a = np.array(ops, dtype=np.int32)
+    vals_a = np.stack([_u(v) for v in vals])
+    chal_a = np.zeros((len(chal), 4), dtype=np.uint64)
+    proof = (ctypes.c_uint8 * 8192)()
+    hooks.ph_poseidon_transcript.restype = ctypes.c_size_t
+    n = hooks.ph_poseidon_transcript(_p(_u(digest)), _p(ops_a), ctypes.c_size_t(len(ops)), _p(vals_a), _p(chal_a), proof)
+    assert bytes(proof[:n]) == bytes(T.proof)
+    assert [_i(c) for c in chal_a] == chal
+
+
 # ---- the whole driver: C++ keygen + create_proof over the test-only ABI shim vs the Python driver on the oracle engine ------
 def _build_shim_and_main():
     from oracle import oracle as orc
@@ -115,8 +153,9 @@ class _RecordingRng:
         return out
 
 
-@pytest.mark.parametrize("shape,k,chacha_poly", [("aggregation", 7, None), ("halo2lib", 8, None), ("aggregation", 7, bytes(range(32)))])
-def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k, chacha_poly):
+@pytest.mark.parametrize("shape,k,chacha_poly,transcript", [("aggregation", 7, None, "evm"), ("halo2lib", 8, None, "evm"), ("aggregation", 7, bytes(range(32)), "evm"),
+                                                          ("halo2lib", 8, None, "poseidon")])
+def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k, chacha_poly, transcript):
     """include/spectre_b200_prover.hpp (keygen + create_proof in C++) over the test-only CPU shim of the C ABI produces the
     same VK commitments and the same proof bytes as spectre_b200/plonk.py on the oracle engine, from the same columns, copies
     and RNG stream -- also when the vanishing argument's random polynomial is drawn by the engine from a ChaCha20 seed
@@ -137,7 +176,11 @@ def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k, chacha_
     E = OracleEngine(k, cs.degree())
     pk = plonk.keygen(E, cs, k, fixed, copies, vk_digest=digest)
     rec = _RecordingRng(SeededRng(77), chacha_poly)
-    proof = plonk.create_proof(E, pk, [instances], adv, rec, EvmTranscriptWrite(pk.vk_digest))
+    if transcript == "poseidon":                                 # the inner snark's transcript: both drivers are transcript-agnostic
+        from spectre_b200.poseidon import PoseidonTranscriptWrite as Tw
+    else:
+        Tw = EvmTranscriptWrite
+    proof = plonk.create_proof(E, pk, [instances], adv, rec, Tw(pk.vk_digest))
     if chacha_poly is not None:
         assert (1 << k) not in [c.shape[0] for c in rec.calls]      # the n-row draw never went through the host stream
     d = str(tmp_path)
@@ -148,6 +191,7 @@ def test_cpp_driver_reproduces_the_python_proof(orc, tmp_path, shape, k, chacha_
         f.write("rng " + " ".join(str(c.shape[0]) for c in rec.calls) + "\n")
         if chacha_poly is not None:
             f.write("chacha_poly %s\n" % chacha_poly.hex())
+        f.write("transcript %s\n" % transcript)
     np.concatenate(fixed).tofile(os.path.join(d, "fixed.bin"))
     np.concatenate(adv).tofile(os.path.join(d, "advice.bin"))
     np.concatenate([c for c in rec.calls if c.shape[0]] or [np.zeros((0, 4), np.uint64)]).tofile(os.path.join(d, "rng.bin"))
