@@ -23,7 +23,8 @@
  * needed then) or be complete, i.e. the producing stream synchronised, before the call. The legacy default stream does
  * NOT order against spb_stream (it is created with cudaStreamNonBlocking).
  * Concurrency (Spectre's RPC `--concurrency N`, prover/src/prover.rs:114): one context serialises its calls; open one
- * context per concurrent proof on the same device(s) -- they share nothing but the GPU and may share one spb_srs.
+ * context per concurrent proof on the same device(s) -- they share nothing but the GPU; every context holds its own handles
+ * (tests/test_gpu_msm.py::test_two_contexts_prove_concurrently_on_one_device; one spb_srs used from two contexts is not exercised).
  * Return value: 0 = ok, negative = error (spb_last_error gives the text); nothing aborts or throws.
  * There is no CPU fallback inside the library: without a usable CUDA device spb_init fails.
  */
