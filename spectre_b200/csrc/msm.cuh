@@ -56,7 +56,10 @@ struct alignas(8) MsmEntry { uint32_t key, val; };
 // for lists beyond the L2 (kLongChunk) only pays when the list really is that long -- witness columns drop most of their
 // digits -- so every kernel that cuts the list derives the same effective length from the entry count on the device.
 static const uint32_t kLongChunk = 96, kShortChunk = 32;
-static const uint64_t kLongChunkMinEntries = 1ull << 24;
+#ifndef SPB_LONG_CHUNK_MIN_ENTRIES
+#define SPB_LONG_CHUNK_MIN_ENTRIES (1ull << 24)   // tests/hostemu lowers it to run the long-chunk path on CPU-sized inputs
+#endif
+static const uint64_t kLongChunkMinEntries = SPB_LONG_CHUNK_MIN_ENTRIES;
 SPB_HD uint32_t msm_effective_chunk(uint32_t L, uint64_t M) { return (L == kLongChunk && M < kLongChunkMinEntries) ? kShortChunk : L; }
 
 static const uint32_t kNoKey = 0xffffffffu;

@@ -116,3 +116,23 @@ def test_g_to_lagrange_of_the_seed0_srs(he, orc):
         out = np.empty((n, 8), dtype=np.uint64)
         he.he_g_to_lagrange(_p(out), _p(np.ascontiguousarray(g)), ctypes.c_uint32(k), _p(w_inv), _p(n_inv))
         assert np.array_equal(out, orc.srs_g_lagrange(k, 0, n)), k
+
+
+def test_long_chunks_are_chosen_from_the_real_entry_count(orc, points):
+    """msm_effective_chunk (msm.cuh): the host asks for the long chunk (96 entries) from the upper bound n * W, the kernels use it
+    only when the sorted list really has that many entries and fall back to 32 otherwise -- accumulate, stitch and the giant
+    path must agree on the same effective length. Built with the threshold lowered to 2000 entries: a uniform column (about
+    6000 entries: long chunks), a witness-like one (most digits dropped: short chunks) and a column of equal scalars (one
+    chain across every chunk) all give the oracle's point."""
+    he = _build("libhostemu_ptx_longchunk.so", ["-DSPB_EMULATE_PTX", "-DSPB_LONG_CHUNK_MIN_ENTRIES=2000"])
+    n = 600
+    rng = np.random.default_rng(3)
+    uniform = orc.fr_random_chacha(n, 0xc4)
+    sparse = orc.fr([0 if rng.random() < 0.8 else int(rng.integers(1, 1 << 16)) for _ in range(n)])
+    equal = orc.fr([12345] * n)
+    for sc, lo, hi in ((uniform, 2000, 1 << 30), (sparse, 1, 1999), (equal, 1, 1 << 30)):
+        want = oracle_affine(orc, sc, points[:n])
+        for precomp in (0, 1):
+            got, M, _ = he_msm(he, sc, points[:n], c=10, L=96, precomp=precomp)
+            assert np.array_equal(got, want)
+            assert lo <= M <= hi, M
