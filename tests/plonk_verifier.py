@@ -46,9 +46,11 @@ def lagrange_evals(k, x, rows):
     return out
 
 
-def verify(cs, k, vk_digest, fixed_commitments, sigma_commitments, instances, proof, tau, transcript_read=EvmTranscriptRead):
+def verify(cs, k, vk_digest, fixed_commitments, sigma_commitments, instances, proof, tau, transcript_read=EvmTranscriptRead, trace=None):
     """True / raises AssertionError with the failing check. transcript_read: the reading transcript class (Keccak EVM transcript by
-    default, spectre_b200.poseidon.PoseidonTranscriptRead for proofs made over the Poseidon transcript)."""
+    default, spectre_b200.poseidon.PoseidonTranscriptRead for proofs made over the Poseidon transcript). trace: a dict that receives
+    the intermediate values (challenges, x^n, Lagrange terms, the expected quotient evaluation, the opening-set quantities) so that
+    they can be compared with what the reference's verifier contract computes for the same proof."""
     n = 1 << k
     bf = cs.blinding_factors()
     usable = n - (bf + 1)
@@ -119,6 +121,9 @@ def verify(cs, k, vk_digest, fixed_commitments, sigma_commitments, instances, pr
         acc = (acc * y + l0 * (a_p - s_p)) % R
         acc = (acc * y + l_active * (a_p - s_p) % R * (a_p - a_inv)) % R
     expected_h = acc * _inv(xn - 1) % R
+    if trace is not None:
+        trace.update(theta=theta, beta=beta, gamma=gamma, y=y, x=x, x_n=xn, l_0=l0, l_last=l_last, l_blind=l_blind,
+                     quotient_numerator=acc, expected_h=expected_h, instance_evals=dict(inst))
 
     # ---- multi-open: queries in the prover's order, with the verifier's commitments ----
     ec_add, ec_mul = pyref.ec_add, pyref.ec_mul
@@ -143,6 +148,8 @@ def verify(cs, k, vk_digest, fixed_commitments, sigma_commitments, instances, pr
     y2 = T.squeeze_challenge(); v = T.squeeze_challenge()
     h1 = T.read_ec_point()
     u = T.squeeze_challenge()
+    if trace is not None:
+        trace.update(shplonk_y=y2, shplonk_v=v, shplonk_u=u)
     h2 = T.read_ec_point()
     assert T.pos == len(proof), "trailing bytes in proof"
     super_pts = []

@@ -122,6 +122,35 @@ def test_reference_verifier_contract_accepts_the_fixture(orc, kats, path):
     assert plonk_verifier.verify(cs, fx["k"], int(fx["vk_digest"]), vk_points[:4], vk_points[4:], [instances], proof, tau)
 
 
+@pytest.mark.parametrize("path", _fixtures(), ids=lambda p: p.split("_")[-2])
+def test_independent_verifier_agrees_with_the_contract_term_by_term(orc, kats, path):
+    """the independent Python verifier (tests/plonk_verifier.py) -- the check the multi-set / theta-lookup
+    shapes rely on -- is pinned against the reference's verifier contract not only on accept / reject but on its intermediate
+    values: every challenge it derives (theta, beta, gamma, y, x, and SHPLONK's y, v, u), x^n, the Lagrange terms l_0 and l_last,
+    the instance evaluation, the quotient numerator and the expected h(x) are words the contract itself stores while verifying
+    the same proof."""
+    import json
+    from tests import plonk_verifier, yul_harness
+    with open(path) as f:
+        fx = json.load(f)
+    contract = fx.get("contract", "sync_step_verifier")
+    instances = [int(v, 16) for v in fx["instances"]]
+    proof = bytes.fromhex(fx["proof"])
+    vk_points = [(int(x, 16), int(y, 16)) for x, y in fx["vk_points"]]
+    tau = orc.fr_ints(orc.srs_tau().reshape(1, 4))[0]
+    ok, m = yul_harness.run_contract(contract, instances, proof, vk_points, tau, kats)
+    assert ok
+    trace = {}
+    cs = plonk_circuits.aggregation_shape()
+    assert plonk_verifier.verify(cs, fx["k"], int(fx["vk_digest"]), vk_points[:4], vk_points[4:], [instances], proof, tau, trace=trace)
+    for name in ("theta", "beta", "gamma", "y", "x", "shplonk_y", "shplonk_v", "shplonk_u", "x_n", "l_0", "l_last", "quotient_numerator", "expected_h"):
+        assert trace[name] in m.written, "the contract never stores the verifier's %s" % name
+    for q, v in trace["instance_evals"].items():
+        assert v in m.written, "instance evaluation %r" % (q,)
+    # control: a value the contract has no reason to hold is not there by accident
+    assert (trace["theta"] + 1) % plonk.R_MOD not in m.written
+
+
 def test_halo2lib_sync_step_shape_proof_verifies(orc):
     """the multi-column shape of the sync-step circuit, scaled down: 4 gate columns, 2 range-lookup
     columns, the spread lookup, permutation sets of two columns"""
