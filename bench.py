@@ -123,6 +123,14 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def workload_config():
+    """`config` of the JSON line: the WORKLOAD, identical in both arms (--impl ours / reference); how each arm runs it is in
+    `schedule` (ours) / `cpu_baseline.sample` (reference)."""
+    return {"workload": workload_text(), "log_n": LOG_N, "msms_per_step": MSMS_PER_STEP, "scalar_bits": 252,
+            "l2": "GPU arm: scalars rotate over 8 resident sets (256 MiB > 126 MB L2), the 64 MiB basis is reused as in the prover; "
+                  "CPU arm: one scalar set, 96 MiB per MSM streams through the host caches"}
+
+
 def workload_text():
     return ("BN254 G1 MSM 2^20 random points / uniform 252-bit scalars per GPU (BASELINE configs[1]); step = %d such commitments "
             "(one batch); N ranks = every MSM is one N*2^20 MSM sharded by point range" % MSMS_PER_STEP)
@@ -164,8 +172,8 @@ def run_reference(args):
         "impl": "reference", "metric": "bn254_g1_msm_pairs_per_s", "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (4x64-bit Montgomery limbs, CPU)", "data": "synthetic",
-        "config": {"workload": workload_text(), "log_n": LOG_N, "msms_per_step": MSMS_PER_STEP,
-                   "sample": "one of a step's %d MSMs (full 2^20 pairs) per CPU step; value = 2^20 / median step seconds" % MSMS_PER_STEP},
+        "config": workload_config(),
+        "sample": "one of a step's %d MSMs (full 2^20 pairs) per CPU step; value = 2^20 / median step seconds" % MSMS_PER_STEP,
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port",
                          "sample": "one full 2^20-pair MSM per step after a full-size warm-up, median of %d; C restatement of halo2 best_multiexp "
                                    "(oracle/halo2_oracle.c); the Rust reference cannot be built here" % args.steps,
@@ -483,12 +491,11 @@ def main():
         "metric": "bn254_g1_msm_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, INT32 IMAD)",
         "data": "synthetic",
-        "config": {"workload": workload_text(), "log_n": LOG_N, "msms_per_step": MSMS_PER_STEP, "scalar_bits": 252, "window_bits": c, "windows": W,
-                   "precomputed_window_tables": not args.no_tables,
-                   "pipelining": "each step is one spb_msm_batch(_dev) call: three stream lanes overlap one MSM's tail with the next one's sort/accumulate",
-                   "l2": "scalars rotate over 8 resident sets (256 MiB > 126 MB L2); the 64 MiB basis is reused as in the prover",
-                   "collective": "one all_gather of the step's 16 x 96-byte partial sums (NCCL) + one C fold" if world > 1 else "none",
-                   "timing": "wall clock between barrier + cuda synchronize pairs around exactly K steps, max over ranks; per-kernel times are CUDA events on the library's streams"},
+        "config": workload_config(),
+        "schedule": {"window_bits": c, "windows": W, "precomputed_window_tables": not args.no_tables,
+                     "pipelining": "each step is one spb_msm_batch(_dev) call: three stream lanes overlap one MSM's tail with the next one's sort/accumulate",
+                     "collective": "one all_gather of the step's 16 x 96-byte partial sums (NCCL) + one C fold" if world > 1 else "none",
+                     "timing": "wall clock between barrier + cuda synchronize pairs around exactly K steps, max over ranks; per-kernel times are CUDA events on the library's streams"},
         "ms_per_msm": ms_per_step / MSMS_PER_STEP, "single_msm_device_ms": single_ms, "g1_adds_per_s": adds * world * MSMS_PER_STEP / (ms_per_step * 1e-3),
         "stages_ms": stages_pipelined, "stages_ms_unpipelined": stages, "srs_setup_s": setup_s,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": N_PAIRS * 32 * MSMS_PER_STEP, "d2h_bytes_per_step": 96 * MSMS_PER_STEP,
