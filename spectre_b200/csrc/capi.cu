@@ -381,6 +381,7 @@ void spb_domain_free(spb_ctx* ctx, spb_domain* dm) {
 }
 uint32_t spb_domain_extended_k(const spb_domain* d) { return d ? d->extended_k : 0; }
 void spb_domain_constants(const spb_domain* d, spb_fr out[8]) {
+  if (!d || !out) return;
   const Fr* src[8] = {&d->omega, &d->omega_inv, &d->extended_omega, &d->extended_omega_inv, &d->g_coset, &d->g_coset_inv, &d->ifft_divisor, &d->extended_ifft_divisor};
   for (int i = 0; i < 8; i++) memcpy(&out[i], src[i], 32);
 }

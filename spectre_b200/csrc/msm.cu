@@ -240,8 +240,12 @@ static int job_collect(spb_ctx* ctx, int lane, const std::vector<MsmPart>& parts
 extern "C" {
 
 uint64_t spb_last_msm_adds(spb_ctx* ctx) { return ctx ? ctx->last_msm_adds : 0; }
-void spb_last_msm_stage_ms(spb_ctx* ctx, float out[7]) { for (int i = 0; i < 7; i++) out[i] = ctx ? ctx->msm_stage_ms[i] : 0.f; }
-void spb_msm_geometry(size_t n, int tables, uint32_t* c, uint32_t* windows) { MsmGeom g = msm_make_geometry(msm_choose_c(n ? n : 1, tables != 0), tables != 0, 0); *c = g.c; *windows = g.W; }
+void spb_last_msm_stage_ms(spb_ctx* ctx, float out[7]) { if (!out) return; for (int i = 0; i < 7; i++) out[i] = ctx ? ctx->msm_stage_ms[i] : 0.f; }
+void spb_msm_geometry(size_t n, int tables, uint32_t* c, uint32_t* windows) {
+  MsmGeom g = msm_make_geometry(msm_choose_c(n ? n : 1, tables != 0), tables != 0, 0);
+  if (c) *c = g.c;
+  if (windows) *windows = g.W;
+}
 
 // ---- ParamsKZG ---------------------------------------------------------------------------------------------
 static spb_srs* srs_alloc(spb_ctx* ctx, uint32_t k) {

@@ -144,3 +144,21 @@ def test_error_paths_and_threads(libpath):
     [t.start() for t in ts]; [t.join() for t in ts]
     assert all(np.array_equal(r, w) for r, w in zip(results, want))
     be.close()
+
+
+def test_every_entry_point_survives_null_arguments(libpath):
+    """`include/spectre_b200.h`: "nothing aborts or throws". Without a GPU no context exists, but every exported function must
+    still refuse an all-NULL call (null context, null pointers, zero sizes) with an error code or a no-op instead of
+    dereferencing -- each one is called in its own process so a crash is caught (spb_init is skipped: it would probe devices)."""
+    import subprocess
+    import sys
+    out = subprocess.run(["nm", "-D", "--defined-only", libpath], capture_output=True, text=True, check=True).stdout
+    names = sorted(l.split()[-1] for l in out.splitlines() if " T spb_" in l)
+    assert len(names) > 80
+    prog = ("import ctypes,sys; lib=ctypes.CDLL(%r)\n"
+            "for n in sys.argv[1:]:\n"
+            "    f=getattr(lib,n); f.restype=ctypes.c_int64; f(*([ctypes.c_void_p(0)]*16)); print('ok',n,flush=True)\n" % libpath)
+    todo = [n for n in names if n != "spb_init"]
+    p = subprocess.run([sys.executable, "-c", prog] + todo, capture_output=True, text=True, timeout=120)
+    done = [l.split()[1] for l in p.stdout.splitlines() if l.startswith("ok ")]
+    assert p.returncode == 0 and done == todo, "crashed in %s" % (todo[len(done)] if len(done) < len(todo) else p.stderr[-300:])
